@@ -1,0 +1,262 @@
+#include "glb/allreduce.h"
+
+#include <algorithm>
+
+#include "glb/common/utils.h"
+
+namespace glb {
+
+using detail::Range;
+using detail::subRange;
+
+void AllreduceOptions::setInputsRaw(const std::vector<void*>& ptrs, size_t n, size_t elemSize) {
+  elements = n;
+  elementSize = elemSize;
+  in.clear();
+  for (void* p : ptrs) in.push_back(context->createUnboundBuffer(p, n * elemSize));
+}
+
+void AllreduceOptions::setOutputsRaw(const std::vector<void*>& ptrs, size_t n, size_t elemSize) {
+  elements = n;
+  elementSize = elemSize;
+  out.clear();
+  for (void* p : ptrs) out.push_back(context->createUnboundBuffer(p, n * elemSize));
+}
+
+namespace detail {
+
+std::vector<int> factorize(int n) {
+  std::vector<int> f;
+  for (int p = 2; p * p <= n; p++) {
+    while (n % p == 0) {
+      f.push_back(p);
+      n /= p;
+    }
+  }
+  if (n > 1) f.push_back(n);
+  return f;
+}
+
+void ringReduceScatter(const std::shared_ptr<Context>& context, UnboundBuffer* buf, size_t elements,
+                       size_t elementSize, const AllreduceOptions::Func& reduce, size_t maxSegmentSize,
+                       uint64_t slot, std::chrono::milliseconds timeout) {
+  const int P = context->size;
+  const int r = context->rank;
+  if (P == 1 || elements == 0) return;
+  const int right = (r + 1) % P;
+  const int left = (r - 1 + P) % P;
+  char* base = static_cast<char*>(buf->ptr);
+  const Range all{0, elements};
+
+  const size_t maxChunkElems = ceilDiv(elements, static_cast<size_t>(P));
+  const size_t segElems = std::max<size_t>(1, std::min(maxChunkElems, maxSegmentSize / elementSize));
+  const size_t nseg = ceilDiv(maxChunkElems, segElems);
+
+  // Two receive landing zones so the next segment arrives while this one is reduced.
+  std::vector<char> tmpStorage(2 * segElems * elementSize);
+  auto tmp = context->createUnboundBuffer(tmpStorage.data(), tmpStorage.size());
+
+  auto segOf = [&](const Range& chunk, size_t j) {
+    Range s;
+    s.off = chunk.off + std::min(chunk.len, j * segElems);
+    s.len = std::min(segElems, chunk.len - std::min(chunk.len, j * segElems));
+    return s;
+  };
+
+  for (int s = 0; s < P - 1; s++) {
+    const Range sendChunk = subRange(all, P, (r - s + P) % P);
+    const Range recvChunk = subRange(all, P, (r - s - 1 + 2 * P) % P);
+    size_t sendsPosted = 0;
+    auto postRecv = [&](size_t j) {
+      Range seg = segOf(recvChunk, j);
+      tmp->recv(left, slot, (j % 2) * segElems * elementSize, seg.len * elementSize);
+    };
+    postRecv(0);
+    for (size_t j = 0; j < nseg; j++) {
+      if (j + 1 < nseg) postRecv(j + 1);
+      Range sseg = segOf(sendChunk, j);
+      buf->send(right, slot, sseg.off * elementSize, sseg.len * elementSize);
+      sendsPosted++;
+      tmp->waitRecv(timeout);
+      Range rseg = segOf(recvChunk, j);
+      if (rseg.len > 0) {
+        char* dst = base + rseg.off * elementSize;
+        reduce(dst, dst, tmpStorage.data() + (j % 2) * segElems * elementSize, rseg.len);
+      }
+    }
+    for (size_t k = 0; k < sendsPosted; k++) buf->waitSend(timeout);
+  }
+}
+
+}  // namespace detail
+
+namespace {
+
+void ringAllgather(const std::shared_ptr<Context>& context, UnboundBuffer* buf, size_t elements,
+                   size_t elementSize, size_t maxSegmentSize, uint64_t slot, std::chrono::milliseconds timeout) {
+  const int P = context->size;
+  const int r = context->rank;
+  const int right = (r + 1) % P;
+  const int left = (r - 1 + P) % P;
+  const Range all{0, elements};
+  const size_t maxChunkElems = ceilDiv(elements, static_cast<size_t>(P));
+  const size_t segElems = std::max<size_t>(1, std::min(maxChunkElems, maxSegmentSize / elementSize));
+  const size_t nseg = ceilDiv(maxChunkElems, segElems);
+  auto segOf = [&](const Range& chunk, size_t j) {
+    Range s;
+    s.off = chunk.off + std::min(chunk.len, j * segElems);
+    s.len = std::min(segElems, chunk.len - std::min(chunk.len, j * segElems));
+    return s;
+  };
+  // After reduce-scatter rank r owns chunk (r + 1) % P.
+  for (int s = 0; s < P - 1; s++) {
+    const Range sendChunk = subRange(all, P, (r + 1 - s + P) % P);
+    const Range recvChunk = subRange(all, P, (r - s + P) % P);
+    // Receives land straight in the output; post them all, then stream the sends.
+    for (size_t j = 0; j < nseg; j++) {
+      Range seg = segOf(recvChunk, j);
+      buf->recv(left, slot, seg.off * elementSize, seg.len * elementSize);
+    }
+    for (size_t j = 0; j < nseg; j++) {
+      Range seg = segOf(sendChunk, j);
+      buf->send(right, slot, seg.off * elementSize, seg.len * elementSize);
+    }
+    for (size_t j = 0; j < nseg; j++) buf->waitRecv(timeout);
+    for (size_t j = 0; j < nseg; j++) buf->waitSend(timeout);
+  }
+}
+
+void ring(const AllreduceOptions& opts, UnboundBuffer* out0) {
+  const auto slot = Slot::build(kAllreduceSlotPrefix, opts.tag);
+  detail::ringReduceScatter(opts.context, out0, opts.elements, opts.elementSize, opts.reduce,
+                            opts.maxSegmentSize, slot, opts.timeout);
+  ringAllgather(opts.context, out0, opts.elements, opts.elementSize, opts.maxSegmentSize, slot + 1,
+                opts.timeout);
+}
+
+void bcube(const AllreduceOptions& opts, UnboundBuffer* out0) {
+  const auto& context = opts.context;
+  const int P = context->size;
+  const int r = context->rank;
+  const auto slot = Slot::build(kAllreduceSlotPrefix, opts.tag);
+  const size_t es = opts.elementSize;
+  char* base = static_cast<char*>(out0->ptr);
+
+  const std::vector<int> factors = detail::factorize(P);
+  const int K = static_cast<int>(factors.size());
+  // Mixed-radix digits of this rank; stride[i] = product of factors below i.
+  std::vector<int> stride(K), digit(K);
+  {
+    int s = 1;
+    for (int i = 0; i < K; i++) {
+      stride[i] = s;
+      digit[i] = (r / s) % factors[i];
+      s *= factors[i];
+    }
+  }
+  auto peerAt = [&](int i, int d) { return r + (d - digit[i]) * stride[i]; };
+
+  std::vector<Range> blocks(K + 1);
+  blocks[0] = Range{0, opts.elements};
+  std::vector<char> tmpStorage;
+
+  // Reduce-scatter: after step i this rank owns blocks[i + 1].
+  for (int i = 0; i < K; i++) {
+    const int f = factors[i];
+    const Range cur = blocks[i];
+    const Range mine = subRange(cur, f, digit[i]);
+    blocks[i + 1] = mine;
+    tmpStorage.resize(std::max<size_t>(1, static_cast<size_t>(f - 1) * mine.len * es));
+    auto tmp = context->createUnboundBuffer(tmpStorage.data(), tmpStorage.size());
+    int k = 0;
+    for (int d = 0; d < f; d++) {
+      if (d == digit[i]) continue;
+      tmp->recv(peerAt(i, d), slot + i, k * mine.len * es, mine.len * es);
+      k++;
+    }
+    for (int d = 0; d < f; d++) {
+      if (d == digit[i]) continue;
+      const Range theirs = subRange(cur, f, d);
+      out0->send(peerAt(i, d), slot + i, theirs.off * es, theirs.len * es);
+    }
+    // Reduce contributions in arrival order.
+    for (int n = 0; n < f - 1; n++) {
+      int src = -1;
+      tmp->waitRecv(&src, opts.timeout);
+      int d = digit[i] + (src - r) / stride[i];
+      int idx = d < digit[i] ? d : d - 1;
+      if (mine.len > 0) {
+        char* dst = base + mine.off * es;
+        opts.reduce(dst, dst, tmpStorage.data() + idx * mine.len * es, mine.len);
+      }
+    }
+    for (int n = 0; n < f - 1; n++) out0->waitSend(opts.timeout);
+  }
+
+  // Allgather: mirror image, results land directly in the output.
+  for (int i = K - 1; i >= 0; i--) {
+    const int f = factors[i];
+    const Range cur = blocks[i];
+    const Range mine = blocks[i + 1];
+    for (int d = 0; d < f; d++) {
+      if (d == digit[i]) continue;
+      const Range theirs = subRange(cur, f, d);
+      out0->recv(peerAt(i, d), slot + K + i, theirs.off * es, theirs.len * es);
+    }
+    for (int d = 0; d < f; d++) {
+      if (d == digit[i]) continue;
+      out0->send(peerAt(i, d), slot + K + i, mine.off * es, mine.len * es);
+    }
+    for (int n = 0; n < f - 1; n++) out0->waitRecv(opts.timeout);
+    for (int n = 0; n < f - 1; n++) out0->waitSend(opts.timeout);
+  }
+}
+
+}  // namespace
+
+void allreduce(const AllreduceOptions& opts) {
+  const auto& context = opts.context;
+  GLB_ENFORCE(context != nullptr, "allreduce: no context");
+  GLB_ENFORCE(!opts.out.empty(), "allreduce: at least one output is required");
+  GLB_ENFORCE(opts.elementSize > 0, "allreduce: element size not set");
+  GLB_ENFORCE(static_cast<bool>(opts.reduce), "allreduce: reduce function not set");
+  const size_t bytes = opts.elements * opts.elementSize;
+  for (const auto& b : opts.in) GLB_ENFORCE_EQ(b->size, bytes, "allreduce: input size mismatch");
+  for (const auto& b : opts.out) GLB_ENFORCE_EQ(b->size, bytes, "allreduce: output size mismatch");
+  if (opts.elements == 0) return;
+
+  // Local phase 1: fold every input into out[0].
+  UnboundBuffer* out0 = opts.out[0].get();
+  if (!opts.in.empty()) {
+    if (opts.in[0]->ptr != out0->ptr) std::memcpy(out0->ptr, opts.in[0]->ptr, bytes);
+    for (size_t i = 1; i < opts.in.size(); i++) {
+      opts.reduce(out0->ptr, out0->ptr, opts.in[i]->ptr, opts.elements);
+    }
+  } else {
+    // In-place over the outputs: they all hold contributions.
+    for (size_t i = 1; i < opts.out.size(); i++) {
+      opts.reduce(out0->ptr, out0->ptr, opts.out[i]->ptr, opts.elements);
+    }
+  }
+
+  if (context->size > 1) {
+    switch (opts.algorithm) {
+      case AllreduceOptions::UNSPECIFIED:
+      case AllreduceOptions::RING:
+        ring(opts, out0);
+        break;
+      case AllreduceOptions::BCUBE:
+        bcube(opts, out0);
+        break;
+      default:
+        GLB_THROW_INVALID_OPERATION_EXCEPTION("allreduce: unknown algorithm ", opts.algorithm);
+    }
+  }
+
+  // Local phase 2: replicate to the remaining outputs.
+  for (size_t i = 1; i < opts.out.size(); i++) {
+    if (opts.out[i]->ptr != out0->ptr) std::memcpy(opts.out[i]->ptr, out0->ptr, bytes);
+  }
+}
+
+}  // namespace glb

@@ -1,0 +1,5 @@
+#include <pybind11/pybind11.h>
+namespace py = pybind11;
+namespace glb_py {
+void registerExtras(py::module_& m) {}
+}  // namespace glb_py

@@ -1,0 +1,221 @@
+// tcp::Pair — one TCP connection to one peer, multiplexing every slot.
+//
+// Wire protocol (little-endian, 48-byte header followed by `nbytes` of payload):
+//
+//   SEND_UNBOUND  eager message for an UnboundBuffer recv posted on `slot`. If no
+//                 matching recv is posted yet the payload is parked in the
+//                 context's unexpected queue and copied when the recv arrives —
+//                 so there is no sender/receiver handshake on the critical path
+//                 (the reference needs NOTIFY_SEND_READY / NOTIFY_RECV_READY round
+//                 trips, pair.cc:913-975), and recv-from-any is a purely local
+//                 match on the receiver.
+//   SEND_BOUND    one-sided write into the peer's bound recv Buffer registered
+//                 under `slot`, at `roffset`. Arrivals that precede registration
+//                 are parked and applied by createRecvBuffer().
+//   PUT / GET_REQ / GET_RESP
+//                 software one-sided access to a region exported through
+//                 UnboundBuffer::getRemoteKey() — served entirely by the remote
+//                 I/O thread, the remote user thread is not involved.
+//
+// Threading: all pair state is guarded by `mu_`. In async mode the device loop
+// thread performs reads and flushes queued writes; writes are attempted inline
+// from the calling thread first. In sync mode the socket is detached from epoll
+// and the waiting user thread drives reads itself (optionally busy-polling).
+// Parity: gloo/transport/tcp/pair.{h,cc}.
+#pragma once
+
+#include <atomic>
+#include <condition_variable>
+#include <deque>
+#include <exception>
+#include <functional>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <unordered_map>
+#include <vector>
+
+#include "glb/common/memory.h"
+#include "glb/transport/pair.h"
+#include "glb/transport/tcp/address.h"
+#include "glb/transport/tcp/device.h"
+#include "glb/transport/tcp/loop.h"
+
+namespace glb {
+namespace transport {
+namespace tcp {
+
+class Buffer;
+class Context;
+class UnboundBuffer;
+
+struct WireHeader {
+  static constexpr uint32_t kMagic = 0x4d424c47;  // "GLBM"
+  uint32_t magic = kMagic;
+  uint16_t opcode = 0;
+  uint16_t flags = 0;
+  uint64_t slot = 0;     // unbound/bound slot, or request id for GET_*
+  uint64_t nbytes = 0;   // payload bytes that follow
+  uint64_t roffset = 0;  // destination offset (bound / put) or source offset (get)
+  uint64_t aux = 0;      // region id for PUT / GET_REQ
+  uint64_t length = 0;   // GET_REQ: bytes requested
+};
+static_assert(sizeof(WireHeader) == 48, "wire header must be 48 bytes");
+
+enum Opcode : uint16_t {
+  OP_SEND_UNBOUND = 1,
+  OP_SEND_BOUND = 2,
+  OP_PUT = 3,
+  OP_GET_REQ = 4,
+  OP_GET_RESP = 5,
+};
+
+class Pair : public ::glb::transport::Pair, private Handler {
+ public:
+  enum State { INITIALIZING = 1, CONNECTING = 2, CONNECTED = 3, CLOSED = 4 };
+
+  Pair(Context* context, Device* device, int selfRank, int peerRank, std::chrono::milliseconds timeout,
+       bool lazy);
+  ~Pair() override;
+
+  const Address& address() const override { return self_; }
+  void connect(const std::vector<char>& bytes) override;
+  void close() override;
+  bool isConnected() override;
+  void setSync(bool sync, bool busyPoll) override;
+
+  std::unique_ptr<::glb::transport::Buffer> createSendBuffer(int slot, void* ptr, size_t size) override;
+  std::unique_ptr<::glb::transport::Buffer> createRecvBuffer(int slot, void* ptr, size_t size) override;
+
+  void send(::glb::transport::UnboundBuffer* buf, uint64_t tag, size_t offset, size_t nbytes) override;
+  void recv(::glb::transport::UnboundBuffer* buf, uint64_t tag, size_t offset, size_t nbytes) override;
+
+  int peerRank() const { return peerRank_; }
+  std::chrono::milliseconds timeout() const { return timeout_; }
+  bool isSync() const { return sync_; }
+
+  // Dial / wait for the inbound connection if that has not happened yet (lazy mode).
+  void ensureConnected();
+
+  // ---- used by Buffer / UnboundBuffer / Context -------------------------------
+  void sendBound(Buffer* buf, size_t offset, size_t length, size_t roffset);
+  void sendUnbound(UnboundBuffer* buf, uint64_t slot, size_t offset, size_t nbytes);
+  void sendPut(UnboundBuffer* buf, uint64_t regionId, size_t offset, size_t roffset, size_t nbytes);
+  void sendGetRequest(uint64_t requestId, uint64_t regionId, size_t roffset, size_t nbytes);
+  void unregisterBuffer(Buffer* buf);
+  // Drop queued sends that reference `buf` (it is being destroyed).
+  void forgetUnbound(UnboundBuffer* buf);
+
+  // Poison this pair: all pending and future operations throw IoException(msg).
+  void signalExceptionExternal(const std::string& msg);
+  // In sync mode: drive the socket from the calling thread until pred() holds.
+  // `lock` must hold mu() on entry and holds it on return.
+  void syncWait(std::unique_lock<std::mutex>& lock, const std::function<bool()>& pred,
+                std::chrono::milliseconds timeout, const char* what);
+  std::mutex& mu() { return mu_; }
+  void throwIfException();  // requires mu_
+
+ protected:
+  // I/O primitives; the TLS pair overrides these.
+  virtual ssize_t ioRecv(void* buf, size_t len);
+  virtual ssize_t ioSend(const struct iovec* iov, int iovcnt);
+  virtual void ioHandshake(bool isInitiator) {}
+  virtual void ioShutdown() {}
+
+  int fd() const { return fd_; }
+
+ private:
+  struct TxOp {
+    WireHeader hdr;
+    const char* data = nullptr;
+    size_t nbytes = 0;
+    size_t sent = 0;
+    bool hasUbuf = false;
+    bool notify = true;
+    WeakAnchor<UnboundBuffer> ubuf;
+    UnboundBuffer* ubufRaw = nullptr;
+    Buffer* bbuf = nullptr;
+  };
+
+  enum RxKind {
+    RX_NONE,
+    RX_UNBOUND_DIRECT,
+    RX_UNBOUND_UNEXPECTED,
+    RX_BOUND_DIRECT,
+    RX_BOUND_UNEXPECTED,
+    RX_PUT,
+    RX_GET_RESP,
+    RX_DISCARD
+  };
+  struct Rx {
+    WireHeader hdr;
+    size_t hdrRead = 0;
+    size_t payloadRead = 0;
+    RxKind kind = RX_NONE;
+    char* dst = nullptr;
+    Lease<UnboundBuffer> ubuf;
+    Buffer* bbuf = nullptr;
+    std::vector<char> stash;
+    void reset() {
+      hdrRead = 0;
+      payloadRead = 0;
+      kind = RX_NONE;
+      dst = nullptr;
+      ubuf.release();
+      bbuf = nullptr;
+      std::vector<char>().swap(stash);
+    }
+  };
+  struct ParkedBound {
+    size_t roffset;
+    std::vector<char> data;
+  };
+
+  void handleEvents(int events) override;
+
+  void dial();                                     // initiator side
+  void attachSocket(Socket sock, bool initiator);  // both sides
+  void waitUntilConnected(std::unique_lock<std::mutex>& lock);
+
+  void enqueue(TxOp&& op);      // requires mu_
+  bool tryWrite(TxOp& op);      // requires mu_; true when fully written
+  void completeTx(TxOp& op);    // requires mu_
+  void flushTx();               // requires mu_
+  void readLoop(size_t budget); // requires mu_
+  void beginMessage();          // requires mu_
+  void finishMessage();         // requires mu_
+  void signalException(const std::string& msg);  // requires mu_
+  void armEvents(bool wantWrite);                // requires mu_
+
+  Context* const context_;
+  Device* const device_;
+  const int selfRank_;
+  const int peerRank_;
+  const std::chrono::milliseconds timeout_;
+  const bool lazy_;
+  Loop* loop_;
+
+  std::mutex dialMu_;
+  std::mutex mu_;
+  std::condition_variable cv_;
+  State state_ = INITIALIZING;
+  bool sync_ = false;
+  bool busyPoll_ = false;
+  bool wantWrite_ = false;
+  bool expecting_ = false;
+  int fd_ = -1;
+  Address self_;
+  Address peer_;
+  bool havePeer_ = false;
+  std::string exMsg_;
+  bool failed_ = false;
+
+  std::deque<TxOp> tx_;
+  Rx rx_;
+  std::unordered_map<int, Buffer*> recvBuffers_;
+  std::unordered_map<int, std::deque<ParkedBound>> parkedBound_;
+};
+
+}  // namespace tcp
+}  // namespace transport
+}  // namespace glb

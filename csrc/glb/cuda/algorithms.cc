@@ -1,0 +1,297 @@
+#include "glb/cuda/algorithms.h"
+
+#include <map>
+#include <mutex>
+
+#include "glb/allreduce.h"
+#include "glb/broadcast.h"
+#include "glb/common/utils.h"
+#include "glb/cuda/kernels.h"
+
+namespace glb {
+namespace cuda {
+
+namespace {
+std::mutex gPcMu;
+std::map<std::pair<Context*, int>, std::shared_ptr<PeerContext>> gPeerContexts;
+
+// Map the reference's algorithm names to what actually runs. By default the named
+// classes resolve per message size (AUTO); literal schedules are opt-in.
+AllreduceAlgo effectiveAlgo(AllreduceAlgo requested) {
+  switch (requested) {
+    case AllreduceAlgo::RING:
+    case AllreduceAlgo::RING_CHUNKED:
+    case AllreduceAlgo::HALVING_DOUBLING:
+    case AllreduceAlgo::BCUBE:
+      return envFlag("CUDA_LITERAL_SCHEDULES", false) ? requested : AllreduceAlgo::AUTO;
+    default:
+      return requested;
+  }
+}
+
+std::vector<CudaStream> makeStreams(const std::vector<void*>& ptrs, const std::vector<cudaStream_t>& user) {
+  std::vector<CudaStream> out;
+  if (!user.empty()) GLB_ENFORCE_EQ(user.size(), ptrs.size(), "need one stream per pointer");
+  for (size_t i = 0; i < ptrs.size(); i++) {
+    int dev = deviceForPointer(ptrs[i]);
+    GLB_ENFORCE_GE(dev, 0, "pointer ", i, " is not a CUDA device pointer");
+    if (user.empty()) {
+      out.emplace_back(dev);
+    } else {
+      out.emplace_back(dev, user[i]);
+    }
+  }
+  return out;
+}
+
+// All ranks decide together whether the peer path is usable.
+}  // namespace
+
+std::vector<CudaStream> makeStreamsFor(const std::vector<void*>& ptrs, const std::vector<cudaStream_t>& user) {
+  return makeStreams(ptrs, user);
+}
+
+namespace {
+bool peerPathUsable(const std::shared_ptr<Context>& ctx, Workspace ws) {
+  if (ws == Workspace::HOST) return false;
+  return deviceCount() > 0 && !envFlag("CUDA_FORCE_HOST_WORKSPACE", false);
+}
+}  // namespace
+
+std::shared_ptr<PeerContext> peerContextFor(const std::shared_ptr<Context>& ctx, int device) {
+  std::unique_lock<std::mutex> g(gPcMu);
+  auto key = std::make_pair(ctx.get(), device);
+  auto it = gPeerContexts.find(key);
+  if (it != gPeerContexts.end()) return it->second;
+  g.unlock();
+  // Construction is collective and may block on peers: do it outside the lock.
+  auto pc = std::make_shared<PeerContext>(ctx, device);
+  g.lock();
+  gPeerContexts[key] = pc;
+  return pc;
+}
+
+void releasePeerContexts(const std::shared_ptr<Context>& ctx) {
+  std::lock_guard<std::mutex> g(gPcMu);
+  for (auto it = gPeerContexts.begin(); it != gPeerContexts.end();) {
+    it = (it->first.first == ctx.get()) ? gPeerContexts.erase(it) : std::next(it);
+  }
+}
+
+// ---- allreduce ---------------------------------------------------------------------------
+
+struct CudaAllreduceCore::Literal {};
+
+CudaAllreduceCore::CudaAllreduceCore(std::shared_ptr<Context> ctx, std::vector<void*> ptrs, size_t count,
+                                     DataType dt, ReduceOp op, std::vector<cudaStream_t> streams,
+                                     AllreduceAlgo algo, Workspace ws)
+    : ctx_(std::move(ctx)),
+      ptrs_(std::move(ptrs)),
+      count_(count),
+      dt_(dt),
+      op_(op),
+      algo_(effectiveAlgo(algo)),
+      syncOutputs_(streams.empty()) {
+  GLB_ENFORCE(!ptrs_.empty(), "need at least one pointer");
+  streams_ = makeStreams(ptrs_, streams);
+  const int dev0 = streams_[0].getDeviceID();
+  if (ctx_->size > 1 && peerPathUsable(ctx_, ws)) {
+    auto pc = peerContextFor(ctx_, dev0);
+    if (pc->peerAccessEverywhere()) {
+      pc_ = pc;
+      reg_ = pc_->registerBuffer(ptrs_[0], count_ * elementSize(dt_));
+    }
+  }
+  if (ctx_->size > 1 && !pc_) {
+    GLB_CUDA_CHECK(cudaMallocHost(&hostScratch_, std::max<size_t>(count_ * elementSize(dt_), 16)));
+  }
+}
+
+CudaAllreduceCore::~CudaAllreduceCore() {
+  if (hostScratch_ != nullptr) cudaFreeHost(hostScratch_);
+}
+
+AllreduceAlgo CudaAllreduceCore::resolvedAlgo() const {
+  if (!pc_) return AllreduceAlgo::AUTO;
+  if (algo_ != AllreduceAlgo::AUTO) return algo_;
+  return chooseAllreduce(*pc_, count_ * elementSize(dt_), dt_, op_, true, reg_ && reg_->mc != nullptr);
+}
+
+void CudaAllreduceCore::run() {
+  if (count_ == 0) return;
+  CudaStream& s0 = streams_[0];
+  const size_t bytes = count_ * elementSize(dt_);
+  DeviceGuard g(s0.getDeviceID());
+
+  // 1. fold the local pointers into ptrs_[0]
+  if (ptrs_.size() > 1) {
+    for (size_t i = 1; i < streams_.size(); i++) {
+      streams_[i].record();
+      s0.waitOn(streams_[i]);
+    }
+    std::vector<const void*> srcs(ptrs_.begin(), ptrs_.end());
+    launchLocalReduceMany(ptrs_[0], srcs.data(), static_cast<int>(srcs.size()), count_, dt_, op_, *s0);
+  }
+
+  // 2. across ranks
+  if (ctx_->size > 1) {
+    if (pc_) {
+      allreduce(*pc_, *reg_, 0, count_, dt_, op_, algo_, *s0);
+    } else {
+      // Host workspace: D2H, host collective over the transport, H2D.
+      s0.copyAsync(hostScratch_, ptrs_[0], bytes);
+      s0.wait();
+      AllreduceOptions opts(ctx_);
+      opts.setOutputsRaw({hostScratch_}, count_, elementSize(dt_));
+      ReduceFn fn = getReduceFn(dt_, op_);
+      opts.setReduceFunction([fn](void* c, const void* a, const void* b, size_t n) { fn(c, a, b, n); });
+      opts.setTag(0x00CDA000u);
+      glb::allreduce(opts);
+      s0.copyAsync(ptrs_[0], hostScratch_, bytes);
+    }
+  }
+
+  // 3. replicate to the other local pointers
+  if (ptrs_.size() > 1) {
+    std::vector<void*> dsts(ptrs_.begin() + 1, ptrs_.end());
+    launchLocalBroadcast(dsts.data(), static_cast<int>(dsts.size()), ptrs_[0], bytes, *s0);
+    s0.record();
+    for (size_t i = 1; i < streams_.size(); i++) streams_[i].waitOn(s0);
+  }
+  if (syncOutputs_) {
+    s0.record();
+    s0.wait();
+  }
+}
+
+// ---- broadcast --------------------------------------------------------------------------------
+
+CudaBroadcastCore::CudaBroadcastCore(std::shared_ptr<Context> ctx, std::vector<void*> ptrs, size_t count,
+                                     DataType dt, int rootRank, int rootPointerRank,
+                                     std::vector<cudaStream_t> streams, Workspace ws)
+    : ctx_(std::move(ctx)),
+      ptrs_(std::move(ptrs)),
+      count_(count),
+      dt_(dt),
+      root_(rootRank),
+      rootPtr_(rootPointerRank),
+      syncOutputs_(streams.empty()) {
+  GLB_ENFORCE(!ptrs_.empty(), "need at least one pointer");
+  GLB_ENFORCE(root_ >= 0 && root_ < ctx_->size, "invalid root rank ", root_);
+  GLB_ENFORCE(rootPtr_ >= 0 && rootPtr_ < static_cast<int>(ptrs_.size()), "invalid root pointer rank");
+  streams_ = makeStreams(ptrs_, streams);
+  // The pointer that takes part in the cross-rank exchange: the root's source
+  // pointer on the root, ptrs[0] elsewhere.
+  const int idx = ctx_->rank == root_ ? rootPtr_ : 0;
+  if (ctx_->size > 1 && peerPathUsable(ctx_, ws)) {
+    auto pc = peerContextFor(ctx_, streams_[idx].getDeviceID());
+    if (pc->peerAccessEverywhere()) {
+      pc_ = pc;
+      reg_ = pc_->registerBuffer(ptrs_[idx], count_ * elementSize(dt_));
+    }
+  }
+  if (ctx_->size > 1 && !pc_) {
+    GLB_CUDA_CHECK(cudaMallocHost(&hostScratch_, std::max<size_t>(count_ * elementSize(dt_), 16)));
+  }
+}
+
+CudaBroadcastCore::~CudaBroadcastCore() {
+  if (hostScratch_ != nullptr) cudaFreeHost(hostScratch_);
+}
+
+void CudaBroadcastCore::run() {
+  if (count_ == 0) return;
+  const size_t bytes = count_ * elementSize(dt_);
+  const bool isRoot = ctx_->rank == root_;
+  const int idx = isRoot ? rootPtr_ : 0;
+  CudaStream& s = streams_[idx];
+  DeviceGuard g(s.getDeviceID());
+  if (ctx_->size > 1) {
+    if (pc_) {
+      broadcast(*pc_, *reg_, 0, bytes, root_, *s);
+    } else {
+      if (isRoot) {
+        s.copyAsync(hostScratch_, ptrs_[idx], bytes);
+        s.wait();
+      }
+      BroadcastOptions opts(ctx_);
+      opts.setOutputRaw(hostScratch_, bytes);
+      opts.setRoot(root_);
+      opts.setTag(0x00CDA001u);
+      glb::broadcast(opts);
+      if (!isRoot) s.copyAsync(ptrs_[idx], hostScratch_, bytes);
+    }
+  }
+  // Local fan-out to the remaining pointers.
+  if (ptrs_.size() > 1) {
+    std::vector<void*> dsts;
+    for (size_t i = 0; i < ptrs_.size(); i++) {
+      if (static_cast<int>(i) != idx) dsts.push_back(ptrs_[i]);
+    }
+    for (size_t i = 0; i < streams_.size(); i++) {
+      if (static_cast<int>(i) == idx) continue;
+      streams_[i].record();
+      s.waitOn(streams_[i]);
+    }
+    launchLocalBroadcast(dsts.data(), static_cast<int>(dsts.size()), ptrs_[idx], bytes, *s);
+    s.record();
+    for (size_t i = 0; i < streams_.size(); i++) {
+      if (static_cast<int>(i) != idx) streams_[i].waitOn(s);
+    }
+  }
+  if (syncOutputs_) {
+    s.record();
+    s.wait();
+  }
+}
+
+}  // namespace cuda
+
+// ---- local allreduce -----------------------------------------------------------------------
+
+template <typename T>
+CudaAllreduceLocal<T>::CudaAllreduceLocal(const std::shared_ptr<Context>& context, const std::vector<T*>& ptrs,
+                                          const size_t count, const std::vector<cudaStream_t>& streams)
+    : Algorithm(context), ptrs_(cuda::eraseType(ptrs)), count_(count), syncOutputs_(streams.empty()) {
+  streams_ = cuda::makeStreamsFor(ptrs_, streams);
+}
+
+template <typename T>
+void CudaAllreduceLocal<T>::run() {
+  if (count_ == 0 || ptrs_.size() < 2) return;
+  cuda::CudaStream& s0 = streams_[0];
+  cuda::DeviceGuard g(s0.getDeviceID());
+  for (size_t i = 1; i < streams_.size(); i++) {
+    streams_[i].record();
+    s0.waitOn(streams_[i]);
+  }
+  std::vector<const void*> srcs(ptrs_.begin(), ptrs_.end());
+  cuda::launchLocalReduceMany(ptrs_[0], srcs.data(), static_cast<int>(srcs.size()), count_, DataTypeOf<T>::value,
+                        ReduceOp::SUM, *s0);
+  std::vector<void*> dsts(ptrs_.begin() + 1, ptrs_.end());
+  cuda::launchLocalBroadcast(dsts.data(), static_cast<int>(dsts.size()), ptrs_[0], count_ * sizeof(T), *s0);
+  s0.record();
+  for (size_t i = 1; i < streams_.size(); i++) streams_[i].waitOn(s0);
+  if (syncOutputs_) s0.wait();
+}
+
+template <typename T>
+void CudaReductionFunction<T>::call(T* dst, const T* src, size_t n, cudaStream_t stream) const {
+  cuda::launchLocalReduce(dst, src, n, DataTypeOf<T>::value, type_, stream);
+}
+
+#define GLB_INSTANTIATE(T)                    \
+  template class CudaAllreduceLocal<T>;       \
+  template class CudaReductionFunction<T>;
+GLB_INSTANTIATE(int8_t)
+GLB_INSTANTIATE(uint8_t)
+GLB_INSTANTIATE(int32_t)
+GLB_INSTANTIATE(int64_t)
+GLB_INSTANTIATE(uint64_t)
+GLB_INSTANTIATE(float)
+GLB_INSTANTIATE(double)
+GLB_INSTANTIATE(float16)
+GLB_INSTANTIATE(bfloat16)
+#undef GLB_INSTANTIATE
+
+}  // namespace glb

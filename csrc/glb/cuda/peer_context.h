@@ -1,0 +1,147 @@
+// PeerContext — the NVLink/NVSwitch peer-memory data plane ("nvl" transport).
+//
+// Built on top of a connected glb::Context (the TCP mesh is the control plane):
+//   1. topology discovery: every rank publishes {hostname, pid, CUDA device,
+//      UUID, PCI bus id, SM count, VMM / multicast capability}; from that each
+//      rank derives same-host / same-process / same-device groups and the P2P
+//      reachability matrix (the reference only counts same-hostname ranks,
+//      transport/context.cc:45-57, and knows PCI distances, common/linux.cc).
+//   2. a symmetric pool per rank (signal pad + staging area), mapped into every
+//      peer: cuMemCreate + POSIX-fd export passed over unix sockets (SCM_RIGHTS)
+//      when the driver supports it — which also lets the pool be bound to an
+//      NVLS multicast object — else cudaMalloc + cudaIpc handles. Ranks living in
+//      the same process (threads-as-ranks tests) share pointers directly.
+//   3. registration of user buffers (registerBuffer) and symmetric allocation
+//      (allocSymmetric) so collectives can run zero-copy on them.
+//
+// This is the natural extension of the reference's RemoteKey/put/get surface
+// (transport/unbound_buffer.h:128-152, ibverbs only) to GPU peer memory; nothing
+// like it exists in the reference.
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <map>
+#include <memory>
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "glb/context.h"
+#include "glb/cuda/cuda_util.h"
+#include "glb/cuda/comm_types.h"
+
+namespace glb {
+namespace cuda {
+
+struct DeviceInfo {
+  char hostname[64];
+  int32_t pid;
+  int32_t device;
+  uint8_t uuid[16];
+  char pciBusId[24];
+  int32_t smCount;
+  int32_t ccMajor;
+  int32_t ccMinor;
+  int32_t vmmSupported;
+  int32_t multicastSupported;
+  uint64_t totalMem;
+  char fdSocket[64];  // abstract unix socket that accepts SCM_RIGHTS messages for this rank
+};
+
+struct PeerOptions {
+  size_t stageBytes = 64ull << 20;  // staging area for unregistered buffers (per rank)
+  bool useVmm = true;               // try cuMem + fd passing before cudaIpc
+  bool useNvls = true;              // bind symmetric memory to a multicast object when possible
+};
+
+// A buffer that every rank can address: peer[r] is rank r's copy as mapped here.
+struct PeerBuffer {
+  void* local = nullptr;
+  size_t bytes = 0;
+  void* peer[kMaxRanks] = {nullptr};
+  void* mc = nullptr;        // multicast (NVLS) alias, or nullptr
+  bool vectorOk = false;     // every rank's pointer is 16-byte aligned
+  PeerPtrs ptrs() const {
+    PeerPtrs p;
+    for (int i = 0; i < kMaxRanks; i++) p.p[i] = peer[i];
+    return p;
+  }
+  PeerPtrs ptrsAt(size_t byteOffset) const {
+    PeerPtrs p;
+    for (int i = 0; i < kMaxRanks; i++) p.p[i] = peer[i] ? static_cast<char*>(peer[i]) + byteOffset : nullptr;
+    return p;
+  }
+  ~PeerBuffer();
+
+ private:
+  friend class PeerContext;
+  struct Impl;
+  std::shared_ptr<Impl> impl_;
+};
+
+class FdChannel;
+
+class PeerContext : public std::enable_shared_from_this<PeerContext> {
+ public:
+  PeerContext(std::shared_ptr<Context> context, int device, PeerOptions opts = PeerOptions());
+  ~PeerContext();
+
+  const int rank;
+  const int size;
+  const int device;
+
+  const std::shared_ptr<Context>& context() const { return context_; }
+  const std::vector<DeviceInfo>& topology() const { return infos_; }
+  // P2P works between every pair of ranks (single host, peer access everywhere).
+  bool peerAccessEverywhere() const { return peerOk_; }
+  bool usingVmm() const { return vmm_; }
+  bool nvlsAvailable() const { return pool_ && pool_->mc != nullptr; }
+  int ranksOnMyDevice() const { return ranksOnMyDevice_; }
+  // Largest grid a collective kernel may use so that all ranks' CTAs are co-resident.
+  int maxBlocks() const { return maxBlocks_; }
+  std::string describe() const;
+
+  // ---- collective calls: every rank, same order ------------------------------------
+  std::shared_ptr<PeerBuffer> allocSymmetric(size_t bytes);
+  std::shared_ptr<PeerBuffer> registerBuffer(void* ptr, size_t bytes);
+  void hostBarrier();
+
+  // ---- kernel arguments --------------------------------------------------------------
+  const CommArgs& comm() const { return comm_; }
+  // Staging area (after the signal pad) of every rank's pool, and its size.
+  PeerPtrs stagePtrs(size_t byteOffset = 0) const;
+  void* stageMc(size_t byteOffset = 0) const;
+  size_t stageBytes() const { return stageBytes_; }
+
+ private:
+  uint32_t nextTag() { return 0x7C000000u + (tagSeq_++ & 0xffffffu); }
+  void exchangeTopology();
+  template <typename T>
+  std::vector<T> allgatherStruct(const T& mine);
+  std::shared_ptr<PeerBuffer> allocVmm(size_t bytes, bool wantMc);
+  std::shared_ptr<PeerBuffer> allocIpc(size_t bytes);
+  std::shared_ptr<PeerBuffer> shareIpc(void* ptr, size_t bytes, bool ownsAllocation);
+  bool sameProcess(int r) const;
+
+  std::shared_ptr<Context> context_;
+  PeerOptions opts_;
+  std::vector<DeviceInfo> infos_;
+  bool peerOk_ = false;
+  bool vmm_ = false;
+  bool nvlsPossible_ = false;
+  int ranksOnMyDevice_ = 1;
+  int maxBlocks_ = 1;
+  uint32_t tagSeq_ = 0;
+  std::unique_ptr<FdChannel> fdChannel_;
+  std::shared_ptr<PeerBuffer> pool_;
+  size_t stageOffset_ = 0;
+  size_t stageBytes_ = 0;
+  CommArgs comm_;
+  // cudaIpc mappings are per (peer, allocation): cache them, opening twice is an error.
+  std::mutex ipcMu_;
+  std::map<std::pair<int, std::string>, void*> ipcCache_;
+};
+
+}  // namespace cuda
+}  // namespace glb

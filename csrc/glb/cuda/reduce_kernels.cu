@@ -1,0 +1,162 @@
+// Local (single-device-visible) element-wise kernels:
+//   localReduce       dst[i] = dst[i] (op) src[i]   — the building block behind
+//                     CudaReductionFunction; 128-bit loads/stores, fp32 accumulate
+//                     for fp16/bf16, size_t counts, grid sized to the SM count.
+//   localReduceMany   dst = reduce(srcs[0..n)) in one pass (multi-pointer local reduce:
+//                     srcs may live on peer devices of the same process).
+//   localBroadcast    copy src to n destinations in one pass.
+//   fill / spin       test helpers (pattern fill; delay kernel that surfaces
+//                     missing stream synchronisation).
+// Parity: gloo/cuda.cu:274-407 (K1-K5), cuda_private.cu:38-61 (K6),
+// test/cuda_base_test.cu:15-27 (K7) — rewritten, not ported: the reference kernels
+// are scalar, int-indexed, one element per thread.
+#include "glb/cuda/device_common.cuh"
+#include "glb/cuda/kernels.h"
+
+namespace glb {
+namespace cuda {
+
+namespace {
+
+constexpr int kLocalThreads = 256;
+constexpr int kMaxSrcs = 16;
+
+struct SrcPtrs {
+  const void* p[kMaxSrcs];
+};
+struct DstPtrs {
+  void* p[kMaxSrcs];
+};
+
+template <typename T>
+__global__ void __launch_bounds__(kLocalThreads)
+localReduceManyKernel(T* __restrict__ dst, SrcPtrs srcs, int nsrc, size_t count, DevOp op, bool vectorOk) {
+  using PT = PackTraits<T>;
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t nvec = vectorOk ? count / PT::kElems : 0;
+  for (size_t v = tid; v < nvec; v += nthreads) {
+    typename PT::AccPack acc = PT::widen(ld128_stream(static_cast<const char*>(srcs.p[0]) + v * 16));
+    for (int s = 1; s < nsrc; s++) PT::combine(acc, ld128_stream(static_cast<const char*>(srcs.p[s]) + v * 16), op);
+    st128(reinterpret_cast<char*>(dst) + v * 16, PT::narrow(acc));
+  }
+  for (size_t i = nvec * PT::kElems + tid; i < count; i += nthreads) {
+    T acc = static_cast<const T*>(srcs.p[0])[i];
+    for (int s = 1; s < nsrc; s++) acc = PT::combineOne(acc, static_cast<const T*>(srcs.p[s])[i], op);
+    dst[i] = acc;
+  }
+}
+
+__global__ void __launch_bounds__(kLocalThreads)
+localBroadcastKernel(DstPtrs dsts, int ndst, const char* __restrict__ src, size_t bytes, bool vectorOk) {
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t nvec = vectorOk ? bytes / 16 : 0;
+  for (size_t v = tid; v < nvec; v += nthreads) {
+    const Pack16 p = ld128_stream(src + v * 16);
+    for (int d = 0; d < ndst; d++) st128_stream(static_cast<char*>(dsts.p[d]) + v * 16, p);
+  }
+  for (size_t i = nvec * 16 + tid; i < bytes; i += nthreads) {
+    const char c = src[i];
+    for (int d = 0; d < ndst; d++) static_cast<char*>(dsts.p[d])[i] = c;
+  }
+}
+
+template <typename T>
+__global__ void fillKernel(T* dst, size_t count, double start, double stride) {
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
+  for (size_t i = tid; i < count; i += nthreads) {
+    const double v = start + stride * static_cast<double>(i);
+    if constexpr (std::is_same<T, __half>::value) {
+      dst[i] = __float2half_rn(static_cast<float>(v));
+    } else if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+      dst[i] = __float2bfloat16_rn(static_cast<float>(v));
+    } else {
+      dst[i] = static_cast<T>(v);
+    }
+  }
+}
+
+__global__ void spinKernel(long long cycles) {
+  const long long start = clock64();
+  while (clock64() - start < cycles) {
+  }
+}
+
+int gridFor(size_t items, int threads) {
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  size_t want = (items + threads - 1) / threads;
+  size_t cap = static_cast<size_t>(sms) * 4;
+  return static_cast<int>(want < 1 ? 1 : (want > cap ? cap : want));
+}
+
+template <typename F>
+void dispatchType(DataType dt, F&& f) {
+  switch (dt) {
+    case DataType::INT8: f(int8_t{}); break;
+    case DataType::UINT8: f(uint8_t{}); break;
+    case DataType::INT16: f(int16_t{}); break;
+    case DataType::INT32: f(int32_t{}); break;
+    case DataType::UINT32: f(uint32_t{}); break;
+    case DataType::INT64: f((long long){}); break;
+    case DataType::UINT64: f((unsigned long long){}); break;
+    case DataType::FLOAT32: f(float{}); break;
+    case DataType::FLOAT64: f(double{}); break;
+    case DataType::FLOAT16: f(__half{}); break;
+    case DataType::BFLOAT16: f(__nv_bfloat16{}); break;
+  }
+}
+
+bool aligned16(const void* p) { return reinterpret_cast<uintptr_t>(p) % 16 == 0; }
+
+}  // namespace
+
+void launchLocalReduceMany(void* dst, const void* const* srcs, int nsrc, size_t count, DataType dt, ReduceOp op,
+                           cudaStream_t stream) {
+  if (count == 0 || nsrc == 0) return;
+  SrcPtrs sp;
+  bool vectorOk = aligned16(dst);
+  for (int i = 0; i < nsrc && i < kMaxSrcs; i++) {
+    sp.p[i] = srcs[i];
+    vectorOk = vectorOk && aligned16(srcs[i]);
+  }
+  dispatchType(dt, [&](auto tag) {
+    using T = decltype(tag);
+    const int grid = gridFor(count / PackTraits<T>::kElems + 1, kLocalThreads);
+    localReduceManyKernel<T><<<grid, kLocalThreads, 0, stream>>>(static_cast<T*>(dst), sp, nsrc, count,
+                                                                static_cast<DevOp>(op), vectorOk);
+  });
+}
+
+void launchLocalReduce(void* dst, const void* src, size_t count, DataType dt, ReduceOp op, cudaStream_t stream) {
+  const void* srcs[2] = {dst, src};
+  launchLocalReduceMany(dst, srcs, 2, count, dt, op, stream);
+}
+
+void launchLocalBroadcast(void* const* dsts, int ndst, const void* src, size_t bytes, cudaStream_t stream) {
+  if (bytes == 0 || ndst == 0) return;
+  DstPtrs dp;
+  bool vectorOk = aligned16(src);
+  for (int i = 0; i < ndst && i < kMaxSrcs; i++) {
+    dp.p[i] = dsts[i];
+    vectorOk = vectorOk && aligned16(dsts[i]);
+  }
+  const int grid = gridFor(bytes / 16 + 1, kLocalThreads);
+  localBroadcastKernel<<<grid, kLocalThreads, 0, stream>>>(dp, ndst, static_cast<const char*>(src), bytes, vectorOk);
+}
+
+void launchFill(void* dst, size_t count, DataType dt, double start, double stride, cudaStream_t stream) {
+  if (count == 0) return;
+  dispatchType(dt, [&](auto tag) {
+    using T = decltype(tag);
+    fillKernel<T><<<gridFor(count, 256), 256, 0, stream>>>(static_cast<T*>(dst), count, start, stride);
+  });
+}
+
+void launchSpin(long long cycles, cudaStream_t stream) { spinKernel<<<1, 1, 0, stream>>>(cycles); }
+
+}  // namespace cuda
+}  // namespace glb

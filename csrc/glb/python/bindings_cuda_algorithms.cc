@@ -1,0 +1,130 @@
+// Old-style CUDA algorithm objects + remaining CUDA collectives for Python.
+#include <pybind11/pybind11.h>
+#include <pybind11/stl.h>
+
+#include "glb/cuda/algorithms.h"
+#include "glb/cuda/collectives.h"
+
+namespace py = pybind11;
+using namespace glb;
+using namespace glb::cuda;
+
+namespace glb_py {
+
+namespace {
+inline void* P(uintptr_t p) { return reinterpret_cast<void*>(p); }
+inline cudaStream_t S(uintptr_t s) { return reinterpret_cast<cudaStream_t>(s); }
+std::vector<void*> ptrs(const std::vector<uintptr_t>& v) {
+  std::vector<void*> o;
+  for (auto p : v) o.push_back(P(p));
+  return o;
+}
+std::vector<cudaStream_t> streams(const std::vector<uintptr_t>& v) {
+  std::vector<cudaStream_t> o;
+  for (auto s : v) o.push_back(S(s));
+  return o;
+}
+}  // namespace
+
+void registerCudaAlgorithms(py::module_& m) {
+  py::class_<CudaAllreduceCore>(m, "CudaAllreduce")
+      .def(py::init([](std::shared_ptr<Context> ctx, std::vector<uintptr_t> p, size_t count, int dtype, int op,
+                       std::vector<uintptr_t> st, int algo, bool hostWorkspace) {
+        py::gil_scoped_release nogil;
+        return std::make_unique<CudaAllreduceCore>(std::move(ctx), ptrs(p), count, static_cast<DataType>(dtype),
+                                                   static_cast<ReduceOp>(op), streams(st),
+                                                   static_cast<AllreduceAlgo>(algo),
+                                                   hostWorkspace ? Workspace::HOST : Workspace::PEER);
+      }), py::arg("ctx"), py::arg("ptrs"), py::arg("count"), py::arg("dtype"), py::arg("op") = 1,
+          py::arg("streams") = std::vector<uintptr_t>(), py::arg("algo") = 0, py::arg("host_workspace") = false)
+      .def("run", [](CudaAllreduceCore& c) { py::gil_scoped_release nogil; c.run(); })
+      .def("resolved_algo", [](CudaAllreduceCore& c) { return std::string(allreduceAlgoName(c.resolvedAlgo())); })
+      .def("uses_peer_memory", &CudaAllreduceCore::usesPeerMemory);
+
+  py::class_<CudaBroadcastCore>(m, "CudaBroadcast")
+      .def(py::init([](std::shared_ptr<Context> ctx, std::vector<uintptr_t> p, size_t count, int dtype, int root,
+                       int rootPtr, std::vector<uintptr_t> st, bool hostWorkspace) {
+        py::gil_scoped_release nogil;
+        return std::make_unique<CudaBroadcastCore>(std::move(ctx), ptrs(p), count, static_cast<DataType>(dtype), root,
+                                                   rootPtr, streams(st),
+                                                   hostWorkspace ? Workspace::HOST : Workspace::PEER);
+      }), py::arg("ctx"), py::arg("ptrs"), py::arg("count"), py::arg("dtype"), py::arg("root") = 0,
+          py::arg("root_pointer") = 0, py::arg("streams") = std::vector<uintptr_t>(), py::arg("host_workspace") = false)
+      .def("run", [](CudaBroadcastCore& c) { py::gil_scoped_release nogil; c.run(); });
+
+  m.def("peer_context_for", [](std::shared_ptr<Context> ctx, int device) {
+    py::gil_scoped_release nogil;
+    return peerContextFor(ctx, device);
+  });
+  m.def("release_peer_contexts", [](std::shared_ptr<Context> ctx) { releasePeerContexts(ctx); });
+
+  // ---- data movement: registered (`*_reg`) and staged (plain pointer) flavours ------------
+  m.def("broadcast_reg", [](PeerContext& pc, const PeerBuffer& b, size_t off, size_t bytes, int root, uintptr_t st) {
+    py::gil_scoped_release nogil;
+    broadcast(pc, b, off, bytes, root, S(st));
+  });
+  m.def("broadcast", [](PeerContext& pc, uintptr_t p, size_t bytes, int root, uintptr_t st) {
+    py::gil_scoped_release nogil;
+    broadcast(pc, P(p), bytes, root, S(st));
+  });
+  m.def("allgatherv_reg", [](PeerContext& pc, uintptr_t in, const PeerBuffer& out, size_t off,
+                             std::vector<size_t> bytesPerRank, uintptr_t st) {
+    py::gil_scoped_release nogil;
+    allgatherv(pc, P(in), out, off, bytesPerRank, S(st));
+  });
+  m.def("allgatherv", [](PeerContext& pc, uintptr_t in, uintptr_t out, std::vector<size_t> bytesPerRank, uintptr_t st) {
+    py::gil_scoped_release nogil;
+    allgatherv(pc, P(in), P(out), bytesPerRank, S(st));
+  });
+  m.def("gatherv_reg", [](PeerContext& pc, uintptr_t in, const PeerBuffer& out, size_t off,
+                          std::vector<size_t> bytesPerRank, int root, uintptr_t st) {
+    py::gil_scoped_release nogil;
+    gatherv(pc, P(in), out, off, bytesPerRank, root, S(st));
+  });
+  m.def("gatherv", [](PeerContext& pc, uintptr_t in, uintptr_t out, std::vector<size_t> bytesPerRank, int root,
+                      uintptr_t st) {
+    py::gil_scoped_release nogil;
+    gatherv(pc, P(in), P(out), bytesPerRank, root, S(st));
+  });
+  m.def("alltoallv_reg", [](PeerContext& pc, uintptr_t in, std::vector<size_t> sendBytes, const PeerBuffer& out,
+                            size_t off, std::vector<size_t> recvBytes, uintptr_t st) {
+    py::gil_scoped_release nogil;
+    alltoallv(pc, P(in), sendBytes, out, off, recvBytes, S(st));
+  });
+  m.def("alltoallv", [](PeerContext& pc, uintptr_t in, std::vector<size_t> sendBytes, uintptr_t out,
+                        std::vector<size_t> recvBytes, uintptr_t st) {
+    py::gil_scoped_release nogil;
+    alltoallv(pc, P(in), sendBytes, P(out), recvBytes, S(st));
+  });
+  m.def("scatter_reg", [](PeerContext& pc, uintptr_t in, const PeerBuffer& out, size_t off, size_t bytes, int root,
+                          uintptr_t st) {
+    py::gil_scoped_release nogil;
+    scatter(pc, P(in), out, off, bytes, root, S(st));
+  });
+  m.def("scatter", [](PeerContext& pc, uintptr_t in, uintptr_t out, size_t bytes, int root, uintptr_t st) {
+    py::gil_scoped_release nogil;
+    scatter(pc, P(in), P(out), bytes, root, S(st));
+  });
+  m.def("reduce_scatter_reg", [](PeerContext& pc, const PeerBuffer& in, size_t off, uintptr_t out,
+                                 std::vector<size_t> counts, int dtype, int op, uintptr_t st) {
+    py::gil_scoped_release nogil;
+    reduce_scatter(pc, in, off, P(out), counts, static_cast<DataType>(dtype), static_cast<ReduceOp>(op), S(st));
+  });
+  m.def("reduce_scatter", [](PeerContext& pc, uintptr_t in, uintptr_t out, std::vector<size_t> counts, int dtype,
+                             int op, uintptr_t st) {
+    py::gil_scoped_release nogil;
+    reduce_scatter(pc, P(in), P(out), counts, static_cast<DataType>(dtype), static_cast<ReduceOp>(op), S(st));
+  });
+  m.def("reduce_reg", [](PeerContext& pc, const PeerBuffer& in, size_t inOff, const PeerBuffer& out, size_t outOff,
+                         size_t count, int dtype, int op, int root, uintptr_t st) {
+    py::gil_scoped_release nogil;
+    reduce(pc, in, inOff, out, outOff, count, static_cast<DataType>(dtype), static_cast<ReduceOp>(op), root, S(st));
+  });
+  m.def("reduce", [](PeerContext& pc, uintptr_t in, uintptr_t out, size_t count, int dtype, int op, int root,
+                     uintptr_t st) {
+    py::gil_scoped_release nogil;
+    reduce(pc, P(in), P(out), count, static_cast<DataType>(dtype), static_cast<ReduceOp>(op), root, S(st));
+  });
+}
+
+}  // namespace glb_py

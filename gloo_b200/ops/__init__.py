@@ -1,3 +1,3 @@
 """Collective operations. `host` works on CPU buffers over the TCP transport;
 `cuda` works on device buffers through the NVLink peer-memory kernels."""
-from . import host  # noqa: F401
+from . import cuda, host  # noqa: F401

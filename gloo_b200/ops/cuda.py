@@ -1,0 +1,266 @@
+"""CUDA-buffer collectives over NVLink peer memory.
+
+``CudaContext`` wraps the native PeerContext (topology exchange + symmetric pool)
+and offers the collective suite for torch CUDA tensors. A tensor is either
+
+* *registered* (``ctx.register(t)`` or allocated with ``ctx.empty(...)``): kernels
+  read/write the peers' copies directly (zero-copy, NVLS-capable when symmetric);
+* anything else: staged through the pool inside the same call.
+
+Every method is asynchronous on the current torch stream unless ``stream`` is given,
+and must be called in the same order on every rank.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, List, Optional, Sequence, Tuple
+
+from .. import _C
+from ..types import DataType, ReduceOp, describe, element_size
+
+_cu = _C.cuda
+
+ALGOS = {"auto": 0, "one_shot": 1, "two_shot": 2, "nvls": 3, "ring": 10, "ring_chunked": 11,
+         "halving_doubling": 12, "bcube": 13}
+
+
+def _stream(stream) -> int:
+    if stream is None:
+        import torch
+
+        return torch.cuda.current_stream().cuda_stream
+    if isinstance(stream, int):
+        return stream
+    return stream.cuda_stream
+
+
+def _algo(a) -> int:
+    return ALGOS[a] if isinstance(a, str) else int(a)
+
+
+class _SymmetricStorage:
+    """Exposes a PeerBuffer through __cuda_array_interface__ so torch can wrap it."""
+
+    def __init__(self, buf, nbytes: int):
+        self.buf = buf
+        self.__cuda_array_interface__ = {
+            "shape": (nbytes,), "typestr": "|u1", "data": (buf.ptr, False), "version": 3, "strides": None,
+        }
+
+
+class CudaContext:
+    def __init__(self, ctx, device: Optional[int] = None, stage_bytes: int = 0, use_vmm: bool = True,
+                 use_nvls: bool = True):
+        import torch
+
+        if device is None:
+            device = torch.cuda.current_device()
+        self.ctx = ctx
+        self.device = int(device)
+        with torch.cuda.device(self.device):
+            self.pc = _cu.PeerContext(ctx, self.device, stage_bytes, use_vmm, use_nvls)
+        self.rank, self.size = self.pc.rank, self.pc.size
+        self._reg: Dict[int, Tuple[Any, int]] = {}  # base ptr -> (PeerBuffer, nbytes)
+        self._keep: List[Any] = []
+
+    # ---- memory -------------------------------------------------------------------------
+    def register(self, tensor):
+        """Collective: make ``tensor``'s memory addressable by every rank."""
+        ptr, n, dt, cuda = describe(tensor)
+        assert cuda, "register() needs a CUDA tensor"
+        nbytes = n * element_size(dt)
+        buf = self.pc.register_buffer(ptr, nbytes)
+        self._reg[ptr] = (buf, nbytes)
+        return buf
+
+    def empty(self, shape, dtype):
+        """Collective: allocate a symmetric tensor (peer-mapped, NVLS-bound when available)."""
+        import math
+
+        import torch
+
+        shape = (shape,) if isinstance(shape, int) else tuple(shape)
+        n = math.prod(shape)
+        es = torch.empty((), dtype=dtype).element_size()
+        nbytes = max(16, n * es)
+        buf = self.pc.alloc_symmetric(nbytes)
+        store = _SymmetricStorage(buf, nbytes)
+        flat = torch.as_tensor(store, device=f"cuda:{self.device}")
+        t = flat[: n * es].view(dtype).view(shape)
+        self._reg[buf.ptr] = (buf, nbytes)
+        self._keep.append(store)
+        return t
+
+    def lookup(self, tensor) -> Tuple[Optional[Any], int]:
+        """(PeerBuffer, byte offset) if ``tensor`` lies inside a registered region."""
+        ptr = tensor.data_ptr()
+        hit = self._reg.get(ptr)
+        nbytes = tensor.numel() * tensor.element_size()
+        if hit is not None and nbytes <= hit[1]:
+            return hit[0], 0
+        for base, (buf, size) in self._reg.items():
+            if base <= ptr and ptr + nbytes <= base + size:
+                return buf, ptr - base
+        return None, 0
+
+    # ---- info ---------------------------------------------------------------------------
+    def describe(self) -> str:
+        return self.pc.describe()
+
+    def topology(self):
+        return self.pc.topology()
+
+    def nvls_available(self) -> bool:
+        return self.pc.nvls_available()
+
+    # ---- collectives ----------------------------------------------------------------------
+    def barrier(self, stream=None):
+        _cu.barrier(self.pc, _stream(stream))
+
+    def allreduce(self, tensor, op: ReduceOp = ReduceOp.SUM, algo="auto", out=None, stream=None):
+        """In place on ``tensor`` (or tensor -> out)."""
+        ptr, n, dt, _ = describe(tensor)
+        s = _stream(stream)
+        if out is None:
+            buf, off = self.lookup(tensor)
+            if buf is not None:
+                _cu.allreduce_registered(self.pc, buf, off, n, int(dt), int(op), _algo(algo), s)
+                return tensor
+            _cu.allreduce(self.pc, ptr, ptr, n, int(dt), int(op), _algo(algo), s)
+            return tensor
+        _cu.allreduce(self.pc, ptr, out.data_ptr(), n, int(dt), int(op), _algo(algo), s)
+        return out
+
+    def broadcast(self, tensor, root: int = 0, stream=None):
+        ptr, n, dt, _ = describe(tensor)
+        nbytes = n * element_size(dt)
+        buf, off = self.lookup(tensor)
+        if buf is not None:
+            _cu.broadcast_reg(self.pc, buf, off, nbytes, root, _stream(stream))
+        else:
+            _cu.broadcast(self.pc, ptr, nbytes, root, _stream(stream))
+        return tensor
+
+    def allgather(self, output, input, stream=None):
+        return self.allgatherv(output, input, [input.numel()] * self.size, stream)
+
+    def allgatherv(self, output, input, counts: Sequence[int], stream=None):
+        es = output.element_size()
+        sizes = [int(c) * es for c in counts]
+        buf, off = self.lookup(output)
+        iptr = input.data_ptr() if input is not None else 0
+        if buf is not None:
+            _cu.allgatherv_reg(self.pc, iptr, buf, off, sizes, _stream(stream))
+        else:
+            _cu.allgatherv(self.pc, iptr, output.data_ptr(), sizes, _stream(stream))
+        return output
+
+    def gather(self, output, input, root: int = 0, stream=None):
+        return self.gatherv(output, input, [input.numel()] * self.size, root, stream)
+
+    def gatherv(self, output, input, counts: Sequence[int], root: int = 0, stream=None):
+        es = input.element_size()
+        sizes = [int(c) * es for c in counts]
+        optr = output.data_ptr() if output is not None else 0
+        buf, off = (self.lookup(output) if output is not None else (None, 0))
+        if buf is not None:
+            _cu.gatherv_reg(self.pc, input.data_ptr(), buf, off, sizes, root, _stream(stream))
+        else:
+            _cu.gatherv(self.pc, input.data_ptr(), optr, sizes, root, _stream(stream))
+        return output
+
+    def alltoall(self, output, input, stream=None):
+        per = input.numel() // self.size
+        return self.alltoallv(output, [per] * self.size, input, [per] * self.size, stream)
+
+    def alltoallv(self, output, out_counts: Sequence[int], input, in_counts: Sequence[int], stream=None):
+        es = input.element_size()
+        send = [int(c) * es for c in in_counts]
+        recv = [int(c) * es for c in out_counts]
+        buf, off = self.lookup(output)
+        if buf is not None:
+            _cu.alltoallv_reg(self.pc, input.data_ptr(), send, buf, off, recv, _stream(stream))
+        else:
+            _cu.alltoallv(self.pc, input.data_ptr(), send, output.data_ptr(), recv, _stream(stream))
+        return output
+
+    def scatter(self, output, input=None, root: int = 0, stream=None):
+        nbytes = output.numel() * output.element_size()
+        iptr = input.data_ptr() if input is not None else 0
+        buf, off = self.lookup(output)
+        if buf is not None:
+            _cu.scatter_reg(self.pc, iptr, buf, off, nbytes, root, _stream(stream))
+        else:
+            _cu.scatter(self.pc, iptr, output.data_ptr(), nbytes, root, _stream(stream))
+        return output
+
+    def reduce_scatter(self, output, input, counts: Optional[Sequence[int]] = None, op: ReduceOp = ReduceOp.SUM,
+                       stream=None):
+        ptr, n, dt, _ = describe(input)
+        if counts is None:
+            base, rem = divmod(n, self.size)
+            counts = [base + (1 if r < rem else 0) for r in range(self.size)]
+        buf, off = self.lookup(input)
+        if buf is not None:
+            _cu.reduce_scatter_reg(self.pc, buf, off, output.data_ptr(), list(counts), int(dt), int(op), _stream(stream))
+        else:
+            _cu.reduce_scatter(self.pc, ptr, output.data_ptr(), list(counts), int(dt), int(op), _stream(stream))
+        return output
+
+    def reduce(self, output, input, root: int = 0, op: ReduceOp = ReduceOp.SUM, stream=None):
+        ptr, n, dt, _ = describe(input)
+        ibuf, ioff = self.lookup(input)
+        obuf, ooff = (self.lookup(output) if output is not None else (None, 0))
+        if ibuf is not None and obuf is not None:
+            _cu.reduce_reg(self.pc, ibuf, ioff, obuf, ooff, n, int(dt), int(op), root, _stream(stream))
+        else:
+            optr = output.data_ptr() if output is not None else 0
+            _cu.reduce(self.pc, ptr, optr, n, int(dt), int(op), root, _stream(stream))
+        return output
+
+
+# ---- old-style class wrappers -----------------------------------------------------------------
+
+def _make_allreduce_class(name: str, algo: str):
+    class _Cls:
+        __doc__ = f"{name}(ctx, tensors, streams=None, op=SUM, host_workspace=False) — run() is one fused launch."
+
+        def __init__(self, ctx, tensors, streams=None, op: ReduceOp = ReduceOp.SUM, host_workspace: bool = False,
+                     literal: bool = False):
+            tensors = list(tensors) if isinstance(tensors, (list, tuple)) else [tensors]
+            self.tensors = tensors
+            _, n, dt, _ = describe(tensors[0])
+            st = [_stream(s) for s in streams] if streams else []
+            self._impl = _cu.CudaAllreduce(ctx, [t.data_ptr() for t in tensors], n, int(dt), int(op), st,
+                                           ALGOS[algo] if literal else ALGOS["auto"], host_workspace)
+
+        def run(self):
+            self._impl.run()
+
+        def resolved_algo(self) -> str:
+            return self._impl.resolved_algo()
+
+        def uses_peer_memory(self) -> bool:
+            return self._impl.uses_peer_memory()
+
+    _Cls.__name__ = name
+    return _Cls
+
+
+CudaAllreduceRing = _make_allreduce_class("CudaAllreduceRing", "ring")
+CudaAllreduceRingChunked = _make_allreduce_class("CudaAllreduceRingChunked", "ring_chunked")
+CudaAllreduceHalvingDoubling = _make_allreduce_class("CudaAllreduceHalvingDoubling", "halving_doubling")
+CudaAllreduceHalvingDoublingPipelined = _make_allreduce_class("CudaAllreduceHalvingDoublingPipelined", "halving_doubling")
+CudaAllreduceBcube = _make_allreduce_class("CudaAllreduceBcube", "bcube")
+
+
+class CudaBroadcastOneToAll:
+    def __init__(self, ctx, tensors, root: int = 0, root_pointer: int = 0, streams=None, host_workspace: bool = False):
+        tensors = list(tensors) if isinstance(tensors, (list, tuple)) else [tensors]
+        self.tensors = tensors
+        _, n, dt, _ = describe(tensors[0])
+        st = [_stream(s) for s in streams] if streams else []
+        self._impl = _cu.CudaBroadcast(ctx, [t.data_ptr() for t in tensors], n, int(dt), root, root_pointer, st,
+                                       host_workspace)
+
+    def run(self):
+        self._impl.run()

@@ -4,6 +4,7 @@
 
 #include <memory>
 
+#include "glb/common/logging.h"
 #include "glb/context.h"
 #include "glb/math.h"
 #include "glb/types.h"

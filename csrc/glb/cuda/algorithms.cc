@@ -131,6 +131,7 @@ void CudaAllreduceCore::run() {
     }
     std::vector<const void*> srcs(ptrs_.begin(), ptrs_.end());
     launchLocalReduceMany(ptrs_[0], srcs.data(), static_cast<int>(srcs.size()), count_, dt_, op_, *s0);
+    noteLaunch();
   }
 
   // 2. across ranks
@@ -155,6 +156,7 @@ void CudaAllreduceCore::run() {
   if (ptrs_.size() > 1) {
     std::vector<void*> dsts(ptrs_.begin() + 1, ptrs_.end());
     launchLocalBroadcast(dsts.data(), static_cast<int>(dsts.size()), ptrs_[0], bytes, *s0);
+    noteLaunch();
     s0.record();
     for (size_t i = 1; i < streams_.size(); i++) streams_[i].waitOn(s0);
   }

@@ -70,6 +70,7 @@ void checkLaunch(const char* what) {
 }  // namespace
 
 uint64_t launchCount() { return gLaunches.load(); }
+void noteLaunch(unsigned n) { gLaunches.fetch_add(n, std::memory_order_relaxed); }
 
 AllreduceAlgo chooseAllreduce(const PeerContext& pc, size_t bytes, DataType dt, ReduceOp op, bool registered,
                               bool hasMulticast) {

@@ -43,7 +43,8 @@ struct Tuning {
 };
 Tuning& tuning();
 // Number of collective kernels launched by this process so far.
-uint64_t launchCount();  // process-wide; initialised from GLB_CUDA_* env vars
+uint64_t launchCount();
+void noteLaunch(unsigned n = 1);  // local (non-collective) kernels report here  // process-wide; initialised from GLB_CUDA_* env vars
 
 // Which variant AUTO resolves to for this call.
 AllreduceAlgo chooseAllreduce(const PeerContext& pc, size_t bytes, DataType dt, ReduceOp op, bool registered,

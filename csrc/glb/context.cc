@@ -40,8 +40,8 @@ int Context::nextSlot(int numSlots) {
 void Context::closeConnections() {
   if (!transportContext_) return;
   for (int i = 0; i < size; i++) {
-    auto& pair = transportContext_->getPair(i);
-    if (pair) pair->close();
+    auto* pair = transportContext_->peekPair(i);
+    if (pair != nullptr) pair->close();
   }
 }
 

@@ -28,6 +28,8 @@ class Context {
 
   virtual std::unique_ptr<Pair>& getPair(int rank) { return pairs_.at(rank); }
   virtual std::unique_ptr<Pair>& createPair(int rank) = 0;
+  // The pair object as is (no lazy connect); may be null.
+  Pair* peekPair(int rank) { return pairs_.at(rank).get(); }
 
   // Generic rendezvous: every rank publishes the addresses of all its pairs under
   // its rank key, then connects to each peer (O(P^2) store traffic). Transports

@@ -43,8 +43,16 @@ def init_context(rank: int, size: int, store=None, path: Optional[str] = None, p
 
 
 def spawn_threads(size: int, fn: Callable[..., Any], *args, base: int = 2, timeout_ms: int = 30000,
-                  lazy: bool = False, shared_device: bool = False, **kwargs) -> List[Any]:
-    """Run ``fn(ctx, *args, **kwargs)`` on ``size`` threads acting as ranks; returns per-rank results."""
+                  lazy: bool = False, shared_device: bool = False, cuda_device: Optional[int] = None,
+                  **kwargs) -> List[Any]:
+    """Run ``fn(ctx, *args, **kwargs)`` on ``size`` threads acting as ranks; returns per-rank results.
+
+    ``cuda_device``: make that GPU current in every rank thread and give each rank
+    its own CUDA stream. Ranks that share a process must never share a stream: the
+    collective kernels of different ranks wait for each other on the device, so
+    they have to be able to run concurrently (the legacy default stream would
+    serialise them and deadlock).
+    """
     store = _C.HashStore()
     results: List[Any] = [None] * size
     errors: List[Optional[BaseException]] = [None] * size
@@ -57,7 +65,15 @@ def spawn_threads(size: int, fn: Callable[..., Any], *args, base: int = 2, timeo
             ctx.set_timeout(timeout_ms)
             ctx.connect_full_mesh(store, dev)
             try:
-                results[rank] = fn(ctx, *args, **kwargs)
+                if cuda_device is not None:
+                    import torch
+
+                    torch.cuda.set_device(cuda_device)
+                    with torch.cuda.stream(torch.cuda.Stream(cuda_device)):
+                        results[rank] = fn(ctx, *args, **kwargs)
+                        torch.cuda.current_stream().synchronize()
+                else:
+                    results[rank] = fn(ctx, *args, **kwargs)
             finally:
                 # Leave together so nobody tears down sockets a peer still needs.
                 try:

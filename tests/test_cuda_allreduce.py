@@ -33,7 +33,6 @@ def test_allreduce_registered(size, algo):
     counts = [1, 3, 8, 100, 1000, 4099, 65536, 300000]
 
     def fn(ctx):
-        torch.cuda.set_device(0)
         cc = gcu.CudaContext(ctx, 0, stage_bytes=8 << 20)
         for count in counts:
             if algo == "one_shot" and count * 4 > 256 * 1024:
@@ -41,12 +40,12 @@ def test_allreduce_registered(size, algo):
             t = _input(ctx.rank, size, count, torch.float32, "cuda:0")
             cc.register(t)
             cc.allreduce(t, algo=algo)
-            torch.cuda.synchronize()
+            torch.cuda.current_stream().synchronize()
             torch.testing.assert_close(t.double().cpu(), _expected(size, count, torch.float32), rtol=1e-5, atol=0)
         cc.pc.host_barrier()
         return True
 
-    assert all(gb.spawn_threads(size, fn))
+    assert all(gb.spawn_threads(size, fn, cuda_device=0))
 
 
 @pytest.mark.parametrize("dtype", DTYPES)
@@ -54,19 +53,18 @@ def test_allreduce_staged_dtypes(dtype):
     size = 4
 
     def fn(ctx):
-        torch.cuda.set_device(0)
         cc = gcu.CudaContext(ctx, 0, stage_bytes=4 << 20)
         for count in [5, 257, 70001, 700001]:
             small = 7 if dtype in (torch.uint8,) else 50
             t = ((torch.arange(count, dtype=torch.float64) % small) + ctx.rank).to(dtype).cuda()
             exp = sum(((torch.arange(count, dtype=torch.float64) % small) + r).to(dtype).double() for r in range(size))
             cc.allreduce(t)  # unregistered: staged through the pool (one-shot or piecewise two-shot)
-            torch.cuda.synchronize()
+            torch.cuda.current_stream().synchronize()
             torch.testing.assert_close(t.double().cpu(), exp.to(dtype).double(), rtol=_tol(dtype), atol=_tol(dtype))
         cc.pc.host_barrier()
         return True
 
-    assert all(gb.spawn_threads(size, fn))
+    assert all(gb.spawn_threads(size, fn, cuda_device=0))
 
 
 @pytest.mark.parametrize("op", [gb.ReduceOp.SUM, gb.ReduceOp.PRODUCT, gb.ReduceOp.MIN, gb.ReduceOp.MAX])
@@ -74,7 +72,6 @@ def test_allreduce_ops(op):
     size = 3
 
     def fn(ctx):
-        torch.cuda.set_device(0)
         cc = gcu.CudaContext(ctx, 0, stage_bytes=4 << 20)
         g = torch.Generator().manual_seed(7)
         data = [torch.randint(1, 4, (100003,), generator=g).float() for _ in range(size)]
@@ -87,12 +84,12 @@ def test_allreduce_ops(op):
             t = data[ctx.rank][:n].cuda()
             cc.register(t)
             cc.allreduce(t, op=op)
-            torch.cuda.synchronize()
+            torch.cuda.current_stream().synchronize()
             torch.testing.assert_close(t.cpu(), exp[:n])
         cc.pc.host_barrier()
         return True
 
-    assert all(gb.spawn_threads(size, fn))
+    assert all(gb.spawn_threads(size, fn, cuda_device=0))
 
 
 def test_old_style_classes_and_streams():
@@ -101,7 +98,6 @@ def test_old_style_classes_and_streams():
              gcu.CudaAllreduceHalvingDoublingPipelined, gcu.CudaAllreduceBcube]
 
     def fn(ctx):
-        torch.cuda.set_device(0)
         for cls in names:
             for count in (100, 200000):
                 # MultiPointer: two local buffers per rank -> 2*size contributions
@@ -131,14 +127,13 @@ def test_old_style_classes_and_streams():
         gcu._cu.peer_context_for(ctx, 0).host_barrier()
         return True
 
-    assert all(gb.spawn_threads(size, fn))
+    assert all(gb.spawn_threads(size, fn, cuda_device=0))
 
 
 def test_host_workspace_fallback():
     size = 2
 
     def fn(ctx):
-        torch.cuda.set_device(0)
         t = _input(ctx.rank, size, 5000, torch.float32, "cuda:0")
         algo = gcu.CudaAllreduceRingChunked(ctx, t, host_workspace=True)
         assert not algo.uses_peer_memory()
@@ -146,23 +141,22 @@ def test_host_workspace_fallback():
         torch.testing.assert_close(t.double().cpu(), _expected(size, 5000, torch.float32), rtol=1e-5, atol=0)
         return True
 
-    assert all(gb.spawn_threads(size, fn))
+    assert all(gb.spawn_threads(size, fn, cuda_device=0))
 
 
 def test_symmetric_tensor_and_barrier():
     size = 2
 
     def fn(ctx):
-        torch.cuda.set_device(0)
         cc = gcu.CudaContext(ctx, 0, stage_bytes=4 << 20)
         t = cc.empty(4096, torch.float32)
         t.copy_(_input(ctx.rank, size, 4096, torch.float32, "cuda:0"))
         cc.barrier()
         cc.allreduce(t, algo="two_shot")
-        torch.cuda.synchronize()
+        torch.cuda.current_stream().synchronize()
         torch.testing.assert_close(t.double().cpu(), _expected(size, 4096, torch.float32), rtol=1e-5, atol=0)
         cc.pc.host_barrier()
         return cc.describe()
 
-    res = gb.spawn_threads(size, fn)
+    res = gb.spawn_threads(size, fn, cuda_device=0)
     assert all("PeerContext" in r for r in res)

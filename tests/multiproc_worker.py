@@ -1,0 +1,58 @@
+"""Worker process for the fork-as-ranks tests (reference: gloo/test/multiproc_test.{h,cc}).
+
+usage: multiproc_worker.py STORE_DIR RANK SIZE MODE [ARGS...]
+Exit codes: 0 ok, 10 IoError (expected when a peer dies), 1 anything else.
+"""
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+
+import numpy as np  # noqa: E402
+
+import gloo_b200 as gb  # noqa: E402
+
+
+def main():
+    store_dir, rank, size, mode = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), sys.argv[4]
+    args = sys.argv[5:]
+    timeout_ms = int(os.environ.get("GLB_TEST_TIMEOUT_MS", "3000"))
+    ctx = gb.init_context(rank, size, path=store_dir, timeout_ms=timeout_ms)
+    # tell the parent we are connected
+    open(os.path.join(store_dir, f"ready_{rank}"), "w").close()
+    try:
+        if mode == "allreduce_loop":
+            n = int(args[0]) if args else 1000
+            buf = np.ones(n, np.float32)
+            deadline = time.time() + 60
+            while time.time() < deadline:
+                buf[:] = 1
+                gb.allreduce(ctx, buf)
+                assert buf[0] == size
+        elif mode == "allreduce_once":
+            buf = np.full(1000, rank + 1, np.float64)
+            gb.allreduce(ctx, buf)
+            assert buf[0] == size * (size + 1) / 2, buf[0]
+        elif mode == "sendrecv_loop":
+            peer = (rank + 1) % size
+            src = (rank - 1) % size
+            a, b = np.ones(100, np.float32), np.zeros(100, np.float32)
+            ua = ctx.create_unbound_buffer(a.ctypes.data, a.nbytes)
+            ub = ctx.create_unbound_buffer(b.ctypes.data, b.nbytes)
+            deadline = time.time() + 60
+            while time.time() < deadline:
+                ub.recv(src, 1)
+                ua.send(peer, 1)
+                ub.wait_recv()
+                ua.wait_send()
+        else:
+            raise SystemExit(f"unknown mode {mode}")
+    except gb.IoError as e:
+        print(f"rank {rank}: IoError: {e}", file=sys.stderr)
+        sys.exit(10)
+    sys.exit(0)
+
+
+if __name__ == "__main__":
+    main()

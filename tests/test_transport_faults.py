@@ -1,0 +1,82 @@
+"""Fault injection with processes as ranks — mirrors gloo/test/transport_test.cc:53-386
+and multiproc_test.{h,cc}: SIGKILL a rank mid-collective -> survivors raise IoError
+quickly; SIGSTOP a rank -> survivors hit the timeout path."""
+import os
+import signal
+import subprocess
+import sys
+import tempfile
+import time
+
+import pytest
+
+WORKER = os.path.join(os.path.dirname(os.path.abspath(__file__)), "multiproc_worker.py")
+
+
+def launch(size, mode, *args, timeout_ms=3000):
+    d = tempfile.mkdtemp(prefix="glb_mp_")
+    env = dict(os.environ, GLB_TEST_TIMEOUT_MS=str(timeout_ms))
+    procs = [subprocess.Popen([sys.executable, WORKER, d, str(r), str(size), mode, *map(str, args)], env=env,
+                              stderr=subprocess.PIPE, text=True) for r in range(size)]
+    return d, procs
+
+
+def wait_ready(d, size, timeout=60):
+    t0 = time.time()
+    while time.time() - t0 < timeout:
+        if all(os.path.exists(os.path.join(d, f"ready_{r}")) for r in range(size)):
+            return
+        time.sleep(0.02)
+    raise AssertionError("workers did not come up")
+
+
+def reap(procs, timeout):
+    out = []
+    for p in procs:
+        try:
+            p.wait(timeout=timeout)
+        except subprocess.TimeoutExpired:
+            p.kill()
+            p.wait()
+        out.append(p.returncode)
+    return out
+
+
+@pytest.mark.parametrize("size", [2, 4])
+def test_healthy_run(size):
+    d, procs = launch(size, "allreduce_once")
+    assert reap(procs, 60) == [0] * size
+
+
+@pytest.mark.parametrize("size", [2, 3, 4])
+@pytest.mark.parametrize("mode", ["allreduce_loop", "sendrecv_loop"])
+def test_sigkill_is_detected(size, mode):
+    timeout_ms = 3000
+    d, procs = launch(size, mode, timeout_ms=timeout_ms)
+    wait_ready(d, size)
+    time.sleep(0.3)
+    t0 = time.time()
+    procs[0].send_signal(signal.SIGKILL)
+    codes = reap(procs, 2 * timeout_ms / 1000 + 10)
+    elapsed = time.time() - t0
+    assert codes[0] == -signal.SIGKILL
+    assert all(c == 10 for c in codes[1:]), (codes, [p.stderr.read()[-300:] for p in procs[1:]])
+    assert elapsed < 2 * timeout_ms / 1000 + 5
+
+
+@pytest.mark.parametrize("size", [2, 3])
+def test_sigstop_hits_timeout(size):
+    timeout_ms = 1500
+    d, procs = launch(size, "allreduce_loop", timeout_ms=timeout_ms)
+    wait_ready(d, size)
+    time.sleep(0.3)
+    procs[0].send_signal(signal.SIGSTOP)
+    t0 = time.time()
+    codes = reap(procs[1:], 4 * timeout_ms / 1000 + 10)
+    elapsed = time.time() - t0
+    procs[0].send_signal(signal.SIGKILL)
+    procs[0].wait()
+    assert all(c == 10 for c in codes), codes
+    assert elapsed >= timeout_ms / 1000 * 0.5
+    errs = " ".join(p.stderr.read() for p in procs[1:])
+    assert "Timed out" in errs or "timeout" in errs.lower() or "closed" in errs.lower()

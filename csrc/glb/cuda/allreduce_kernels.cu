@@ -37,7 +37,7 @@ __global__ void barrierKernel(CommArgs a) {
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-oneShotAllreduceKernel(CommArgs a, const T* __restrict__ in, T* __restrict__ out, size_t count, DevOp op,
+oneShotAllreduceKernel(CommArgs a, const T* in, T* out, size_t count, DevOp op,
                        PeerPtrs stage, size_t halfBytes, bool vectorOk) {
   using PT = PackTraits<T>;
   const uint32_t e = loadEpoch(a);

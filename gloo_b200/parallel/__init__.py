@@ -1,0 +1,25 @@
+"""Consumers of the collectives — the parallelism strategies of SURVEY §2.18.
+
+The reference implements none of these (it is the substrate they call); each helper
+here is a thin, explicit mapping from a strategy to the collective it consumes:
+
+  DataParallel        gradient allreduce in size-capped buckets (+ broadcast of params)
+  ZeroShard           ZeRO/FSDP: reduce_scatter gradients, allgather parameters
+  TensorParallel      Megatron column/row-parallel linear: allgather / allreduce
+  SequenceParallel    Megatron-SP: reduce_scatter + allgather along the sequence
+  MoEDispatcher       expert parallel dispatch/combine: alltoallv
+  UlyssesAttention    head<->sequence alltoall
+  RingExchange        ring-attention / pipeline neighbour send-recv (KV rotation)
+
+Everything accepts either a CUDA ``CudaContext`` (NVLink kernels) or a host context
+(TCP); tensors decide which path runs.
+"""
+from .strategies import (  # noqa: F401
+    DataParallel,
+    MoEDispatcher,
+    RingExchange,
+    SequenceParallel,
+    TensorParallel,
+    UlyssesAttention,
+    ZeroShard,
+)

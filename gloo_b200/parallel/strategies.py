@@ -1,0 +1,225 @@
+from __future__ import annotations
+
+from typing import Iterable, List, Optional, Sequence
+
+from .. import _C
+from ..ops import host as H
+from ..types import ReduceOp
+
+
+def _is_cuda(t) -> bool:
+    return bool(getattr(t, "is_cuda", False))
+
+
+class _Base:
+    def __init__(self, ctx, cuda_ctx=None):
+        """ctx: host context (control plane, CPU tensors); cuda_ctx: ops.cuda.CudaContext."""
+        self.ctx = ctx
+        self.cc = cuda_ctx
+        self.rank, self.size = ctx.rank, ctx.size
+
+    def _allreduce(self, t, op=ReduceOp.SUM):
+        if _is_cuda(t):
+            self.cc.allreduce(t, op=op)
+        else:
+            H.allreduce(self.ctx, t, op=op)
+        return t
+
+
+class DataParallel(_Base):
+    """Gradient synchronisation for data parallelism.
+
+    Gradients are flattened into buckets of at most ``bucket_bytes`` (sized for launch
+    latency and overlap, not link count — NVSwitch gives every peer full bandwidth)
+    which live in symmetric memory, so each bucket is one zero-copy fused kernel.
+    """
+
+    def __init__(self, ctx, cuda_ctx=None, bucket_bytes: int = 64 << 20):
+        super().__init__(ctx, cuda_ctx)
+        self.bucket_bytes = bucket_bytes
+        self._buckets = {}
+
+    def broadcast_parameters(self, params: Iterable, root: int = 0):
+        for p in params:
+            t = p.data if hasattr(p, "data") else p
+            if _is_cuda(t):
+                self.cc.broadcast(t, root=root)
+            else:
+                H.broadcast(self.ctx, t, root=root)
+
+    def _bucket(self, key, numel, dtype, device):
+        b = self._buckets.get(key)
+        if b is None or b.numel() < numel:
+            if device.type == "cuda":
+                b = self.cc.empty(numel, dtype)  # symmetric: zero-copy, NVLS-capable
+            else:
+                import torch
+
+                b = torch.empty(numel, dtype=dtype)
+            self._buckets[key] = b
+        return b[:numel]
+
+    def allreduce_gradients(self, params: Iterable, average: bool = True):
+        import torch
+
+        grads = [p.grad for p in params if getattr(p, "grad", None) is not None]
+        if not grads:
+            return
+        groups, cur, cur_bytes = [], [], 0
+        for g in grads:
+            nbytes = g.numel() * g.element_size()
+            if cur and (cur_bytes + nbytes > self.bucket_bytes or g.dtype != cur[0].dtype):
+                groups.append(cur)
+                cur, cur_bytes = [], 0
+            cur.append(g)
+            cur_bytes += nbytes
+        if cur:
+            groups.append(cur)
+        for i, group in enumerate(groups):
+            n = sum(g.numel() for g in group)
+            flat = self._bucket((i, group[0].dtype), n, group[0].dtype, group[0].device)
+            off = 0
+            for g in group:
+                flat[off:off + g.numel()].copy_(g.reshape(-1))
+                off += g.numel()
+            self._allreduce(flat)
+            if average:
+                flat.div_(self.size)
+            off = 0
+            for g in group:
+                g.copy_(flat[off:off + g.numel()].view_as(g))
+                off += g.numel()
+
+
+class ZeroShard(_Base):
+    """ZeRO / FSDP building blocks: each rank owns 1/P of a flat parameter vector."""
+
+    def shard_range(self, numel: int):
+        base, rem = divmod(numel, self.size)
+        counts = [base + (1 if r < rem else 0) for r in range(self.size)]
+        start = sum(counts[: self.rank])
+        return start, counts[self.rank], counts
+
+    def reduce_scatter_gradients(self, flat_grad, out_shard, average: bool = True):
+        _, _, counts = self.shard_range(flat_grad.numel())
+        if _is_cuda(flat_grad):
+            self.cc.reduce_scatter(out_shard, flat_grad, counts)
+        else:
+            H.reduce_scatter(self.ctx, out_shard, flat_grad, counts)
+        if average:
+            out_shard.div_(self.size) if hasattr(out_shard, "div_") else None
+        return out_shard
+
+    def allgather_parameters(self, flat_param, shard):
+        _, _, counts = self.shard_range(flat_param.numel())
+        if _is_cuda(flat_param):
+            self.cc.allgatherv(flat_param, shard, counts)
+        else:
+            H.allgatherv(self.ctx, flat_param, counts, shard)
+        return flat_param
+
+
+class TensorParallel(_Base):
+    """Megatron tensor parallelism: row-parallel output is an allreduce of partial sums;
+    column-parallel output is an allgather along the feature dimension."""
+
+    def row_parallel_output(self, partial):
+        return self._allreduce(partial)
+
+    def column_parallel_gather(self, local, out):
+        if _is_cuda(local):
+            self.cc.allgather(out, local)
+        else:
+            H.allgather(self.ctx, out, local)
+        return out
+
+
+class SequenceParallel(_Base):
+    """Megatron sequence parallelism: reduce_scatter along the sequence going in,
+    allgather coming out."""
+
+    def scatter_reduce(self, full, shard):
+        return ZeroShard(self.ctx, self.cc).reduce_scatter_gradients(full, shard, average=False)
+
+    def gather(self, shard, full):
+        return ZeroShard(self.ctx, self.cc).allgather_parameters(full, shard)
+
+
+class MoEDispatcher(_Base):
+    """Expert parallelism: tokens routed to experts living on other ranks.
+
+    dispatch(): rows of ``tokens`` (already sorted by destination rank) are exchanged
+    with alltoallv; the per-source receive counts come from a tiny alltoall of the
+    send counts. combine() is the inverse exchange.
+    """
+
+    def exchange_counts(self, send_counts: Sequence[int]) -> List[int]:
+        import numpy as np
+
+        s = np.asarray(send_counts, dtype=np.int64)
+        r = np.zeros_like(s)
+        H.alltoall(self.ctx, r, s)
+        return [int(x) for x in r]
+
+    def dispatch(self, tokens, send_counts: Sequence[int], out, recv_counts: Optional[Sequence[int]] = None):
+        if recv_counts is None:
+            recv_counts = self.exchange_counts(send_counts)
+        width = tokens.shape[-1] if tokens.dim() > 1 else 1
+        sc = [c * width for c in send_counts]
+        rc = [c * width for c in recv_counts]
+        if _is_cuda(tokens):
+            self.cc.alltoallv(out, rc, tokens, sc)
+        else:
+            H.alltoallv(self.ctx, out, rc, tokens, sc)
+        return out, list(recv_counts)
+
+    def combine(self, expert_out, recv_counts: Sequence[int], out, send_counts: Sequence[int]):
+        # inverse of dispatch: what I received goes back to where it came from
+        return self.dispatch(expert_out, recv_counts, out, send_counts)[0]
+
+
+class UlyssesAttention(_Base):
+    """DeepSpeed-Ulysses: [S/P, H, D] <-> [S, H/P, D] with one alltoall each way."""
+
+    def seq_to_heads(self, x, out):
+        if _is_cuda(x):
+            self.cc.alltoall(out, x)
+        else:
+            H.alltoall(self.ctx, out, x)
+        return out
+
+    heads_to_seq = seq_to_heads
+
+
+class RingExchange(_Base):
+    """Neighbour exchange for ring attention (KV rotation) and pipeline parallelism.
+
+    CPU tensors go through UnboundBuffer send/recv. CUDA tensors use the alltoallv
+    kernel with a single non-zero destination (a direct NVLink write to the right
+    neighbour), which keeps the rotation a single launch.
+    """
+
+    def rotate(self, send, recv, step: int = 1):
+        right, left = (self.rank + step) % self.size, (self.rank - step) % self.size
+        if self.size == 1:
+            recv.copy_(send)
+            return recv
+        if _is_cuda(send):
+            n = send.numel()
+            sc = [n if j == right else 0 for j in range(self.size)]
+            rc = [n if j == left else 0 for j in range(self.size)]
+            self.cc.alltoallv(recv, rc, send, sc)
+            return recv
+        from ..types import describe
+
+        sp, sn, sdt, _ = describe(send)
+        rp, rn, _, _ = describe(recv)
+        nbytes = send.numel() * send.element_size() if hasattr(send, "numel") else send.nbytes
+        sb = self.ctx.create_unbound_buffer(sp, nbytes)
+        rb = self.ctx.create_unbound_buffer(rp, nbytes)
+        slot = _C.slot_build(0x7E, step)
+        rb.recv(left, slot)
+        sb.send(right, slot)
+        rb.wait_recv()
+        sb.wait_send()
+        return recv

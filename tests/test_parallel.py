@@ -1,0 +1,107 @@
+"""parallel/ strategies on the host path (CPU tensors over TCP)."""
+import numpy as np
+import torch
+
+import gloo_b200 as gb
+from gloo_b200.models import DDPMLP, train_step
+from gloo_b200.parallel import (DataParallel, MoEDispatcher, RingExchange, TensorParallel, UlyssesAttention,
+                                ZeroShard)
+
+
+def test_ddp_matches_single_process():
+    size = 4
+    torch.manual_seed(0)
+    ref = DDPMLP()
+    x = torch.randn(size * 8, 64)
+    y = torch.randn(size * 8, 8)
+    # single process, full batch
+    single = DDPMLP()
+    single.load_state_dict(ref.state_dict())
+    loss = torch.nn.functional.mse_loss(single(x), y)
+    loss.backward()
+    want = [p.grad.clone() for p in single.parameters()]
+
+    def fn(ctx):
+        m = DDPMLP()
+        if ctx.rank == 0:
+            m.load_state_dict(ref.state_dict())
+        dp = DataParallel(ctx, bucket_bytes=16 << 10)
+        dp.broadcast_parameters(m.parameters())
+        xs, ys = x[ctx.rank * 8:(ctx.rank + 1) * 8], y[ctx.rank * 8:(ctx.rank + 1) * 8]
+        train_step(m, dp, xs, ys, lr=0.0)
+        return [p.grad.clone() for p in m.parameters()]
+
+    for grads in gb.spawn_threads(size, fn):
+        for g, w in zip(grads, want):
+            torch.testing.assert_close(g, w, rtol=1e-4, atol=1e-5)
+
+
+def test_zero_shard_roundtrip():
+    size = 3
+
+    def fn(ctx):
+        z = ZeroShard(ctx)
+        n = 1000
+        start, cnt, counts = z.shard_range(n)
+        g = torch.arange(n, dtype=torch.float32) + ctx.rank
+        shard = torch.zeros(cnt)
+        z.reduce_scatter_gradients(g, shard, average=False)
+        exp = (torch.arange(n, dtype=torch.float32) * size + sum(range(size)))[start:start + cnt]
+        torch.testing.assert_close(shard, exp)
+        full = torch.zeros(n)
+        z.allgather_parameters(full, shard)
+        torch.testing.assert_close(full, torch.arange(n, dtype=torch.float32) * size + sum(range(size)))
+        return True
+
+    assert all(gb.spawn_threads(size, fn))
+
+
+def test_moe_dispatch_combine():
+    size = 4
+
+    def fn(ctx):
+        moe = MoEDispatcher(ctx)
+        width = 8
+        send = [(ctx.rank + j) % 3 + 1 for j in range(size)]
+        rows = sum(send)
+        tokens = torch.cat([torch.full((send[j], width), float(ctx.rank * 10 + j)) for j in range(size)])
+        recv = moe.exchange_counts(send)
+        assert recv == [(j + ctx.rank) % 3 + 1 for j in range(size)]
+        out = torch.zeros(sum(recv), width)
+        moe.dispatch(tokens, send, out, recv)
+        exp = torch.cat([torch.full((recv[j], width), float(j * 10 + ctx.rank)) for j in range(size)])
+        torch.testing.assert_close(out, exp)
+        back = torch.zeros(rows, width)
+        moe.combine(out, recv, back, send)
+        torch.testing.assert_close(back, tokens)
+        return True
+
+    assert all(gb.spawn_threads(size, fn))
+
+
+def test_tp_ulysses_ring():
+    size = 4
+
+    def fn(ctx):
+        tp = TensorParallel(ctx)
+        part = torch.full((16,), float(ctx.rank + 1))
+        tp.row_parallel_output(part)
+        assert float(part[0]) == 10.0
+        out = torch.zeros(size * 4)
+        tp.column_parallel_gather(torch.full((4,), float(ctx.rank)), out)
+        torch.testing.assert_close(out, torch.arange(size).repeat_interleave(4).float())
+        u = UlyssesAttention(ctx)
+        x = torch.arange(size * 6, dtype=torch.float32) + 100 * ctx.rank
+        y = torch.zeros_like(x)
+        u.seq_to_heads(x, y)
+        exp = torch.cat([torch.arange(ctx.rank * 6, ctx.rank * 6 + 6, dtype=torch.float32) + 100 * j for j in range(size)])
+        torch.testing.assert_close(y, exp)
+        ring = RingExchange(ctx)
+        kv = torch.full((32,), float(ctx.rank))
+        nxt = torch.zeros(32)
+        for step in range(1, size):
+            ring.rotate(kv, nxt, step)
+            assert float(nxt[0]) == float((ctx.rank - step) % size)
+        return True
+
+    assert all(gb.spawn_threads(size, fn))

@@ -7,6 +7,7 @@
 #include "glb/broadcast.h"
 #include "glb/common/utils.h"
 #include "glb/cuda/kernels.h"
+#include "glb/cuda/schedules.h"
 
 namespace glb {
 namespace cuda {
@@ -23,7 +24,7 @@ AllreduceAlgo effectiveAlgo(AllreduceAlgo requested) {
     case AllreduceAlgo::RING_CHUNKED:
     case AllreduceAlgo::HALVING_DOUBLING:
     case AllreduceAlgo::BCUBE:
-      return envFlag("CUDA_LITERAL_SCHEDULES", false) ? requested : AllreduceAlgo::AUTO;
+      return requested;
     default:
       return requested;
   }
@@ -46,6 +47,10 @@ std::vector<CudaStream> makeStreams(const std::vector<void*>& ptrs, const std::v
 
 // All ranks decide together whether the peer path is usable.
 }  // namespace
+
+AllreduceAlgo namedAlgo(AllreduceAlgo named) {
+  return envFlag("CUDA_LITERAL_SCHEDULES", false) ? named : AllreduceAlgo::AUTO;
+}
 
 std::vector<CudaStream> makeStreamsFor(const std::vector<void*>& ptrs, const std::vector<cudaStream_t>& user) {
   return makeStreams(ptrs, user);
@@ -80,7 +85,24 @@ void releasePeerContexts(const std::shared_ptr<Context>& ctx) {
 
 // ---- allreduce ---------------------------------------------------------------------------
 
-struct CudaAllreduceCore::Literal {};
+struct CudaAllreduceCore::Literal {
+  Schedule schedule;
+  SchedStep* deviceTable = nullptr;
+  int device = 0;
+  ~Literal() {
+    if (deviceTable != nullptr) {
+      DeviceGuard g(device);
+      cudaFree(deviceTable);
+    }
+  }
+};
+
+namespace {
+bool isLiteral(AllreduceAlgo a) {
+  return a == AllreduceAlgo::RING || a == AllreduceAlgo::RING_CHUNKED || a == AllreduceAlgo::HALVING_DOUBLING ||
+         a == AllreduceAlgo::BCUBE;
+}
+}  // namespace
 
 CudaAllreduceCore::CudaAllreduceCore(std::shared_ptr<Context> ctx, std::vector<void*> ptrs, size_t count,
                                      DataType dt, ReduceOp op, std::vector<cudaStream_t> streams,
@@ -100,6 +122,31 @@ CudaAllreduceCore::CudaAllreduceCore(std::shared_ptr<Context> ctx, std::vector<v
     if (pc->peerAccessEverywhere()) {
       pc_ = pc;
       reg_ = pc_->registerBuffer(ptrs_[0], count_ * elementSize(dt_));
+      if (isLiteral(algo_) && count_ > 0) {
+        const size_t es = elementSize(dt_);
+        const size_t pack = 16 / es;
+        auto lit = std::make_unique<Literal>();
+        lit->device = dev0;
+        AllreduceAlgo a = algo_;
+        // The whole-vector ring stages every rank's input in its pool; if that does
+        // not fit, the chunked ring is the closest literal schedule.
+        if (a == AllreduceAlgo::RING && count_ * es > pc_->stageBytes() / 2) a = AllreduceAlgo::RING_CHUNKED;
+        switch (a) {
+          case AllreduceAlgo::RING: lit->schedule = buildRingSchedule(ctx_->rank, ctx_->size, count_, pack); break;
+          case AllreduceAlgo::RING_CHUNKED:
+            lit->schedule = buildRingChunkedSchedule(ctx_->rank, ctx_->size, count_, pack);
+            break;
+          case AllreduceAlgo::HALVING_DOUBLING:
+            lit->schedule = buildHalvingDoublingSchedule(ctx_->rank, ctx_->size, count_, pack);
+            break;
+          default: lit->schedule = buildBcubeSchedule(ctx_->rank, ctx_->size, count_, ctx_->base, pack); break;
+        }
+        DeviceGuard g(dev0);
+        const size_t tb = lit->schedule.steps.size() * sizeof(SchedStep);
+        GLB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&lit->deviceTable), std::max<size_t>(tb, 16)));
+        GLB_CUDA_CHECK(cudaMemcpy(lit->deviceTable, lit->schedule.steps.data(), tb, cudaMemcpyHostToDevice));
+        literal_ = std::move(lit);
+      }
     }
   }
   if (ctx_->size > 1 && !pc_) {
@@ -113,6 +160,7 @@ CudaAllreduceCore::~CudaAllreduceCore() {
 
 AllreduceAlgo CudaAllreduceCore::resolvedAlgo() const {
   if (!pc_) return AllreduceAlgo::AUTO;
+  if (literal_) return algo_;
   if (algo_ != AllreduceAlgo::AUTO) return algo_;
   return chooseAllreduce(*pc_, count_ * elementSize(dt_), dt_, op_, true, reg_ && reg_->mc != nullptr);
 }
@@ -136,7 +184,16 @@ void CudaAllreduceCore::run() {
 
   // 2. across ranks
   if (ctx_->size > 1) {
-    if (pc_) {
+    if (pc_ && literal_) {
+      const size_t vecs = bytes / 16 / ctx_->size;
+      const int blocks = std::max(1, std::min<int>({pc_->maxBlocks(), tuning().maxBlocks,
+                                                    static_cast<int>(vecs / kThreads) + 1}));
+      launchSchedule(pc_->comm(), reg_->ptrs(), pc_->stagePtrs(pc_->stageBytes() / 2), literal_->deviceTable,
+                     static_cast<int>(literal_->schedule.steps.size()), dt_, op_, reg_->vectorOk, blocks, *s0);
+      noteLaunch();
+      cudaError_t le = cudaGetLastError();
+      if (le != cudaSuccess) GLB_THROW(Exception, "schedule kernel launch failed: ", cudaGetErrorString(le));
+    } else if (pc_) {
       allreduce(*pc_, *reg_, 0, count_, dt_, op_, algo_, *s0);
     } else {
       // Host workspace: D2H, host collective over the transport, H2D.

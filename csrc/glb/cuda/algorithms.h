@@ -47,6 +47,9 @@ enum class Workspace { PEER, HOST };
 // PeerContext bound to (context, device); created collectively on first use.
 std::shared_ptr<PeerContext> peerContextFor(const std::shared_ptr<Context>& ctx, int device);
 void releasePeerContexts(const std::shared_ptr<Context>& ctx);
+// The variant a reference-named class runs: AUTO (per-size selection) unless literal
+// schedules are requested with GLB_CUDA_LITERAL_SCHEDULES=1.
+AllreduceAlgo namedAlgo(AllreduceAlgo named);
 std::vector<CudaStream> makeStreamsFor(const std::vector<void*>& ptrs, const std::vector<cudaStream_t>& user);
 
 class CudaAllreduceCore {
@@ -153,7 +156,7 @@ const CudaReductionFunction<T>* CudaReductionFunction<T>::max = new CudaReductio
          const CudaReductionFunction<T>* fn = CudaReductionFunction<T>::sum)                              \
         : Algorithm(context),                                                                             \
           core_(context, cuda::eraseType(ptrs), count, DataTypeOf<T>::value, fn->type(), streams,         \
-                cuda::AllreduceAlgo::Algo, cuda::WorkspaceOf<W>::value) {}                                \
+                cuda::namedAlgo(cuda::AllreduceAlgo::Algo), cuda::WorkspaceOf<W>::value) {}                                \
     void run() override { core_.run(); }                                                                  \
     cuda::CudaAllreduceCore& core() { return core_; }                                                     \
                                                                                                           \

@@ -114,6 +114,18 @@ void registerCuda(py::module_& root) {
   });
   m.def("allreduce_algo_name", [](int a) { return std::string(allreduceAlgoName(static_cast<AllreduceAlgo>(a))); });
 
+  // Dedicated (never pooled / shared) streams: torch.cuda.Stream() hands out streams from
+  // a 32-entry pool, so two ranks living in one process can end up on the same stream —
+  // fatal for kernels that wait for each other on the device.
+  m.def("create_stream", [](int device, bool highPriority) {
+    DeviceGuard g(device);
+    int lo = 0, hi = 0;
+    GLB_CUDA_CHECK(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    cudaStream_t s = nullptr;
+    GLB_CUDA_CHECK(cudaStreamCreateWithPriority(&s, cudaStreamNonBlocking, highPriority ? hi : lo));
+    return reinterpret_cast<uintptr_t>(s);
+  }, py::arg("device"), py::arg("high_priority") = false);
+  m.def("destroy_stream", [](uintptr_t s) { cudaStreamDestroy(S(s)); });
   m.def("launch_count", &launchCount);
   m.def("get_tuning", [] {
     const auto& t = tuning();

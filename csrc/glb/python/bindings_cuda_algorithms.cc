@@ -4,6 +4,7 @@
 
 #include "glb/cuda/algorithms.h"
 #include "glb/cuda/collectives.h"
+#include "glb/cuda/schedules.h"
 
 namespace py = pybind11;
 using namespace glb;
@@ -51,6 +52,29 @@ void registerCudaAlgorithms(py::module_& m) {
       }), py::arg("ctx"), py::arg("ptrs"), py::arg("count"), py::arg("dtype"), py::arg("root") = 0,
           py::arg("root_pointer") = 0, py::arg("streams") = std::vector<uintptr_t>(), py::arg("host_workspace") = false)
       .def("run", [](CudaBroadcastCore& c) { py::gil_scoped_release nogil; c.run(); });
+
+  // Step tables of the literal schedules (pure host code: testable without a GPU).
+  m.def("build_schedule", [](const std::string& name, int rank, int size, size_t count, int base, size_t pack) {
+    Schedule sc;
+    if (name == "ring") sc = buildRingSchedule(rank, size, count, pack);
+    else if (name == "ring_chunked") sc = buildRingChunkedSchedule(rank, size, count, pack);
+    else if (name == "halving_doubling") sc = buildHalvingDoublingSchedule(rank, size, count, pack);
+    else if (name == "bcube") sc = buildBcubeSchedule(rank, size, count, base, pack);
+    else GLB_THROW_INVALID_OPERATION_EXCEPTION("unknown schedule ", name);
+    py::list out;
+    for (const auto& st : sc.steps) {
+      py::dict d;
+      d["mode"] = st.mode;
+      d["from_stage"] = st.fromStage;
+      d["off"] = st.off;
+      d["len"] = st.len;
+      py::list peers;
+      for (int i = 0; i < st.npeers; i++) peers.append(st.peers[i]);
+      d["peers"] = peers;
+      out.append(d);
+    }
+    return out;
+  }, py::arg("name"), py::arg("rank"), py::arg("size"), py::arg("count"), py::arg("base") = 2, py::arg("pack") = 4);
 
   m.def("peer_context_for", [](std::shared_ptr<Context> ctx, int device) {
     py::gil_scoped_release nogil;

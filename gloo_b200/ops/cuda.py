@@ -37,6 +37,15 @@ def _algo(a) -> int:
     return ALGOS[a] if isinstance(a, str) else int(a)
 
 
+def new_stream(device: Optional[int] = None, high_priority: bool = False):
+    """A dedicated CUDA stream as a torch ExternalStream (never shared through torch's pool)."""
+    import torch
+
+    device = torch.cuda.current_device() if device is None else device
+    raw = _cu.create_stream(int(device), high_priority)
+    return torch.cuda.ExternalStream(raw, device=device)
+
+
 class _SymmetricStorage:
     """Exposes a PeerBuffer through __cuda_array_interface__ so torch can wrap it."""
 

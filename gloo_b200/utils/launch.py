@@ -69,9 +69,14 @@ def spawn_threads(size: int, fn: Callable[..., Any], *args, base: int = 2, timeo
                     import torch
 
                     torch.cuda.set_device(cuda_device)
-                    with torch.cuda.stream(torch.cuda.Stream(cuda_device)):
-                        results[rank] = fn(ctx, *args, **kwargs)
-                        torch.cuda.current_stream().synchronize()
+                    # A dedicated stream (torch.cuda.Stream() comes from a shared pool).
+                    raw = _C.cuda.create_stream(cuda_device)
+                    try:
+                        with torch.cuda.stream(torch.cuda.ExternalStream(raw, device=cuda_device)):
+                            results[rank] = fn(ctx, *args, **kwargs)
+                            torch.cuda.current_stream().synchronize()
+                    finally:
+                        _C.cuda.destroy_stream(raw)
                 else:
                     results[rank] = fn(ctx, *args, **kwargs)
             finally:

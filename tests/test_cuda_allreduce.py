@@ -98,6 +98,7 @@ def test_old_style_classes_and_streams():
              gcu.CudaAllreduceHalvingDoublingPipelined, gcu.CudaAllreduceBcube]
 
     def fn(ctx):
+        streams = [gcu.new_stream(0) for _ in range(2)]  # dedicated: torch's pool could alias ranks
         for cls in names:
             for count in (100, 200000):
                 # MultiPointer: two local buffers per rank -> 2*size contributions
@@ -112,7 +113,6 @@ def test_old_style_classes_and_streams():
                 for t in ts:
                     torch.testing.assert_close(t.double().cpu(), exp, rtol=1e-5, atol=0)
                 # async variant: user streams + delayed initialisation
-                streams = [torch.cuda.Stream() for _ in range(ptrs)]
                 ts2 = [torch.empty(count, device="cuda") for _ in range(ptrs)]
                 algo2 = cls(ctx, ts2, streams=streams)
                 for i, s in enumerate(streams):
@@ -160,3 +160,26 @@ def test_symmetric_tensor_and_barrier():
 
     res = gb.spawn_threads(size, fn, cuda_device=0)
     assert all("PeerContext" in r for r in res)
+
+
+@pytest.mark.parametrize("size", [2, 3, 4, 8])
+def test_literal_schedules(size):
+    """The named schedules executed literally over peer pointers (one kernel each)."""
+    classes = [gcu.CudaAllreduceRing, gcu.CudaAllreduceRingChunked, gcu.CudaAllreduceHalvingDoubling,
+               gcu.CudaAllreduceBcube]
+
+    def fn(ctx):
+        for cls in classes:
+            for dtype in (torch.float32, torch.float16):
+                for count in (1, 100, 4099, 300000):
+                    small = 8
+                    t = ((torch.arange(count, dtype=torch.float64) % small) + ctx.rank).to(dtype).cuda()
+                    algo = cls(ctx, t, literal=True)
+                    assert algo.resolved_algo() in ("ring", "ring_chunked", "halving_doubling", "bcube")
+                    algo.run()
+                    exp = (torch.arange(count, dtype=torch.float64) % small) * size + size * (size - 1) / 2
+                    torch.testing.assert_close(t.double().cpu(), exp, rtol=1e-3, atol=1e-3)
+        gcu._cu.peer_context_for(ctx, 0).host_barrier()
+        return True
+
+    assert all(gb.spawn_threads(size, fn, cuda_device=0))

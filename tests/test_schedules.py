@@ -1,0 +1,74 @@
+"""The literal CUDA schedules (ring / ring_chunked / halving_doubling / bcube) are step
+tables built on the host; simulate them with numpy (steps are barrier-separated, all
+reads of a step see the state left by the previous step) and check the allreduce."""
+import numpy as np
+import pytest
+
+import gloo_b200 as gb
+
+build = gb._C.cuda.build_schedule
+
+
+def simulate(name, size, count, base=2, pack=4):
+    tables = [build(name, r, size, count, base, pack) for r in range(size)]
+    nsteps = {len(t) for t in tables}
+    assert len(nsteps) == 1, f"ranks disagree on step count: {nsteps}"
+    bufs = [np.arange(count, dtype=np.float64) * size + r for r in range(size)]
+    stage = [np.zeros(count) for _ in range(size)]
+    for s in range(nsteps.pop()):
+        prev = [b.copy() for b in bufs]
+        prev_stage = [b.copy() for b in stage]
+        writes = [None] * size
+        for r in range(size):
+            st = tables[r][s]
+            lo, hi = st["off"], st["off"] + st["len"]
+            assert hi <= count
+            if st["len"] == 0:
+                continue
+            src = prev_stage if st["from_stage"] else prev
+            if st["mode"] == 2:    # STAGE
+                stage[r][lo:hi] = prev[r][lo:hi]
+            elif st["mode"] == 1:  # COPY
+                bufs[r][lo:hi] = src[st["peers"][0]][lo:hi]
+            else:                  # REDUCE
+                acc = prev[r][lo:hi].copy()
+                for p in st["peers"]:
+                    acc += src[p][lo:hi]
+                bufs[r][lo:hi] = acc
+            writes[r] = (lo, hi, st["mode"])
+        # race check: nobody may read a range that its owner writes in the same step
+        for r in range(size):
+            st = tables[r][s]
+            if st["len"] == 0 or st["mode"] == 2:
+                continue
+            lo, hi = st["off"], st["off"] + st["len"]
+            for p in st["peers"]:
+                w = writes[p]
+                if w is None or st["from_stage"] != (w[2] == 2):
+                    continue
+                assert hi <= w[0] or lo >= w[1], f"{name}: step {s}: rank {r} reads [{lo},{hi}) of rank {p} which writes [{w[0]},{w[1]})"
+    exp = np.arange(count, dtype=np.float64) * size * size + size * (size - 1) / 2
+    for r in range(size):
+        np.testing.assert_array_equal(bufs[r], exp, err_msg=f"{name} P={size} n={count} rank {r}")
+
+
+@pytest.mark.parametrize("name", ["ring", "ring_chunked", "halving_doubling", "bcube"])
+@pytest.mark.parametrize("size", [2, 3, 4, 5, 6, 7, 8, 12, 16])
+def test_schedule_is_an_allreduce(name, size):
+    for count in (1, 7, 64, 1000, 4099):
+        simulate(name, size, count)
+
+
+@pytest.mark.parametrize("base,size", [(3, 9), (4, 16), (4, 8), (3, 6)])
+def test_bcube_bases(base, size):
+    simulate("bcube", size, 5000, base=base)
+    # fewer, wider steps than base 2
+    assert len(build("bcube", 0, size, 5000, base, 4)) <= len(build("bcube", 0, size, 5000, 2, 4))
+
+
+def test_step_counts_match_cost_model():
+    # docs/algorithms.md: ring P-1 rounds (+1 publish step), chunked ring 2(P-1), HD 2 lg P
+    assert len(build("ring", 0, 8, 1 << 20, 2, 4)) == 8
+    assert len(build("ring_chunked", 0, 8, 1 << 20, 2, 4)) == 14
+    assert len(build("halving_doubling", 0, 8, 1 << 20, 2, 4)) == 6
+    assert len(build("halving_doubling", 0, 6, 1 << 20, 2, 4)) == 4 + 2  # fold in/out around 4 ranks

@@ -28,6 +28,7 @@
 #include "glb/rendezvous/prefix_store.h"
 #include "glb/scatter.h"
 #include "glb/transport/tcp/device.h"
+#include "glb/transport/tcp/tls/device.h"
 #include "glb/types.h"
 
 namespace py = pybind11;
@@ -212,6 +213,14 @@ PYBIND11_MODULE(_C, m) {
     a.numLoops = numLoops;
     return lazy ? transport::tcp::CreateLazyDevice(a) : transport::tcp::CreateDevice(a);
   }, py::arg("hostname") = "", py::arg("iface") = "", py::arg("lazy") = false, py::arg("num_loops") = 1);
+
+  m.def("create_tls_device", [](const std::string& hostname, const std::string& pkey, const std::string& cert,
+                                const std::string& caFile, const std::string& caPath) {
+    transport::tcp::attr a;
+    a.hostname = hostname;
+    return transport::tcp::tls::CreateDevice(a, pkey, cert, caFile, caPath);
+  }, py::arg("hostname"), py::arg("pkey"), py::arg("cert"), py::arg("ca_file") = "", py::arg("ca_path") = "");
+  m.def("tls_available", &transport::tcp::tls::opensslAvailable);
 
   py::class_<transport::RemoteKey>(m, "RemoteKey")
       .def_readonly("rank", &transport::RemoteKey::rank)

@@ -119,6 +119,8 @@ struct attr resolve(const struct attr& in) {
 
 }  // namespace
 
+struct attr resolveAttr(const struct attr& in) { return resolve(in); }
+
 std::shared_ptr<::glb::transport::Device> CreateDevice(const struct attr& src) {
   return std::make_shared<Device>(resolve(src), /*lazy=*/false);
 }

@@ -528,7 +528,7 @@ void Pair::handleEvents(int events) {
 
 void Pair::readLoop(size_t budget) {
   size_t consumed = 0;
-  while (state_ == CONNECTED && consumed < budget) {
+  while (state_ == CONNECTED && (consumed < budget || ioPending())) {
     if (rx_.hdrRead < sizeof(WireHeader)) {
       ssize_t n = ioRecv(reinterpret_cast<char*>(&rx_.hdr) + rx_.hdrRead, sizeof(WireHeader) - rx_.hdrRead);
       if (n > 0) {

@@ -121,6 +121,9 @@ class Pair : public ::glb::transport::Pair, private Handler {
   virtual ssize_t ioSend(const struct iovec* iov, int iovcnt);
   virtual void ioHandshake(bool isInitiator) {}
   virtual void ioShutdown() {}
+  // Bytes already buffered above the socket (TLS): the read loop must not yield to
+  // epoll while this is true, the fd would not become readable again.
+  virtual bool ioPending() { return false; }
 
   int fd() const { return fd_; }
 

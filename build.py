@@ -70,8 +70,10 @@ def write_ninja(verbose: bool) -> Path:
 
     py_inc = sysconfig.get_paths()["include"]
     common_inc = f"-I{CSRC} -I{CUDA_HOME}/include"
+    have_mpi = os.path.exists("/usr/include/mpi.h") or bool(shutil.which("mpicxx"))
+    mpi_def = "-DGLB_USE_MPI=1 " if have_mpi else "-DGLB_USE_MPI=0 "
     cxxflags = (
-        "-std=c++17 -O2 -g1 -fPIC -Wall -Wextra -Wno-unused-parameter -Wno-missing-field-initializers "
+        mpi_def + "-std=c++17 -O2 -g1 -fPIC -Wall -Wextra -Wno-unused-parameter -Wno-missing-field-initializers "
         "-fvisibility=hidden -pthread -DGLB_USE_CUDA=1 " + common_inc
     )
     nvccflags = (

@@ -4,6 +4,7 @@
 
 #include "glb/cuda/algorithms.h"
 #include "glb/cuda/collectives.h"
+#include "glb/cuda/nccl_wrapper.h"
 #include "glb/cuda/schedules.h"
 
 namespace py = pybind11;
@@ -52,6 +53,39 @@ void registerCudaAlgorithms(py::module_& m) {
       }), py::arg("ctx"), py::arg("ptrs"), py::arg("count"), py::arg("dtype"), py::arg("root") = 0,
           py::arg("root_pointer") = 0, py::arg("streams") = std::vector<uintptr_t>(), py::arg("host_workspace") = false)
       .def("run", [](CudaBroadcastCore& c) { py::gil_scoped_release nogil; c.run(); });
+
+  // NCCL comparator (baseline only).
+  m.def("nccl_available", &ncclAvailable);
+  m.def("nccl_version", &ncclVersionString);
+  py::class_<NcclComm, std::shared_ptr<NcclComm>>(m, "NcclComm")
+      .def_static("init_rank", [](std::shared_ptr<Context> ctx, int device) {
+        py::gil_scoped_release nogil;
+        return NcclComm::initRank(ctx, device);
+      })
+      .def_static("init_all", [](std::vector<int> devices) {
+        py::gil_scoped_release nogil;
+        return NcclComm::initAll(devices);
+      })
+      .def_property_readonly("rank", &NcclComm::rank)
+      .def_property_readonly("size", &NcclComm::size)
+      .def("allreduce", [](NcclComm& c, uintptr_t src, uintptr_t dst, size_t n, int dt, int op, uintptr_t st) {
+        c.allreduce(P(src), P(dst), n, static_cast<DataType>(dt), static_cast<ReduceOp>(op), S(st));
+      })
+      .def("reduce", [](NcclComm& c, uintptr_t src, uintptr_t dst, size_t n, int dt, int op, int root, uintptr_t st) {
+        c.reduce(P(src), P(dst), n, static_cast<DataType>(dt), static_cast<ReduceOp>(op), root, S(st));
+      })
+      .def("reduce_scatter", [](NcclComm& c, uintptr_t src, uintptr_t dst, size_t n, int dt, int op, uintptr_t st) {
+        c.reduceScatter(P(src), P(dst), n, static_cast<DataType>(dt), static_cast<ReduceOp>(op), S(st));
+      })
+      .def("broadcast", [](NcclComm& c, uintptr_t src, uintptr_t dst, size_t n, int dt, int root, uintptr_t st) {
+        c.broadcast(P(src), P(dst), n, static_cast<DataType>(dt), root, S(st));
+      })
+      .def("allgather", [](NcclComm& c, uintptr_t src, uintptr_t dst, size_t n, int dt, uintptr_t st) {
+        c.allgather(P(src), P(dst), n, static_cast<DataType>(dt), S(st));
+      })
+      .def("alltoall", [](NcclComm& c, uintptr_t src, uintptr_t dst, size_t n, int dt, uintptr_t st) {
+        c.alltoall(P(src), P(dst), n, static_cast<DataType>(dt), S(st));
+      });
 
   // Step tables of the literal schedules (pure host code: testable without a GPU).
   m.def("build_schedule", [](const std::string& name, int rank, int size, size_t count, int base, size_t pack) {

@@ -15,7 +15,26 @@ Context::Context(int rank, int size, int base) : rank(rank), size(size), base(ba
   GLB_ENFORCE_GE(size, 1);
 }
 
-Context::~Context() = default;
+Context::~Context() { clearAttachments(); }
+
+std::shared_ptr<void> Context::getAttachment(const std::string& key) {
+  std::lock_guard<std::mutex> g(attachMu_);
+  auto it = attachments_.find(key);
+  return it == attachments_.end() ? nullptr : it->second;
+}
+
+void Context::setAttachment(const std::string& key, std::shared_ptr<void> value) {
+  std::lock_guard<std::mutex> g(attachMu_);
+  attachments_[key] = std::move(value);
+}
+
+void Context::clearAttachments() {
+  std::map<std::string, std::shared_ptr<void>> drop;
+  {
+    std::lock_guard<std::mutex> g(attachMu_);
+    drop.swap(attachments_);
+  }
+}
 
 std::shared_ptr<transport::Device>& Context::getDevice() {
   GLB_ENFORCE(device_, "Device not set!");
@@ -38,6 +57,7 @@ int Context::nextSlot(int numSlots) {
 }
 
 void Context::closeConnections() {
+  clearAttachments();
   if (!transportContext_) return;
   for (int i = 0; i < size; i++) {
     auto* pair = transportContext_->peekPair(i);

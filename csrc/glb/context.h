@@ -6,7 +6,10 @@
 
 #include <atomic>
 #include <chrono>
+#include <map>
 #include <memory>
+#include <mutex>
+#include <string>
 #include <vector>
 
 #include "glb/transport/pair.h"
@@ -45,11 +48,19 @@ class Context {
 
   std::unique_ptr<transport::RemoteKey> deserializeRemoteKey(const std::string& serialized);
 
+  // Objects whose lifetime is tied to this context (e.g. the CUDA PeerContext that the
+  // old-style CUDA algorithms share). They are destroyed before the transport.
+  std::shared_ptr<void> getAttachment(const std::string& key);
+  void setAttachment(const std::string& key, std::shared_ptr<void> value);
+  void clearAttachments();
+
  protected:
   std::shared_ptr<transport::Device> device_;
   std::shared_ptr<transport::Context> transportContext_;
   std::atomic<int> slot_{0};
   std::chrono::milliseconds timeout_;
+  std::mutex attachMu_;
+  std::map<std::string, std::shared_ptr<void>> attachments_;  // declared last: destroyed first
 };
 
 }  // namespace glb

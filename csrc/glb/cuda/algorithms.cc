@@ -13,8 +13,6 @@ namespace glb {
 namespace cuda {
 
 namespace {
-std::mutex gPcMu;
-std::map<std::pair<Context*, int>, std::shared_ptr<PeerContext>> gPeerContexts;
 
 // Map the reference's algorithm names to what actually runs. By default the named
 // classes resolve per message size (AUTO); literal schedules are opt-in.
@@ -64,24 +62,17 @@ bool peerPathUsable(const std::shared_ptr<Context>& ctx, Workspace ws) {
 }  // namespace
 
 std::shared_ptr<PeerContext> peerContextFor(const std::shared_ptr<Context>& ctx, int device) {
-  std::unique_lock<std::mutex> g(gPcMu);
-  auto key = std::make_pair(ctx.get(), device);
-  auto it = gPeerContexts.find(key);
-  if (it != gPeerContexts.end()) return it->second;
-  g.unlock();
-  // Construction is collective and may block on peers: do it outside the lock.
+  // The PeerContext is an attachment of the context: it is shared by every algorithm
+  // built on that context and dies with it (or at closeConnections()).
+  const std::string key = strcat_all("cuda.peer.", device);
+  if (auto existing = ctx->getAttachment(key)) return std::static_pointer_cast<PeerContext>(existing);
+  // Construction is collective and may block on peers.
   auto pc = std::make_shared<PeerContext>(ctx, device);
-  g.lock();
-  gPeerContexts[key] = pc;
+  ctx->setAttachment(key, pc);
   return pc;
 }
 
-void releasePeerContexts(const std::shared_ptr<Context>& ctx) {
-  std::lock_guard<std::mutex> g(gPcMu);
-  for (auto it = gPeerContexts.begin(); it != gPeerContexts.end();) {
-    it = (it->first.first == ctx.get()) ? gPeerContexts.erase(it) : std::next(it);
-  }
-}
+void releasePeerContexts(const std::shared_ptr<Context>& ctx) { ctx->clearAttachments(); }
 
 // ---- allreduce ---------------------------------------------------------------------------
 

@@ -165,7 +165,7 @@ bool envOverride(const char* name, bool dflt) { return envFlag(name, dflt); }
 }  // namespace
 
 PeerContext::PeerContext(std::shared_ptr<Context> context, int dev, PeerOptions opts)
-    : rank(context->rank), size(context->size), device(dev), context_(std::move(context)), opts_(opts) {
+    : rank(context->rank), size(context->size), device(dev), context_(context), opts_(opts) {
   GLB_ENFORCE_LE(size, kMaxRanks, "PeerContext supports at most ", kMaxRanks, " ranks");
   GLB_ENFORCE(deviceCount() > 0, "PeerContext needs a CUDA device");
   GLB_ENFORCE(device >= 0 && device < deviceCount(), "invalid CUDA device ", device);
@@ -199,6 +199,12 @@ PeerContext::~PeerContext() {
   ipcCache_.clear();
 }
 
+std::shared_ptr<Context> PeerContext::context() const {
+  auto c = context_.lock();
+  GLB_ENFORCE(c != nullptr, "the context this PeerContext was built on has been destroyed");
+  return c;
+}
+
 bool PeerContext::sameProcess(int r) const {
   return infos_[r].pid == infos_[rank].pid && std::strcmp(infos_[r].hostname, infos_[rank].hostname) == 0;
 }
@@ -209,7 +215,7 @@ std::vector<T> PeerContext::allgatherStruct(const T& mine) {
   std::vector<T> all(size);
   all[rank] = mine;
   if (size > 1) {
-    AllgatherOptions o(context_);
+    AllgatherOptions o(context());
     o.setOutputRaw(all.data(), all.size() * sizeof(T));
     o.setTag(nextTag());
     allgather(o);
@@ -218,7 +224,7 @@ std::vector<T> PeerContext::allgatherStruct(const T& mine) {
 }
 
 void PeerContext::hostBarrier() {
-  BarrierOptions o(context_);
+  BarrierOptions o(context());
   o.setTag(nextTag());
   barrier(o);
 }
@@ -435,7 +441,7 @@ std::shared_ptr<PeerBuffer> PeerContext::allocVmm(size_t bytes, bool wantMc) {
       continue;
     }
     try {
-      int fd = fdChannel_->recvFd(r, tag, context_->getTimeout());
+      int fd = fdChannel_->recvFd(r, tag, context()->getTimeout());
       CUmemGenericAllocationHandle h = 0;
       CUresult res = d.cuMemImportFromShareableHandle(&h, reinterpret_cast<void*>(static_cast<uintptr_t>(fd)),
                                                       CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
@@ -491,7 +497,7 @@ std::shared_ptr<PeerBuffer> PeerContext::allocVmm(size_t bytes, bool wantMc) {
         for (int r = 1; r < size; r++) fdChannel_->sendFd(infos_[r].fdSocket, mfd, 0, mtag);
         ::close(mfd);
       } else {
-        int mfd = fdChannel_->recvFd(0, mtag, context_->getTimeout());
+        int mfd = fdChannel_->recvFd(0, mtag, context()->getTimeout());
         CUresult res = d.cuMemImportFromShareableHandle(&mc, reinterpret_cast<void*>(static_cast<uintptr_t>(mfd)),
                                                         CU_MEM_HANDLE_TYPE_POSIX_FILE_DESCRIPTOR);
         ::close(mfd);

@@ -91,7 +91,8 @@ class PeerContext : public std::enable_shared_from_this<PeerContext> {
   const int size;
   const int device;
 
-  const std::shared_ptr<Context>& context() const { return context_; }
+  // The control-plane context (throws if it has been destroyed).
+  std::shared_ptr<Context> context() const;
   const std::vector<DeviceInfo>& topology() const { return infos_; }
   // P2P works between every pair of ranks (single host, peer access everywhere).
   bool peerAccessEverywhere() const { return peerOk_; }
@@ -124,7 +125,7 @@ class PeerContext : public std::enable_shared_from_this<PeerContext> {
   std::shared_ptr<PeerBuffer> shareIpc(void* ptr, size_t bytes, bool ownsAllocation);
   bool sameProcess(int r) const;
 
-  std::shared_ptr<Context> context_;
+  std::weak_ptr<Context> context_;  // weak: the context may own this object as an attachment
   PeerOptions opts_;
   std::vector<DeviceInfo> infos_;
   bool peerOk_ = false;

@@ -179,6 +179,7 @@ void CudaAllreduceCore::run() {
       const size_t vecs = bytes / 16 / ctx_->size;
       const int blocks = std::max(1, std::min<int>({pc_->maxBlocks(), tuning().maxBlocks,
                                                     static_cast<int>(vecs / kThreads) + 1}));
+      pc_->launchGuard();
       launchSchedule(pc_->comm(), reg_->ptrs(), pc_->stagePtrs(pc_->stageBytes() / 2), literal_->deviceTable,
                      static_cast<int>(literal_->schedule.steps.size()), dt_, op_, reg_->vectorOk, blocks, *s0);
       noteLaunch();

@@ -83,6 +83,7 @@ AllreduceAlgo chooseAllreduce(const PeerContext& pc, size_t bytes, DataType dt, 
 
 void barrier(PeerContext& pc, cudaStream_t stream) {
   DeviceGuard g(pc.device);
+  pc.launchGuard();
   launchBarrier(pc.comm(), stream);
   checkLaunch("barrier");
 }
@@ -99,6 +100,7 @@ void allreduce(PeerContext& pc, const PeerBuffer& buf, size_t byteOffset, size_t
   if (pc.size == 1) return;  // single rank: the buffer already holds the result
   const bool hasMc = buf.mc != nullptr && byteOffset % 16 == 0;
   if (algo == AllreduceAlgo::AUTO) algo = chooseAllreduce(pc, bytes, dt, op, true, hasMc);
+  pc.launchGuard();
   switch (algo) {
     case AllreduceAlgo::ONE_SHOT: {
       const auto l = layoutOf(pc);
@@ -143,6 +145,7 @@ void allreduce(PeerContext& pc, const void* in, void* out, size_t count, DataTyp
   const bool mcOk = pc.nvlsAvailable();
   if (algo == AllreduceAlgo::AUTO) algo = chooseAllreduce(pc, bytes, dt, op, false, mcOk);
   if (algo == AllreduceAlgo::ONE_SHOT && bytes <= l.half) {
+    pc.launchGuard();
     const int blocks = blocksFor(pc, bytes / 16, 1, tuning().oneShotBlocks);
     launchOneShotAllreduce(pc.comm(), in, out, count, dt, op, pc.stagePtrs(0), l.half, blocks, stream);
     checkLaunch("allreduce(one-shot)");
@@ -164,6 +167,7 @@ void allreduce(PeerContext& pc, const void* in, void* out, size_t count, DataTyp
     const char* src = static_cast<const char*>(in) + done * es;
     char* dst = static_cast<char*>(out) + done * es;
     GLB_CUDA_CHECK(cudaMemcpyAsync(myStage, src, n * es, cudaMemcpyDeviceToDevice, stream));
+    pc.launchGuard();
     if (algo == AllreduceAlgo::NVLS) {
       const int blocks = blocksFor(pc, ceilDiv(n * es, 16) / pc.size, 4, tuning().maxBlocks);
       launchNvlsAllreduce(pc.comm(), pc.stageMc(l.bulkOff), stage, n, dt, blocks, stream);
@@ -226,6 +230,7 @@ void broadcast(PeerContext& pc, const PeerBuffer& buf, size_t byteOffset, size_t
     mode = 1;
   }
   const int blocks = bwBlocks(pc, mode == 1 ? bytes / pc.size * 2 : bytes);
+  pc.launchGuard();
   launchBroadcast(pc.comm(), buf.ptrsAt(byteOffset), buf.mc ? static_cast<char*>(buf.mc) + byteOffset : nullptr,
                   bytes, root, mode, vec, blocks, stream);
   checkLaunch("broadcast");
@@ -248,6 +253,7 @@ void broadcast(PeerContext& pc, void* ptr, size_t bytes, int root, cudaStream_t 
     } else if (n > tuning().bcastDirectMaxBytes && pc.size > 2) {
       mode = 1;
     }
+    pc.launchGuard();
     launchBroadcast(pc.comm(), stage, pc.stageMc(l.bulkOff), n, root, mode, true,
                     bwBlocks(pc, mode == 1 ? n / pc.size * 2 : n), stream);
     checkLaunch("broadcast(staged)");
@@ -261,6 +267,7 @@ void gatherCommon(PeerContext& pc, const void* in, const PeerPtrs& outs, void* m
   GLB_ENFORCE_EQ(static_cast<int>(bytesPerRank.size()), pc.size, "need one byte count per rank");
   auto off = prefix(bytesPerRank);
   const bool vec = vecOut && reinterpret_cast<uintptr_t>(in) % 16 == 0;
+  pc.launchGuard();
   launchGatherPush(pc.comm(), in, outs, mcOut, off.data(), bytesPerRank.data(), onlyDst, vec,
                    bwBlocks(pc, bytesPerRank[pc.rank]), stream);
   checkLaunch("allgather/gather");
@@ -337,6 +344,7 @@ void alltoallCommon(PeerContext& pc, const void* in, const std::vector<size_t>& 
   for (int j = 0; j < pc.size; j++) dstOff[j] = uniform ? static_cast<size_t>(pc.rank) * sendBytes[0] : ~size_t(0);
   const bool vec = vecOut && reinterpret_cast<uintptr_t>(in) % 16 == 0;
   size_t total = soff.back();
+  pc.launchGuard();
   launchAlltoallPush(pc.comm(), in, outs, soff.data(), sendBytes.data(), dstOff.data(), uniform ? nullptr : roff.data(),
                      -1, vec, bwBlocks(pc, total), stream);
   checkLaunch("alltoall");
@@ -383,6 +391,7 @@ void scatter(PeerContext& pc, const void* in, const PeerBuffer& out, size_t outO
   std::vector<size_t> soff(pc.size), slen(pc.size, bytes), doff(pc.size, 0);
   for (int j = 0; j < pc.size; j++) soff[j] = static_cast<size_t>(j) * bytes;
   const bool vec = out.vectorOk && outOffset % 16 == 0 && (pc.rank != root || reinterpret_cast<uintptr_t>(in) % 16 == 0);
+  pc.launchGuard();
   launchAlltoallPush(pc.comm(), in, out.ptrsAt(outOffset), soff.data(), slen.data(), doff.data(), nullptr, root, vec,
                      bwBlocks(pc, bytes * pc.size), stream);
   checkLaunch("scatter");
@@ -397,6 +406,7 @@ void scatter(PeerContext& pc, const void* in, void* out, size_t bytes, int root,
   auto st = stagedBulk(pc, bytes, "scatter");
   std::vector<size_t> soff(pc.size), slen(pc.size, bytes), doff(pc.size, 0);
   for (int j = 0; j < pc.size; j++) soff[j] = static_cast<size_t>(j) * bytes;
+  pc.launchGuard();
   launchAlltoallPush(pc.comm(), in, st.ptrs, soff.data(), slen.data(), doff.data(), nullptr, root,
                      pc.rank != root || reinterpret_cast<uintptr_t>(in) % 16 == 0, bwBlocks(pc, bytes * pc.size), stream);
   checkLaunch("scatter(staged)");
@@ -411,6 +421,7 @@ void reducePullCommon(PeerContext& pc, const PeerPtrs& ins, void* mcIn, bool vec
   auto off = prefix(counts);
   const size_t es = elementSize(dt);
   const bool useMc = mcIn != nullptr && nvlsSupports(dt, op) && counts[pc.rank] * es >= tuning().nvlsMinBytes;
+  pc.launchGuard();
   launchReducePull(pc.comm(), ins, mcIn, out, off.data(), counts.data(), dt, op, vecIn, useMc,
                    blocksFor(pc, counts[pc.rank] * es / 16, 1, tuning().maxBlocks), stream);
   checkLaunch("reduce_scatter");

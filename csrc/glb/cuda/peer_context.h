@@ -107,6 +107,14 @@ class PeerContext : public std::enable_shared_from_this<PeerContext> {
   std::shared_ptr<PeerBuffer> allocSymmetric(size_t bytes);
   std::shared_ptr<PeerBuffer> registerBuffer(void* ptr, size_t bytes);
   void hostBarrier();
+  // Call right before launching a kernel that waits for its peers. When several ranks
+  // share one GPU (threads-as-ranks tests) a peer that is still inside a device-
+  // synchronising call (cudaMalloc from an allocator, cudaFree, ...) would block behind
+  // our spinning kernel and never launch its own: rendezvous on the host first so every
+  // rank is at its launch point. No-op with one rank per GPU.
+  void launchGuard() {
+    if (ranksOnMyDevice_ > 1) hostBarrier();
+  }
 
   // ---- kernel arguments --------------------------------------------------------------
   const CommArgs& comm() const { return comm_; }

@@ -16,53 +16,65 @@ scheduleKernel(CommArgs a, PeerPtrs bufs, PeerPtrs stage, const SchedStep* __res
   T* local = static_cast<T*>(bufs.p[a.rank]);
   T* myStage = static_cast<T*>(stage.p[a.rank]);
 
+  // Ownership rule: pack (or element) index i of the buffer is always handled by global
+  // thread i % nthreads — in every step and on every rank. The inter-rank barrier only
+  // synchronises CTAs with the same blockIdx, so a value read in step s must have been
+  // written in step s-1 by the SAME (block, thread) slot on the peer; with absolute
+  // ownership that holds no matter how the ranges of consecutive steps differ.
+  auto firstOwned = [&](size_t begin) { return begin + (tid + nthreads - begin % nthreads) % nthreads; };
+
   for (int s = 0; s < nsteps; s++) {
     // Step s may read what peers produced in step s-1 (and, for s == 0, their inputs).
     blockBarrier(a, e + 1 + s);
     const SchedStep st = table[s];
     const size_t off = st.off, len = st.len;
     if (len == 0) continue;
+    // Vector part: whole 16-byte packs inside [off, off+len) (ranges are pack aligned
+    // except possibly at their very end); the rest goes element by element.
     const bool v16 = vectorOk && (off * sizeof(T)) % 16 == 0;
-    const size_t nvec = v16 ? len / PT::kElems : 0;
-    char* dst = reinterpret_cast<char*>((st.mode == SCHED_STAGE ? myStage : local) + off);
+    const size_t pvBegin = off * sizeof(T) / 16;
+    const size_t pvEnd = v16 ? pvBegin + len / PT::kElems : pvBegin;
+    const size_t tailBegin = v16 ? off + (len / PT::kElems) * PT::kElems : off;
+    const size_t tailEnd = off + len;
+    char* lbase = reinterpret_cast<char*>(local);
+    char* sbase = reinterpret_cast<char*>(myStage);
     if (st.mode == SCHED_STAGE) {
-      const char* src = reinterpret_cast<const char*>(local + off);
-      for (size_t v = tid; v < nvec; v += nthreads) st128(dst + v * 16, ld128_stream(src + v * 16));
-      for (size_t i = nvec * PT::kElems + tid; i < len; i += nthreads) myStage[off + i] = local[off + i];
+      for (size_t pv = firstOwned(pvBegin); pv < pvEnd; pv += nthreads) st128(sbase + pv * 16, ld128_stream(lbase + pv * 16));
+      for (size_t i = firstOwned(tailBegin); i < tailEnd; i += nthreads) myStage[i] = local[i];
       continue;
     }
     const PeerPtrs& srcs = st.fromStage ? stage : bufs;
     if (st.mode == SCHED_COPY) {
-      const char* src = reinterpret_cast<const char*>(static_cast<const T*>(srcs.p[st.peers[0]]) + off);
+      const char* src = static_cast<const char*>(srcs.p[st.peers[0]]);
       constexpr int U = 4;
-      for (size_t v0 = tid; v0 < nvec; v0 += nthreads * U) {
+      for (size_t pv0 = firstOwned(pvBegin); pv0 < pvEnd; pv0 += nthreads * U) {
         Pack16 p[U];
 #pragma unroll
         for (int u = 0; u < U; u++) {
-          const size_t v = v0 + u * nthreads;
-          if (v < nvec) p[u] = ld128_stream(src + v * 16);
+          const size_t pv = pv0 + u * nthreads;
+          if (pv < pvEnd) p[u] = ld128_stream(src + pv * 16);
         }
 #pragma unroll
         for (int u = 0; u < U; u++) {
-          const size_t v = v0 + u * nthreads;
-          if (v < nvec) st128(dst + v * 16, p[u]);
+          const size_t pv = pv0 + u * nthreads;
+          if (pv < pvEnd) st128(lbase + pv * 16, p[u]);
         }
       }
-      for (size_t i = nvec * PT::kElems + tid; i < len; i += nthreads) {
-        local[off + i] = static_cast<const T*>(srcs.p[st.peers[0]])[off + i];
+      for (size_t i = firstOwned(tailBegin); i < tailEnd; i += nthreads) {
+        local[i] = static_cast<const T*>(srcs.p[st.peers[0]])[i];
       }
     } else {
-      for (size_t v = tid; v < nvec; v += nthreads) {
-        typename PT::AccPack acc = PT::widen(ld128(dst + v * 16));
+      for (size_t pv = firstOwned(pvBegin); pv < pvEnd; pv += nthreads) {
+        typename PT::AccPack acc = PT::widen(ld128(lbase + pv * 16));
         for (int p = 0; p < st.npeers; p++) {
-          PT::combine(acc, ld128_stream(reinterpret_cast<const char*>(static_cast<const T*>(srcs.p[st.peers[p]]) + off) + v * 16), op);
+          PT::combine(acc, ld128_stream(static_cast<const char*>(srcs.p[st.peers[p]]) + pv * 16), op);
         }
-        st128(dst + v * 16, PT::narrow(acc));
+        st128(lbase + pv * 16, PT::narrow(acc));
       }
-      for (size_t i = nvec * PT::kElems + tid; i < len; i += nthreads) {
-        T acc = local[off + i];
-        for (int p = 0; p < st.npeers; p++) acc = PT::combineOne(acc, static_cast<const T*>(srcs.p[st.peers[p]])[off + i], op);
-        local[off + i] = acc;
+      for (size_t i = firstOwned(tailBegin); i < tailEnd; i += nthreads) {
+        T acc = local[i];
+        for (int p = 0; p < st.npeers; p++) acc = PT::combineOne(acc, static_cast<const T*>(srcs.p[st.peers[p]])[i], op);
+        local[i] = acc;
       }
     }
   }

@@ -95,7 +95,9 @@ broadcastKernel(CommArgs a, PeerPtrs bufs, char* mc, size_t bytes, int root, int
     }
     blockBarrier(a, e + 2);
     used = 3;
-    if (a.rank != root) {
+    // Every rank (the root too: nobody else holds its slice) now pushes the slice it
+    // owns to all ranks that still miss it, i.e. everyone but itself and the root.
+    {
       size_t b, en;
       shareOfB(units, P, a.rank, b, en);
       const char* src = static_cast<const char*>(bufs.p[a.rank]) + b * 16;

@@ -232,6 +232,37 @@ constexpr bool isHotType() {
 
 }  // namespace
 
+// Force-load every kernel of this file. With CUDA's lazy module loading the first
+// launch of a kernel may have to synchronise the context; if a peer rank on the same
+// device is already spinning inside its collective kernel that launch never happens
+// (documented lazy-loading deadlock for kernels that assume concurrency).
+namespace {
+template <typename K>
+void touch(K kernel) {
+  cudaFuncAttributes attr;
+  cudaFuncGetAttributes(&attr, reinterpret_cast<const void*>(kernel));
+}
+}  // namespace
+
+void preloadAllreduceKernels() {
+  touch(barrierKernel);
+  for (DataType dt : {DataType::INT8, DataType::UINT8, DataType::INT16, DataType::INT32, DataType::UINT32, DataType::INT64,
+                      DataType::UINT64, DataType::FLOAT32, DataType::FLOAT64, DataType::FLOAT16, DataType::BFLOAT16}) {
+    dispatchType(dt, [&](auto tag) {
+      using T = decltype(tag);
+      touch(oneShotAllreduceKernel<T>);
+      touch(twoShotAllreduceKernel<T, 0, 1>);
+      if constexpr (isHotType<T>()) {
+        touch(twoShotAllreduceKernel<T, 2, 4>);
+        touch(twoShotAllreduceKernel<T, 4, 2>);
+        touch(twoShotAllreduceKernel<T, 8, 2>);
+        touch(nvlsAllreduceKernel<T, 4>);
+      }
+    });
+  }
+  cudaGetLastError();
+}
+
 void launchBarrier(const CommArgs& a, cudaStream_t stream) {
   barrierKernel<<<1, 32, 0, stream>>>(a);
 }

@@ -324,5 +324,28 @@ void launchReducePull(const CommArgs& a, const PeerPtrs& ins, void* mcIn, void* 
 #undef GLB_CASE
 }
 
+
+void preloadCollectiveKernels() {
+  auto touch = [](const void* k) {
+    cudaFuncAttributes attr;
+    cudaFuncGetAttributes(&attr, k);
+  };
+  touch(reinterpret_cast<const void*>(broadcastKernel));
+  touch(reinterpret_cast<const void*>(gatherPushKernel));
+  touch(reinterpret_cast<const void*>(alltoallPushKernel));
+  touch(reinterpret_cast<const void*>(reducePullKernel<int8_t>));
+  touch(reinterpret_cast<const void*>(reducePullKernel<uint8_t>));
+  touch(reinterpret_cast<const void*>(reducePullKernel<int16_t>));
+  touch(reinterpret_cast<const void*>(reducePullKernel<int32_t>));
+  touch(reinterpret_cast<const void*>(reducePullKernel<uint32_t>));
+  touch(reinterpret_cast<const void*>(reducePullKernel<long long>));
+  touch(reinterpret_cast<const void*>(reducePullKernel<unsigned long long>));
+  touch(reinterpret_cast<const void*>(reducePullKernel<float>));
+  touch(reinterpret_cast<const void*>(reducePullKernel<double>));
+  touch(reinterpret_cast<const void*>(reducePullKernel<__half>));
+  touch(reinterpret_cast<const void*>(reducePullKernel<__nv_bfloat16>));
+  cudaGetLastError();
+}
+
 }  // namespace cuda
 }  // namespace glb

@@ -9,6 +9,12 @@
 namespace glb {
 namespace cuda {
 
+// Force-load all kernels of the library on the current device (idempotent, cheap).
+void preloadAllreduceKernels();
+void preloadCollectiveKernels();
+void preloadScheduleKernels();
+void preloadLocalKernels();
+
 // allreduce_kernels.cu
 void launchBarrier(const CommArgs& a, cudaStream_t stream);
 void launchOneShotAllreduce(const CommArgs& a, const void* in, void* out, size_t count, DataType dt, ReduceOp op,

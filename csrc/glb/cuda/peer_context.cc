@@ -14,6 +14,7 @@
 #include "glb/allgather.h"
 #include "glb/barrier.h"
 #include "glb/common/utils.h"
+#include "glb/cuda/kernels.h"
 
 namespace glb {
 namespace cuda {
@@ -176,6 +177,11 @@ PeerContext::PeerContext(std::shared_ptr<Context> context, int dev, PeerOptions 
 
   DeviceGuard g(device);
   GLB_CUDA_CHECK(cudaFree(nullptr));
+  // Load every kernel now, while no peer can be spinning on this device yet.
+  preloadAllreduceKernels();
+  preloadCollectiveKernels();
+  preloadScheduleKernels();
+  preloadLocalKernels();
   fdChannel_ = std::make_unique<FdChannel>(rank);
   exchangeTopology();
 

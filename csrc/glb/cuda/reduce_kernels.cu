@@ -158,5 +158,23 @@ void launchFill(void* dst, size_t count, DataType dt, double start, double strid
 
 void launchSpin(long long cycles, cudaStream_t stream) { spinKernel<<<1, 1, 0, stream>>>(cycles); }
 
+void preloadLocalKernels() {
+  auto touch = [](const void* k) {
+    cudaFuncAttributes attr;
+    cudaFuncGetAttributes(&attr, k);
+  };
+  for (DataType dt : {DataType::INT8, DataType::UINT8, DataType::INT16, DataType::INT32, DataType::UINT32, DataType::INT64,
+                      DataType::UINT64, DataType::FLOAT32, DataType::FLOAT64, DataType::FLOAT16, DataType::BFLOAT16}) {
+    dispatchType(dt, [&](auto tag) {
+      using T = decltype(tag);
+      touch(reinterpret_cast<const void*>(localReduceManyKernel<T>));
+      touch(reinterpret_cast<const void*>(fillKernel<T>));
+    });
+  }
+  touch(reinterpret_cast<const void*>(localBroadcastKernel));
+  touch(reinterpret_cast<const void*>(spinKernel));
+  cudaGetLastError();
+}
+
 }  // namespace cuda
 }  // namespace glb

@@ -105,5 +105,25 @@ void launchSchedule(const CommArgs& a, const PeerPtrs& bufs, const PeerPtrs& sta
 #undef GLB_CASE
 }
 
+
+void preloadScheduleKernels() {
+  auto touch = [](const void* k) {
+    cudaFuncAttributes attr;
+    cudaFuncGetAttributes(&attr, k);
+  };
+  touch(reinterpret_cast<const void*>(scheduleKernel<int8_t>));
+  touch(reinterpret_cast<const void*>(scheduleKernel<uint8_t>));
+  touch(reinterpret_cast<const void*>(scheduleKernel<int16_t>));
+  touch(reinterpret_cast<const void*>(scheduleKernel<int32_t>));
+  touch(reinterpret_cast<const void*>(scheduleKernel<uint32_t>));
+  touch(reinterpret_cast<const void*>(scheduleKernel<long long>));
+  touch(reinterpret_cast<const void*>(scheduleKernel<unsigned long long>));
+  touch(reinterpret_cast<const void*>(scheduleKernel<float>));
+  touch(reinterpret_cast<const void*>(scheduleKernel<double>));
+  touch(reinterpret_cast<const void*>(scheduleKernel<__half>));
+  touch(reinterpret_cast<const void*>(scheduleKernel<__nv_bfloat16>));
+  cudaGetLastError();
+}
+
 }  // namespace cuda
 }  // namespace glb

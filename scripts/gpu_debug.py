@@ -7,6 +7,7 @@ import subprocess
 import sys
 import time
 
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 

@@ -3,6 +3,10 @@ import sys
 
 import pytest
 
+# Ranks are threads sharing one GPU in the GPU tests: a rank loading a (torch) kernel for
+# the first time must not block behind another rank's waiting collective kernel.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
+
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 
 

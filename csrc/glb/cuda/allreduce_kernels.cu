@@ -27,6 +27,8 @@
 namespace glb {
 namespace cuda {
 
+bool oneShotPushEnabled();
+
 __global__ void barrierKernel(CommArgs a) {
   const uint32_t e = loadEpoch(a);
   blockBarrier(a, e + 1);
@@ -34,6 +36,60 @@ __global__ void barrierKernel(CommArgs a) {
 }
 
 // ---- one-shot ---------------------------------------------------------------------
+
+// Push flavour for the smallest messages: every rank STORES its contribution into slot
+// `rank` of every peer's pool (posted writes, no round trip), one barrier, then reads the P
+// slots from its own memory. Saves the remote-load round trip of the pull flavour at the
+// cost of P x the staging space, so it is used while P * bytes fits one half.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+oneShotPushAllreduceKernel(CommArgs a, const T* in, T* out, size_t count, DevOp op, PeerPtrs stage,
+                           size_t halfBytes, size_t slotBytes, bool vectorOk) {
+  using PT = PackTraits<T>;
+  const uint32_t e = loadEpoch(a);
+  const uint32_t parity = ld_relaxed_sys(&a.sig[a.rank]->stageSeq) & 1u;
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t base = parity * halfBytes;
+  const size_t nvec = vectorOk ? count / PT::kElems : 0;
+  const size_t tailStart = nvec * PT::kElems;
+  const size_t mySlot = base + static_cast<size_t>(a.rank) * slotBytes;
+
+  for (size_t v = tid; v < nvec; v += nthreads) {
+    const Pack16 p = ld128_stream(reinterpret_cast<const char*>(in) + v * 16);
+#pragma unroll
+    for (int r = 0; r < kMaxRanks; r++) {
+      if (r < a.nranks) st128_stream(static_cast<char*>(stage.p[r]) + mySlot + v * 16, p);
+    }
+  }
+  for (size_t i = tailStart + tid; i < count; i += nthreads) {
+    const T x = in[i];
+    for (int r = 0; r < a.nranks; r++) reinterpret_cast<T*>(static_cast<char*>(stage.p[r]) + mySlot)[i] = x;
+  }
+
+  blockBarrier(a, e + 1);
+
+  const char* mine = static_cast<const char*>(stage.p[a.rank]) + base;
+  for (size_t v = tid; v < nvec; v += nthreads) {
+    Pack16 p[kMaxRanks];
+#pragma unroll
+    for (int r = 0; r < kMaxRanks; r++) {
+      if (r < a.nranks) p[r] = ld128(mine + r * slotBytes + v * 16);
+    }
+    typename PT::AccPack acc = PT::widen(p[0]);
+#pragma unroll
+    for (int r = 1; r < kMaxRanks; r++) {
+      if (r < a.nranks) PT::combine(acc, p[r], op);
+    }
+    st128(reinterpret_cast<char*>(out) + v * 16, PT::narrow(acc));
+  }
+  for (size_t i = tailStart + tid; i < count; i += nthreads) {
+    T acc = reinterpret_cast<const T*>(mine)[i];
+    for (int r = 1; r < a.nranks; r++) acc = PT::combineOne(acc, reinterpret_cast<const T*>(mine + r * slotBytes)[i], op);
+    out[i] = acc;
+  }
+  retire(a, 1, 1);
+}
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
@@ -251,6 +307,7 @@ void preloadAllreduceKernels() {
     dispatchType(dt, [&](auto tag) {
       using T = decltype(tag);
       touch(oneShotAllreduceKernel<T>);
+      touch(oneShotPushAllreduceKernel<T>);
       touch(twoShotAllreduceKernel<T, 0, 1>);
       if constexpr (isHotType<T>()) {
         touch(twoShotAllreduceKernel<T, 2, 4>);
@@ -263,6 +320,13 @@ void preloadAllreduceKernels() {
   cudaGetLastError();
 }
 
+bool& oneShotPushFlag() {
+  static bool v = true;
+  return v;
+}
+bool oneShotPushEnabled() { return oneShotPushFlag(); }
+void setOneShotPush(bool on) { oneShotPushFlag() = on; }
+
 void launchBarrier(const CommArgs& a, cudaStream_t stream) {
   barrierKernel<<<1, 32, 0, stream>>>(a);
 }
@@ -270,11 +334,20 @@ void launchBarrier(const CommArgs& a, cudaStream_t stream) {
 void launchOneShotAllreduce(const CommArgs& a, const void* in, void* out, size_t count, DataType dt, ReduceOp op,
                             const PeerPtrs& stage, size_t halfBytes, int blocks, cudaStream_t stream) {
   const bool vectorOk = (reinterpret_cast<uintptr_t>(in) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+  // Push while every rank's copy fits a slot (half / P), else pull.
+  const size_t slotBytes = (halfBytes / static_cast<size_t>(a.nranks)) / 16 * 16;
+  const bool push = count * elementSize(dt) <= slotBytes && oneShotPushEnabled();
   dispatchType(dt, [&](auto tag) {
     using T = decltype(tag);
-    oneShotAllreduceKernel<T><<<blocks, kThreads, 0, stream>>>(a, static_cast<const T*>(in), static_cast<T*>(out),
-                                                               count, static_cast<DevOp>(op), stage, halfBytes,
-                                                               vectorOk);
+    if (push) {
+      oneShotPushAllreduceKernel<T><<<blocks, kThreads, 0, stream>>>(a, static_cast<const T*>(in), static_cast<T*>(out),
+                                                                     count, static_cast<DevOp>(op), stage, halfBytes,
+                                                                     slotBytes, vectorOk);
+    } else {
+      oneShotAllreduceKernel<T><<<blocks, kThreads, 0, stream>>>(a, static_cast<const T*>(in), static_cast<T*>(out),
+                                                                 count, static_cast<DevOp>(op), stage, halfBytes,
+                                                                 vectorOk);
+    }
   });
 }
 

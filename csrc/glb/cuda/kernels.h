@@ -22,6 +22,8 @@ void launchOneShotAllreduce(const CommArgs& a, const void* in, void* out, size_t
 void launchTwoShotAllreduce(const CommArgs& a, const PeerPtrs& bufs, size_t count, DataType dt, ReduceOp op,
                             bool vectorOk, int blocks, cudaStream_t stream);
 bool nvlsSupports(DataType dt, ReduceOp op);
+void setOneShotPush(bool on);  // tuning / A-B testing of the push flavour of one-shot
+bool oneShotPushEnabled();
 void launchNvlsAllreduce(const CommArgs& a, void* mcPtr, const PeerPtrs& bufs, size_t count, DataType dt, int blocks,
                          cudaStream_t stream);
 

@@ -29,6 +29,9 @@ def main():
     ap.add_argument("--max-elements", type=int, default=100_000_000)
     ap.add_argument("--variants", default="one_shot,two_shot,nvls,staged,ring_chunked,halving_doubling,bcube,nccl")
     ap.add_argument("--blocks", default="")
+    ap.add_argument("--sizes", default="", help="comma separated element counts (default: built-in sweep)")
+    ap.add_argument("--tune-blocks", default="", help="e.g. 32,64,128: extra pass over --tune-sizes per block count")
+    ap.add_argument("--tune-sizes", default="262144,4000000,100000000")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     local = int(os.environ.get("LOCAL_RANK", 0))
@@ -60,6 +63,8 @@ def main():
         n *= 10
     sizes = sorted(set(sizes + [x for x in (2048, 16384, 65536, 262144, 524288, 2_000_000, 5_000_000, 30_000_000)
                                 if x <= args.max_elements]))
+    if args.sizes:
+        sizes = [int(x) for x in args.sizes.split(",")]
     rows = []
     dt_code = {torch.float32: 5, torch.float16: 7, torch.bfloat16: 8}[dtype]
 
@@ -135,10 +140,32 @@ def main():
         del sym, plain, reg
         torch.cuda.synchronize()
         gb.barrier(ctx)
+    tune = []
+    if args.tune_blocks:
+        for n in [int(x) for x in args.tune_sizes.split(",")]:
+            nbytes = n * es
+            sym = cc.empty(n, dtype)
+            sym.fill_(1)
+            reg = torch.ones(n, dtype=dtype, device="cuda")
+            cc.register(reg)
+            for nb in [int(x) for x in args.tune_blocks.split(",")]:
+                gb._C.cuda.set_tuning({"max_blocks": nb, "one_shot_blocks": min(nb, 32)})
+                row = {"elements": n, "bytes": nbytes, "blocks": nb}
+                iters = 20 if nbytes < (64 << 20) else 8
+                if nbytes <= (256 << 10):
+                    row["one_shot"] = round(timed(lambda: cc.allreduce(reg, algo="one_shot", stream=stream), iters)[0], 2)
+                row["two_shot"] = round(timed(lambda: cc.allreduce(reg, algo="two_shot", stream=stream), iters)[0], 2)
+                if cc.nvls_available():
+                    row["nvls"] = round(timed(lambda: cc.allreduce(sym, algo="nvls", stream=stream), iters)[0], 2)
+                tune.append(row)
+                if rank == 0:
+                    print("TUNE", json.dumps(row), flush=True)
+            torch.cuda.synchronize()
+            gb.barrier(ctx)
     if rank == 0 and args.out:
         os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
         with open(args.out, "w") as f:
-            json.dump({"world": world, "dtype": args.dtype, "describe": cc.describe(), "rows": rows}, f, indent=1)
+            json.dump({"world": world, "dtype": args.dtype, "describe": cc.describe(), "rows": rows, "tune": tune}, f, indent=1)
     torch.cuda.synchronize()
     gb.barrier(ctx)
     ctx.close_connections()

@@ -120,6 +120,7 @@ def run_ours(args):
     store = gb.FileStore(rendezvous_dir("ours"))
     ctx = gb.init_context(rank, world, store=store, device=gb.create_device("127.0.0.1"), timeout_ms=120000)
     inputs = 2 if world == 1 else 1
+    cc = gcu.CudaContext(ctx, local, stage_bytes=64 << 20)
     stream = torch.cuda.Stream()
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > L2
 
@@ -133,8 +134,15 @@ def run_ours(args):
         torch.cuda.synchronize()
         gb.barrier(ctx)
 
-    def make(elements):
-        ts = [torch.empty(elements, dtype=torch.float32, device=dev) for _ in range(inputs)]
+    def make(elements, symmetric=True):
+        # The harness owns the buffers (as the reference's benchmark does). By default they
+        # come from the library's symmetric allocator: peer-mapped and, on >2 GPUs, bound to
+        # an NVSwitch multicast object so the reduction can run inside the switch. Plain
+        # cudaMalloc'ed tensors (symmetric=False) are registered through cudaIpc instead.
+        if symmetric:
+            ts = [cc.empty(elements, torch.float32) for _ in range(inputs)]
+        else:
+            ts = [torch.empty(elements, dtype=torch.float32, device=dev) for _ in range(inputs)]
         algo = gcu.CudaAllreduceRingChunked(ctx, ts, streams=[stream] * inputs)
         return ts, algo
 
@@ -214,6 +222,39 @@ def run_ours(args):
     e2e_val = e2e_algbw * 2 * (world - 1) / world if world > 1 else e2e_algbw
     del hin, hout, ts, algo
 
+    # ---- same size on plain cudaMalloc'ed buffers (cudaIpc-registered) and the NCCL comparator ----
+    def time_k(fn):
+        for _ in range(3):
+            fn()
+        sync_all()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        for _ in range(args.steps):
+            fn()
+        b.record(stream)
+        stream.synchronize()
+        sync_all()
+        return float(host_max([a.elapsed_time(b)])[0]) / args.steps
+
+    extra = {}
+    if world > 1:
+        pts, palgo = make(E, symmetric=False)
+        with torch.cuda.stream(stream):
+            fill(pts, E)
+        pms = time_k(palgo.run)
+        extra["plain_cudamalloc_buffers"] = {"ms_per_step": round(pms, 5), "variant": palgo.resolved_algo(),
+                                             "busbw_gbs": round(size_bytes / (pms * 1e-3) / 1e9 * 2 * (world - 1) / world, 3)}
+        try:
+            nccl = gb._C.cuda.NcclComm.init_rank(ctx, local)
+            ptr = pts[0].data_ptr()
+            nms = time_k(lambda: nccl.allreduce(ptr, ptr, E, int(gb.DataType.FLOAT32), 1, stream.cuda_stream))
+            extra["nccl_comparator"] = {"ms_per_step": round(nms, 5), "version": gb._C.cuda.nccl_version(),
+                                        "busbw_gbs": round(size_bytes / (nms * 1e-3) / 1e9 * 2 * (world - 1) / world, 3)}
+            del nccl
+        except Exception as e:  # noqa: BLE001
+            extra["nccl_comparator"] = {"unavailable": str(e)[:200]}
+        del pts, palgo
+
     # ---- latency sweep: per-iteration events, L2 flushed between iterations ----------------
     sweep = []
     if not args.no_sweep:
@@ -258,6 +299,7 @@ def run_ours(args):
             "config": {"model": "cuda_allreduce_ring_chunked", "elements": E, "bytes_per_gpu": size_bytes,
                        "inputs_per_rank": inputs, "global_batch": world * inputs, "seq_len": E,
                        "parallelism": f"allreduce x{world}", "kernel_variant": resolved,
+                       "buffers": "library symmetric allocator (peer-mapped; NVLS multicast-bound when >2 GPUs)",
                        "l2": "inputs larger than L2 (400 MB > 126 MB) for the headline; 256 MB flush between sweep iterations",
                        "timing": "CUDA events on the launching stream, max over ranks"},
             "algbw_gbs": round(algbw, 3), "busbw_gbs": round(busbw, 3) if busbw else None,
@@ -267,6 +309,7 @@ def run_ours(args):
             "e2e": {"value": round(e2e_val, 3), "unit": "GB/s", "ms_per_step": round(e2e_ms, 4),
                     "h2d_bytes_per_step": size_bytes * inputs, "d2h_bytes_per_step": size_bytes},
             "gpu_launches": int(launches),
+            **extra,
             "sweep": sweep,
         }
         print(json.dumps(out), flush=True)

@@ -61,13 +61,14 @@ bool peerPathUsable(const std::shared_ptr<Context>& ctx, Workspace ws) {
 }
 }  // namespace
 
-std::shared_ptr<PeerContext> peerContextFor(const std::shared_ptr<Context>& ctx, int device) {
+std::shared_ptr<PeerContext> peerContextFor(const std::shared_ptr<Context>& ctx, int device,
+                                            const PeerOptions& optsIfCreated) {
   // The PeerContext is an attachment of the context: it is shared by every algorithm
   // built on that context and dies with it (or at closeConnections()).
   const std::string key = strcat_all("cuda.peer.", device);
   if (auto existing = ctx->getAttachment(key)) return std::static_pointer_cast<PeerContext>(existing);
   // Construction is collective and may block on peers.
-  auto pc = std::make_shared<PeerContext>(ctx, device);
+  auto pc = std::make_shared<PeerContext>(ctx, device, optsIfCreated);
   ctx->setAttachment(key, pc);
   return pc;
 }
@@ -112,7 +113,7 @@ CudaAllreduceCore::CudaAllreduceCore(std::shared_ptr<Context> ctx, std::vector<v
     auto pc = peerContextFor(ctx_, dev0);
     if (pc->peerAccessEverywhere()) {
       pc_ = pc;
-      reg_ = pc_->registerBuffer(ptrs_[0], count_ * elementSize(dt_));
+      reg_ = pc_->resolveBuffer(ptrs_[0], count_ * elementSize(dt_), &regOffset_);
       if (isLiteral(algo_) && count_ > 0) {
         const size_t es = elementSize(dt_);
         const size_t pack = 16 / es;
@@ -153,7 +154,7 @@ AllreduceAlgo CudaAllreduceCore::resolvedAlgo() const {
   if (!pc_) return AllreduceAlgo::AUTO;
   if (literal_) return algo_;
   if (algo_ != AllreduceAlgo::AUTO) return algo_;
-  return chooseAllreduce(*pc_, count_ * elementSize(dt_), dt_, op_, true, reg_ && reg_->mc != nullptr);
+  return chooseAllreduce(*pc_, count_ * elementSize(dt_), dt_, op_, true, reg_ && reg_->mc != nullptr && regOffset_ % 16 == 0);
 }
 
 void CudaAllreduceCore::run() {
@@ -180,13 +181,13 @@ void CudaAllreduceCore::run() {
       const int blocks = std::max(1, std::min<int>({pc_->maxBlocks(), tuning().maxBlocks,
                                                     static_cast<int>(vecs / kThreads) + 1}));
       pc_->launchGuard();
-      launchSchedule(pc_->comm(), reg_->ptrs(), pc_->stagePtrs(pc_->stageBytes() / 2), literal_->deviceTable,
-                     static_cast<int>(literal_->schedule.steps.size()), dt_, op_, reg_->vectorOk, blocks, *s0);
+      launchSchedule(pc_->comm(), reg_->ptrsAt(regOffset_), pc_->stagePtrs(pc_->stageBytes() / 2), literal_->deviceTable,
+                     static_cast<int>(literal_->schedule.steps.size()), dt_, op_, reg_->vectorOk && regOffset_ % 16 == 0, blocks, *s0);
       noteLaunch();
       cudaError_t le = cudaGetLastError();
       if (le != cudaSuccess) GLB_THROW(Exception, "schedule kernel launch failed: ", cudaGetErrorString(le));
     } else if (pc_) {
-      allreduce(*pc_, *reg_, 0, count_, dt_, op_, algo_, *s0);
+      allreduce(*pc_, *reg_, regOffset_, count_, dt_, op_, algo_, *s0);
     } else {
       // Host workspace: D2H, host collective over the transport, H2D.
       s0.copyAsync(hostScratch_, ptrs_[0], bytes);
@@ -238,7 +239,7 @@ CudaBroadcastCore::CudaBroadcastCore(std::shared_ptr<Context> ctx, std::vector<v
     auto pc = peerContextFor(ctx_, streams_[idx].getDeviceID());
     if (pc->peerAccessEverywhere()) {
       pc_ = pc;
-      reg_ = pc_->registerBuffer(ptrs_[idx], count_ * elementSize(dt_));
+      reg_ = pc_->resolveBuffer(ptrs_[idx], count_ * elementSize(dt_), &regOffset_);
     }
   }
   if (ctx_->size > 1 && !pc_) {
@@ -259,7 +260,7 @@ void CudaBroadcastCore::run() {
   DeviceGuard g(s.getDeviceID());
   if (ctx_->size > 1) {
     if (pc_) {
-      broadcast(*pc_, *reg_, 0, bytes, root_, *s);
+      broadcast(*pc_, *reg_, regOffset_, bytes, root_, *s);
     } else {
       if (isRoot) {
         s.copyAsync(hostScratch_, ptrs_[idx], bytes);

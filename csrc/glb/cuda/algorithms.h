@@ -45,7 +45,8 @@ namespace cuda {
 enum class Workspace { PEER, HOST };
 
 // PeerContext bound to (context, device); created collectively on first use.
-std::shared_ptr<PeerContext> peerContextFor(const std::shared_ptr<Context>& ctx, int device);
+std::shared_ptr<PeerContext> peerContextFor(const std::shared_ptr<Context>& ctx, int device,
+                                            const PeerOptions& optsIfCreated = PeerOptions());
 void releasePeerContexts(const std::shared_ptr<Context>& ctx);
 // The variant a reference-named class runs: AUTO (per-size selection) unless literal
 // schedules are requested with GLB_CUDA_LITERAL_SCHEDULES=1.
@@ -72,6 +73,7 @@ class CudaAllreduceCore {
   std::vector<CudaStream> streams_;
   std::shared_ptr<PeerContext> pc_;
   std::shared_ptr<PeerBuffer> reg_;
+  size_t regOffset_ = 0;
   void* hostScratch_ = nullptr;  // pinned, host workspace only
   struct Literal;
   std::unique_ptr<Literal> literal_;
@@ -95,6 +97,7 @@ class CudaBroadcastCore {
   std::vector<CudaStream> streams_;
   std::shared_ptr<PeerContext> pc_;
   std::shared_ptr<PeerBuffer> reg_;
+  size_t regOffset_ = 0;
   void* hostScratch_ = nullptr;
 };
 

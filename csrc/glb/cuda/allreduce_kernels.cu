@@ -160,7 +160,7 @@ twoShotAllreduceKernel(CommArgs a, PeerPtrs bufs, size_t count, DevOp op, bool v
   const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
 
   // Everybody's kernel has started => everybody's input is final.
-  blockBarrier(a, e + 1);
+  blockBarrier<false>(a, e + 1);
 
   const size_t nvec = vectorOk ? count / PT::kElems : 0;
   size_t vb, ve;
@@ -231,7 +231,7 @@ nvlsAllreduceKernel(CommArgs a, char* mcBase, PeerPtrs bufs, size_t count) {
   const uint32_t e = loadEpoch(a);
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
-  blockBarrier(a, e + 1);
+  blockBarrier<false>(a, e + 1);
   const size_t nvec = count / PT::kElems;
   size_t vb, ve;
   shareOf(nvec, a.nranks, a.rank, vb, ve);

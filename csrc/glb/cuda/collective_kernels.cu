@@ -51,7 +51,7 @@ broadcastKernel(CommArgs a, PeerPtrs bufs, char* mc, size_t bytes, int root, int
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
   const int P = a.nranks;
-  blockBarrier(a, e + 1);  // every destination may now be overwritten
+  blockBarrier<false>(a, e + 1);  // every destination may now be overwritten
   uint32_t used = 2;
   if (mode == 0) {
     if (a.rank == root) {
@@ -143,7 +143,7 @@ gatherPushKernel(CommArgs a, const char* __restrict__ in, PeerPtrs outs, char* m
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
   const int P = a.nranks;
-  blockBarrier(a, e + 1);
+  blockBarrier<false>(a, e + 1);
   const size_t off = va.off[a.rank];
   const size_t len = va.len[a.rank];
   const bool v16 = vec && off % 16 == 0;
@@ -258,7 +258,7 @@ reducePullKernel(CommArgs a, PeerPtrs ins, char* mcIn, T* __restrict__ out, EArg
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
   const int P = a.nranks;
-  blockBarrier(a, e + 1);
+  blockBarrier<false>(a, e + 1);
   const size_t off = ea.off[a.rank], len = ea.len[a.rank];
   const bool v16 = vec && (off * sizeof(T)) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0;
   const size_t nvec = v16 ? len / PT::kElems : 0;

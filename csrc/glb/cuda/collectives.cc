@@ -76,7 +76,12 @@ void noteLaunch(unsigned n) { gLaunches.fetch_add(n, std::memory_order_relaxed);
 AllreduceAlgo chooseAllreduce(const PeerContext& pc, size_t bytes, DataType dt, ReduceOp op, bool registered,
                               bool hasMulticast) {
   const auto& t = tuning();
-  if (bytes <= t.oneShotMaxBytes && bytes <= layoutOf(pc).half) return AllreduceAlgo::ONE_SHOT;
+  // One-shot moves (P-1)*S into every GPU, so its break-even shrinks with P. Measured
+  // (profiles/runs/sweep_allreduce_{2,8}gpu_f32.json): ~128 KiB at P=2, ~32 KiB at P=8,
+  // i.e. oneShotMaxBytes (256 KiB) / P.
+  if (bytes <= t.oneShotMaxBytes / static_cast<size_t>(std::max(pc.size, 1)) && bytes <= layoutOf(pc).half) {
+    return AllreduceAlgo::ONE_SHOT;
+  }
   // In-switch reduction moves ~S(1+1/P) per direction against 2S(P-1)/P for two-shot:
   // a win from P = 4 up, a loss at P = 2 (measured: 994 us vs 645 us for 400 MB).
   if (hasMulticast && pc.size > 2 && bytes >= t.nvlsMinBytes && nvlsSupports(dt, op)) return AllreduceAlgo::NVLS;

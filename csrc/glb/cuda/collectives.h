@@ -35,8 +35,8 @@ enum class AllreduceAlgo : int {
 const char* allreduceAlgoName(AllreduceAlgo a);
 
 struct Tuning {
-  size_t oneShotMaxBytes = 256 * 1024;  // <= : one-shot; above: two-shot / NVLS
-  size_t nvlsMinBytes = 512 * 1024;     // >= : NVLS when the buffer has a multicast alias
+  size_t oneShotMaxBytes = 256 * 1024;  // one-shot while bytes <= this / P; above: two-shot / NVLS
+  size_t nvlsMinBytes = 32 * 1024;      // >= : NVLS when the buffer has a multicast alias (and P > 2)
   int maxBlocks = 64;                   // CTAs for the bandwidth kernels (clamped to co-residency cap)
   int oneShotBlocks = 8;
   size_t bcastDirectMaxBytes = 256 * 1024;  // <= : root pushes everything itself

@@ -29,6 +29,9 @@ enum class DevOp : int { SUM = 1, PRODUCT = 2, MAX = 3, MIN = 4 };
 __device__ __forceinline__ void st_release_sys(uint32_t* p, uint32_t v) {
   asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
+__device__ __forceinline__ void st_relaxed_sys(uint32_t* p, uint32_t v) {
+  asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
 __device__ __forceinline__ uint32_t ld_acquire_sys(const uint32_t* p) {
   uint32_t v;
   asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
@@ -43,11 +46,19 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
 // All CTAs with the same blockIdx on every rank rendezvous. Everything the
 // callers wrote before (including stores into peer memory) is visible to every
 // peer's block after it returns (bar.sync + cumulative release/acquire at .sys).
+// kRelease=false is for the FIRST barrier of a kernel that has not written anything a
+// peer will read: "my kernel has started" needs no fence (the inputs were produced by
+// earlier kernels and are already visible system-wide), which saves a MEMBAR.SYS.
+template <bool kRelease = true>
 __device__ __forceinline__ void blockBarrier(const CommArgs& a, uint32_t epoch) {
   __syncthreads();
   if (threadIdx.x < a.nranks) {
     const int peer = threadIdx.x;
-    st_release_sys(&a.sig[peer]->flag[blockIdx.x][a.rank], epoch);
+    if (kRelease) {
+      st_release_sys(&a.sig[peer]->flag[blockIdx.x][a.rank], epoch);
+    } else {
+      st_relaxed_sys(&a.sig[peer]->flag[blockIdx.x][a.rank], epoch);
+    }
     const uint32_t* mine = &a.sig[a.rank]->flag[blockIdx.x][peer];
     while (static_cast<int32_t>(ld_acquire_sys(mine) - epoch) < 0) {
     }

@@ -317,7 +317,52 @@ void* PeerContext::stageMc(size_t byteOffset) const {
   return pool_->mc ? static_cast<char*>(pool_->mc) + stageOffset_ + byteOffset : nullptr;
 }
 
-std::shared_ptr<PeerBuffer> PeerContext::allocSymmetric(size_t bytes) {
+bool PeerContext::agree(bool mine) {
+  auto all = allgatherStruct(static_cast<int>(mine ? 1 : 0));
+  for (int v : all) {
+    if (!v) return false;
+  }
+  return true;
+}
+
+std::shared_ptr<PeerBuffer> PeerContext::resolveBuffer(void* ptr, size_t bytes, size_t* byteOffset) {
+  std::shared_ptr<PeerBuffer> hit;
+  size_t off = 0;
+  {
+    std::lock_guard<std::mutex> g(symMu_);
+    for (auto it = symmetric_.begin(); it != symmetric_.end();) {
+      auto b = it->lock();
+      if (!b) {
+        it = symmetric_.erase(it);
+        continue;
+      }
+      char* base = static_cast<char*>(b->local);
+      char* p = static_cast<char*>(ptr);
+      if (p >= base && p + bytes <= base + b->bytes) {
+        hit = b;
+        off = static_cast<size_t>(p - base);
+      }
+      ++it;
+    }
+  }
+  // Symmetric use needs the same offset everywhere (peer pointers are base + offset).
+  struct Probe {
+    int found;
+    int pad;
+    uint64_t off;
+  } mine{hit ? 1 : 0, 0, off};
+  auto all = allgatherStruct(mine);
+  bool everywhere = true;
+  for (const auto& x : all) everywhere = everywhere && x.found && x.off == all[0].off;
+  if (everywhere && hit) {
+    *byteOffset = off;
+    return hit;
+  }
+  *byteOffset = 0;
+  return registerBuffer(ptr, bytes);
+}
+
+std::shared_ptr<PeerBuffer> PeerContext::allocSymmetricImpl(size_t bytes) {
   GLB_ENFORCE(peerOk_ || size == 1, "allocSymmetric: peers are not all P2P-reachable from this device");
   DeviceGuard g(device);
   if (vmm_) {
@@ -341,6 +386,13 @@ std::shared_ptr<PeerBuffer> PeerContext::allocSymmetric(size_t bytes) {
     nvlsPossible_ = false;
   }
   return allocIpc(bytes);
+}
+
+std::shared_ptr<PeerBuffer> PeerContext::allocSymmetric(size_t bytes) {
+  auto b = allocSymmetricImpl(bytes);
+  std::lock_guard<std::mutex> g(symMu_);
+  symmetric_.push_back(b);
+  return b;
 }
 
 namespace {

@@ -106,6 +106,12 @@ class PeerContext : public std::enable_shared_from_this<PeerContext> {
   // ---- collective calls: every rank, same order ------------------------------------
   std::shared_ptr<PeerBuffer> allocSymmetric(size_t bytes);
   std::shared_ptr<PeerBuffer> registerBuffer(void* ptr, size_t bytes);
+  // Collective: true iff `mine` is true on every rank.
+  bool agree(bool mine);
+  // Resolve [ptr, ptr+bytes) for zero-copy use: if it lies inside one of this context's
+  // symmetric allocations ON EVERY RANK the owning PeerBuffer (+ byte offset) is returned
+  // (NVLS-capable); otherwise the range is registered through cudaIpc. Collective.
+  std::shared_ptr<PeerBuffer> resolveBuffer(void* ptr, size_t bytes, size_t* byteOffset);
   void hostBarrier();
   // Call right before launching a kernel that waits for its peers. When several ranks
   // share one GPU (threads-as-ranks tests) a peer that is still inside a device-
@@ -128,6 +134,7 @@ class PeerContext : public std::enable_shared_from_this<PeerContext> {
   void exchangeTopology();
   template <typename T>
   std::vector<T> allgatherStruct(const T& mine);
+  std::shared_ptr<PeerBuffer> allocSymmetricImpl(size_t bytes);
   std::shared_ptr<PeerBuffer> allocVmm(size_t bytes, bool wantMc);
   std::shared_ptr<PeerBuffer> allocIpc(size_t bytes);
   std::shared_ptr<PeerBuffer> shareIpc(void* ptr, size_t bytes, bool ownsAllocation);
@@ -144,6 +151,8 @@ class PeerContext : public std::enable_shared_from_this<PeerContext> {
   uint32_t tagSeq_ = 0;
   std::unique_ptr<FdChannel> fdChannel_;
   std::shared_ptr<PeerBuffer> pool_;
+  std::mutex symMu_;
+  std::vector<std::weak_ptr<PeerBuffer>> symmetric_;  // live allocSymmetric() results
   size_t stageOffset_ = 0;
   size_t stageBytes_ = 0;
   CommArgs comm_;

@@ -110,10 +110,15 @@ void registerCudaAlgorithms(py::module_& m) {
     return out;
   }, py::arg("name"), py::arg("rank"), py::arg("size"), py::arg("count"), py::arg("base") = 2, py::arg("pack") = 4);
 
-  m.def("peer_context_for", [](std::shared_ptr<Context> ctx, int device) {
+  m.def("peer_context_for", [](std::shared_ptr<Context> ctx, int device, size_t stageBytes, bool useVmm, bool useNvls) {
+    PeerOptions o;
+    if (stageBytes > 0) o.stageBytes = stageBytes;
+    o.useVmm = useVmm;
+    o.useNvls = useNvls;
     py::gil_scoped_release nogil;
-    return peerContextFor(ctx, device);
-  });
+    return peerContextFor(ctx, device, o);
+  }, py::arg("ctx"), py::arg("device"), py::arg("stage_bytes") = 0, py::arg("use_vmm") = true, py::arg("use_nvls") = true,
+     "The PeerContext attached to (ctx, device); created collectively on first use with the given options.");
   m.def("release_peer_contexts", [](std::shared_ptr<Context> ctx) { releasePeerContexts(ctx); });
 
   // ---- data movement: registered (`*_reg`) and staged (plain pointer) flavours ------------

@@ -66,7 +66,10 @@ class CudaContext:
         self.ctx = ctx
         self.device = int(device)
         with torch.cuda.device(self.device):
-            self.pc = _cu.PeerContext(ctx, self.device, stage_bytes, use_vmm, use_nvls)
+            # One PeerContext per (context, device), shared with the old-style CUDA classes
+            # (it is an attachment of the context): symmetric tensors allocated here are
+            # recognised by CudaAllreduce* / CudaBroadcastOneToAll and get the NVLS path.
+            self.pc = _cu.peer_context_for(ctx, self.device, stage_bytes, use_vmm, use_nvls)
         self.rank, self.size = self.pc.rank, self.pc.size
         self._reg: Dict[int, Tuple[Any, int]] = {}  # base ptr -> (PeerBuffer, nbytes)
         self._keep: List[Any] = []

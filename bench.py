@@ -333,7 +333,10 @@ def run_reference(args):
             print(json.dumps({"impl": "reference", "unavailable": "baseline/_ref/bin/benchmark_cuda missing "
                               "(pip cannot install the CMake-only reference; build it with baseline/build_reference.sh)"}))
         return
-    inputs = 2 if world == 1 else 1
+    # The reference cannot place two inputs on one GPU (its local reduce goes through NCCL,
+    # which needs unique devices: nccl.cu:111-116), so its 1-GPU run uses one buffer and
+    # does D2H + H2D of it; our 1-GPU run reduces and re-broadcasts two buffers (more work).
+    inputs = 1
     base = rendezvous_dir("ref")
     env = dict(os.environ)
     env["CUDA_VISIBLE_DEVICES"] = str(local)

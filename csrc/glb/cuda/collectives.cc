@@ -105,7 +105,10 @@ void allreduce(PeerContext& pc, const PeerBuffer& buf, size_t byteOffset, size_t
   GLB_ENFORCE(op != ReduceOp::CUSTOM, "custom reductions run on the host path only");
   DeviceGuard g(pc.device);
   char* local = static_cast<char*>(buf.local) + byteOffset;
-  if (pc.size == 1) return;  // single rank: the buffer already holds the result
+  // Single rank: the buffer already holds the result. GLB_CUDA_FORCE_KERNELS=1 still
+  // launches the kernel (loopback on local memory) so it can be profiled with Nsight
+  // Compute, which cannot replay kernels that wait for a peer.
+  if (pc.size == 1 && !envFlag("CUDA_FORCE_KERNELS", false)) return;
   const bool hasMc = buf.mc != nullptr && byteOffset % 16 == 0;
   if (algo == AllreduceAlgo::AUTO) algo = chooseAllreduce(pc, bytes, dt, op, true, hasMc);
   pc.launchGuard();

@@ -17,25 +17,57 @@ __device__ __forceinline__ void shareOfB(size_t n, int parts, int r, size_t& beg
   end = begin + base + (static_cast<size_t>(r) < rem ? 1 : 0);
 }
 
-// Copy `bytes` from src to dst with the whole grid (both 16-byte aligned when vec).
-__device__ __forceinline__ void gridCopy(char* dst, const char* src, size_t bytes, bool vec, size_t tid,
-                                         size_t nthreads) {
-  const size_t nvec = vec ? bytes / 16 : 0;
+template <typename W>
+__device__ __forceinline__ void gridCopyWords(char* dst, const char* src, size_t bytes, size_t tid, size_t nthreads) {
+  const size_t n = bytes / sizeof(W);
   constexpr int U = 4;
-  for (size_t v0 = tid; v0 < nvec; v0 += nthreads * U) {
-    Pack16 p[U];
+  for (size_t i0 = tid; i0 < n; i0 += nthreads * U) {
+    W w[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      const size_t v = v0 + u * nthreads;
-      if (v < nvec) p[u] = ld128_stream(src + v * 16);
+      const size_t i = i0 + u * nthreads;
+      if (i < n) w[u] = reinterpret_cast<const W*>(src)[i];
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      const size_t v = v0 + u * nthreads;
-      if (v < nvec) st128_stream(dst + v * 16, p[u]);
+      const size_t i = i0 + u * nthreads;
+      if (i < n) reinterpret_cast<W*>(dst)[i] = w[u];
     }
   }
-  for (size_t i = nvec * 16 + tid; i < bytes; i += nthreads) dst[i] = src[i];
+  for (size_t i = n * sizeof(W) + tid; i < bytes; i += nthreads) dst[i] = src[i];
+}
+
+// Copy `bytes` from src to dst with the whole grid, using the widest access both
+// pointers are aligned for (16 B packs when `vec`, else 8 / 4 / 2 / 1 bytes).
+__device__ __forceinline__ void gridCopy(char* dst, const char* src, size_t bytes, bool vec, size_t tid,
+                                         size_t nthreads) {
+  const uintptr_t both = reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src);
+  if (vec && both % 16 == 0) {
+    const size_t nvec = bytes / 16;
+    constexpr int U = 4;
+    for (size_t v0 = tid; v0 < nvec; v0 += nthreads * U) {
+      Pack16 p[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const size_t v = v0 + u * nthreads;
+        if (v < nvec) p[u] = ld128_stream(src + v * 16);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const size_t v = v0 + u * nthreads;
+        if (v < nvec) st128_stream(dst + v * 16, p[u]);
+      }
+    }
+    for (size_t i = nvec * 16 + tid; i < bytes; i += nthreads) dst[i] = src[i];
+  } else if (both % 8 == 0) {
+    gridCopyWords<unsigned long long>(dst, src, bytes, tid, nthreads);
+  } else if (both % 4 == 0) {
+    gridCopyWords<unsigned int>(dst, src, bytes, tid, nthreads);
+  } else if (both % 2 == 0) {
+    gridCopyWords<unsigned short>(dst, src, bytes, tid, nthreads);
+  } else {
+    for (size_t i = tid; i < bytes; i += nthreads) dst[i] = src[i];
+  }
 }
 
 }  // namespace
@@ -57,9 +89,22 @@ broadcastKernel(CommArgs a, PeerPtrs bufs, char* mc, size_t bytes, int root, int
     if (a.rank == root) {
       const char* src = static_cast<const char*>(bufs.p[root]);
       const size_t nvec = vec ? bytes / 16 : 0;
-      for (size_t v = tid; v < nvec; v += nthreads) {
-        const Pack16 p = ld128_stream(src + v * 16);
-        for (int i = 1; i < P; i++) st128_stream(static_cast<char*>(bufs.p[(root + i) % P]) + v * 16, p);
+      constexpr int U = 4;
+      for (size_t v0 = tid; v0 < nvec; v0 += nthreads * U) {
+        Pack16 p[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const size_t v = v0 + u * nthreads;
+          if (v < nvec) p[u] = ld128_stream(src + v * 16);
+        }
+        for (int i = 1; i < P; i++) {
+          char* dst = static_cast<char*>(bufs.p[(root + i) % P]);
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const size_t v = v0 + u * nthreads;
+            if (v < nvec) st128_stream(dst + v * 16, p[u]);
+          }
+        }
       }
       for (size_t i = nvec * 16 + tid; i < bytes; i += nthreads) {
         const char c = src[i];
@@ -157,9 +202,22 @@ gatherPushKernel(CommArgs a, const char* __restrict__ in, PeerPtrs outs, char* m
       for (int r = 0; r < P; r++) (static_cast<char*>(outs.p[r]) + off)[i] = c;
     }
   } else {
-    for (size_t v = tid; v < nvec; v += nthreads) {
-      const Pack16 p = ld128_stream(in + v * 16);
-      for (int i = 0; i < P; i++) st128_stream(static_cast<char*>(outs.p[(a.rank + i) % P]) + off + v * 16, p);
+    constexpr int U = 4;
+    for (size_t v0 = tid; v0 < nvec; v0 += nthreads * U) {
+      Pack16 p[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const size_t v = v0 + u * nthreads;
+        if (v < nvec) p[u] = ld128_stream(in + v * 16);
+      }
+      for (int i = 0; i < P; i++) {
+        char* dst = static_cast<char*>(outs.p[(a.rank + i) % P]) + off;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const size_t v = v0 + u * nthreads;
+          if (v < nvec) st128_stream(dst + v * 16, p[u]);
+        }
+      }
     }
     for (size_t i = nvec * 16 + tid; i < len; i += nthreads) {
       const char c = in[i];
@@ -249,7 +307,7 @@ struct EArgs {
   size_t len[kMaxRanks];
 };
 
-template <typename T>
+template <typename T, int NR, int UNROLL>
 __global__ void __launch_bounds__(kThreads)
 reducePullKernel(CommArgs a, PeerPtrs ins, char* mcIn, T* __restrict__ out, EArgs ea, DevOp op, bool vec,
                  bool useMc) {
@@ -257,7 +315,7 @@ reducePullKernel(CommArgs a, PeerPtrs ins, char* mcIn, T* __restrict__ out, EArg
   const uint32_t e = loadEpoch(a);
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
-  const int P = a.nranks;
+  const int P = NR > 0 ? NR : a.nranks;
   blockBarrier<false>(a, e + 1);
   const size_t off = ea.off[a.rank], len = ea.len[a.rank];
   const bool v16 = vec && (off * sizeof(T)) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0;
@@ -266,23 +324,52 @@ reducePullKernel(CommArgs a, PeerPtrs ins, char* mcIn, T* __restrict__ out, EArg
   if (useMc && v16) {
     if constexpr (std::is_same<T, float>::value || std::is_same<T, __half>::value ||
                   std::is_same<T, __nv_bfloat16>::value) {
-      for (size_t v = tid; v < nvec; v += nthreads) {
-        st128(reinterpret_cast<char*>(out) + v * 16, Multimem<T>::ldReduceAdd(mcIn + byteOff + v * 16));
+      constexpr int U = 4;
+      for (size_t v0 = tid; v0 < nvec; v0 += nthreads * U) {
+        Pack16 r[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const size_t v = v0 + u * nthreads;
+          if (v < nvec) r[u] = Multimem<T>::ldReduceAdd(mcIn + byteOff + v * 16);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const size_t v = v0 + u * nthreads;
+          if (v < nvec) st128(reinterpret_cast<char*>(out) + v * 16, r[u]);
+        }
       }
     }
   } else {
-    for (size_t v = tid; v < nvec; v += nthreads) {
-      Pack16 p[kMaxRanks];
+    constexpr int kSlots = NR > 0 ? NR : kMaxRanks;
+    const char* peer[kSlots];
 #pragma unroll
-      for (int i = 0; i < kMaxRanks; i++) {
-        if (i < P) p[i] = ld128_stream(static_cast<const char*>(ins.p[(a.rank + i) % P]) + byteOff + v * 16);
-      }
-      typename PT::AccPack acc = PT::widen(p[0]);
+    for (int i = 0; i < kSlots; i++) {
+      peer[i] = i < P ? static_cast<const char*>(ins.p[(a.rank + i) % P]) + byteOff : nullptr;
+    }
+    for (size_t v0 = tid; v0 < nvec; v0 += nthreads * UNROLL) {
+      Pack16 p[UNROLL][kSlots];
 #pragma unroll
-      for (int i = 1; i < kMaxRanks; i++) {
-        if (i < P) PT::combine(acc, p[i], op);
+      for (int u = 0; u < UNROLL; u++) {
+        const size_t v = v0 + static_cast<size_t>(u) * nthreads;
+        if (v < nvec) {
+#pragma unroll
+          for (int i = 0; i < kSlots; i++) {
+            if (i < P) p[u][i] = ld128_stream(peer[i] + v * 16);
+          }
+        }
       }
-      st128(reinterpret_cast<char*>(out) + v * 16, PT::narrow(acc));
+#pragma unroll
+      for (int u = 0; u < UNROLL; u++) {
+        const size_t v = v0 + static_cast<size_t>(u) * nthreads;
+        if (v < nvec) {
+          typename PT::AccPack acc = PT::widen(p[u][0]);
+#pragma unroll
+          for (int i = 1; i < kSlots; i++) {
+            if (i < P) PT::combine(acc, p[u][i], op);
+          }
+          st128(reinterpret_cast<char*>(out) + v * 16, PT::narrow(acc));
+        }
+      }
     }
   }
   for (size_t i = nvec * PT::kElems + tid; i < len; i += nthreads) {
@@ -294,6 +381,24 @@ reducePullKernel(CommArgs a, PeerPtrs ins, char* mcIn, T* __restrict__ out, EArg
   retire(a, 2, 0);
 }
 
+namespace {
+template <typename T>
+void launchReducePullT(const CommArgs& a, const PeerPtrs& ins, char* mc, void* out, const EArgs& ea, DevOp dop, bool vec,
+                       bool useMc, int blocks, cudaStream_t stream) {
+  constexpr bool hot = std::is_same<T, float>::value || std::is_same<T, __half>::value ||
+                       std::is_same<T, __nv_bfloat16>::value;
+  if constexpr (hot) {
+    switch (a.nranks) {
+      case 2: reducePullKernel<T, 2, 4><<<blocks, kThreads, 0, stream>>>(a, ins, mc, static_cast<T*>(out), ea, dop, vec, useMc); return;
+      case 4: reducePullKernel<T, 4, 2><<<blocks, kThreads, 0, stream>>>(a, ins, mc, static_cast<T*>(out), ea, dop, vec, useMc); return;
+      case 8: reducePullKernel<T, 8, 2><<<blocks, kThreads, 0, stream>>>(a, ins, mc, static_cast<T*>(out), ea, dop, vec, useMc); return;
+      default: break;
+    }
+  }
+  reducePullKernel<T, 0, 1><<<blocks, kThreads, 0, stream>>>(a, ins, mc, static_cast<T*>(out), ea, dop, vec, useMc);
+}
+}  // namespace
+
 void launchReducePull(const CommArgs& a, const PeerPtrs& ins, void* mcIn, void* out, const size_t* elemOff,
                       const size_t* elemLen, DataType dt, ReduceOp op, bool vec, bool useMc, int blocks,
                       cudaStream_t stream) {
@@ -304,9 +409,9 @@ void launchReducePull(const CommArgs& a, const PeerPtrs& ins, void* mcIn, void* 
   }
   const DevOp dop = static_cast<DevOp>(op);
   char* mc = static_cast<char*>(mcIn);
-#define GLB_CASE(E, T)                                                                                        \
-  case DataType::E:                                                                                           \
-    reducePullKernel<T><<<blocks, kThreads, 0, stream>>>(a, ins, mc, static_cast<T*>(out), ea, dop, vec, useMc); \
+#define GLB_CASE(E, T)                                                              \
+  case DataType::E:                                                                 \
+    launchReducePullT<T>(a, ins, mc, out, ea, dop, vec, useMc, blocks, stream);     \
     break;
   switch (dt) {
     GLB_CASE(INT8, int8_t)
@@ -333,17 +438,17 @@ void preloadCollectiveKernels() {
   touch(reinterpret_cast<const void*>(broadcastKernel));
   touch(reinterpret_cast<const void*>(gatherPushKernel));
   touch(reinterpret_cast<const void*>(alltoallPushKernel));
-  touch(reinterpret_cast<const void*>(reducePullKernel<int8_t>));
-  touch(reinterpret_cast<const void*>(reducePullKernel<uint8_t>));
-  touch(reinterpret_cast<const void*>(reducePullKernel<int16_t>));
-  touch(reinterpret_cast<const void*>(reducePullKernel<int32_t>));
-  touch(reinterpret_cast<const void*>(reducePullKernel<uint32_t>));
-  touch(reinterpret_cast<const void*>(reducePullKernel<long long>));
-  touch(reinterpret_cast<const void*>(reducePullKernel<unsigned long long>));
-  touch(reinterpret_cast<const void*>(reducePullKernel<float>));
-  touch(reinterpret_cast<const void*>(reducePullKernel<double>));
-  touch(reinterpret_cast<const void*>(reducePullKernel<__half>));
-  touch(reinterpret_cast<const void*>(reducePullKernel<__nv_bfloat16>));
+#define GLB_TOUCH_RP(T) touch(reinterpret_cast<const void*>(reducePullKernel<T, 0, 1>));
+  GLB_TOUCH_RP(int8_t) GLB_TOUCH_RP(uint8_t) GLB_TOUCH_RP(int16_t) GLB_TOUCH_RP(int32_t) GLB_TOUCH_RP(uint32_t)
+  GLB_TOUCH_RP(long long) GLB_TOUCH_RP(unsigned long long) GLB_TOUCH_RP(float) GLB_TOUCH_RP(double)
+  GLB_TOUCH_RP(__half) GLB_TOUCH_RP(__nv_bfloat16)
+#undef GLB_TOUCH_RP
+#define GLB_TOUCH_HOT(T)                                                   \
+  touch(reinterpret_cast<const void*>(reducePullKernel<T, 2, 4>));         \
+  touch(reinterpret_cast<const void*>(reducePullKernel<T, 4, 2>));         \
+  touch(reinterpret_cast<const void*>(reducePullKernel<T, 8, 2>));
+  GLB_TOUCH_HOT(float) GLB_TOUCH_HOT(__half) GLB_TOUCH_HOT(__nv_bfloat16)
+#undef GLB_TOUCH_HOT
   cudaGetLastError();
 }
 

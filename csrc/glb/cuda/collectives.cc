@@ -30,6 +30,7 @@ Tuning& tuning() {
     x.nvlsMinBytes = static_cast<size_t>(envInt("CUDA_NVLS_MIN", static_cast<long>(x.nvlsMinBytes)));
     x.maxBlocks = static_cast<int>(envInt("CUDA_BLOCKS", x.maxBlocks));
     x.oneShotBlocks = static_cast<int>(envInt("CUDA_ONESHOT_BLOCKS", x.oneShotBlocks));
+    x.copyBlocks = static_cast<int>(envInt("CUDA_COPY_BLOCKS", x.copyBlocks));
     setOneShotPush(envFlag("CUDA_ONESHOT_PUSH", true));
     x.bcastDirectMaxBytes = static_cast<size_t>(envInt("CUDA_BCAST_DIRECT_MAX", static_cast<long>(x.bcastDirectMaxBytes)));
     return x;
@@ -221,8 +222,12 @@ StagedOut stagedBulk(const PeerContext& pc, size_t needBytes, const char* what) 
   return s;
 }
 
+// Store-only kernels (broadcast / gather / alltoall pushes) are light on registers, so two
+// CTAs per SM stay co-resident: their cap is 2x the reduce kernels'.
 int bwBlocks(const PeerContext& pc, size_t bytes) {
-  return blocksFor(pc, bytes / 16, 4, tuning().maxBlocks);
+  size_t want = ceilDiv(std::max<size_t>(bytes / 16, 1), static_cast<size_t>(kThreads) * 4);
+  int cap = std::min({tuning().copyBlocks, 2 * pc.maxBlocks(), kMaxBlocks});
+  return std::max(1, static_cast<int>(std::min<size_t>(want, static_cast<size_t>(cap))));
 }
 
 }  // namespace

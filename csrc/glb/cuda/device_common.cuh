@@ -75,13 +75,13 @@ __device__ __forceinline__ void retire(const CommArgs& a, uint32_t barriersUsed,
   __syncthreads();
   if (threadIdx.x == 0) {
     SignalPad* me = a.sig[a.rank];
-    __threadfence();
+    // No fences: the ticket is an L2 atomic (the last CTA sees every earlier arrival) and
+    // the counters are next read by the NEXT launch, after this kernel has retired.
     uint32_t ticket = atomicAdd(&me->done, 1u);
     if (ticket == gridDim.x - 1) {
       me->done = 0;
       me->epoch += barriersUsed;
       me->stageSeq += stagedLaunch;
-      __threadfence();
     }
   }
 }

@@ -115,7 +115,20 @@ broadcastKernel(CommArgs a, PeerPtrs bufs, char* mc, size_t bytes, int root, int
     if (a.rank == root) {
       const char* src = static_cast<const char*>(bufs.p[root]);
       const size_t nvec = bytes / 16;
-      for (size_t v = tid; v < nvec; v += nthreads) multimemSt128(mc + v * 16, ld128_stream(src + v * 16));
+      constexpr int U = 4;
+      for (size_t v0 = tid; v0 < nvec; v0 += nthreads * U) {
+        Pack16 p[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const size_t v = v0 + u * nthreads;
+          if (v < nvec) p[u] = ld128_stream(src + v * 16);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const size_t v = v0 + u * nthreads;
+          if (v < nvec) multimemSt128(mc + v * 16, p[u]);
+        }
+      }
       for (size_t i = nvec * 16 + tid; i < bytes; i += nthreads) {
         const char c = src[i];
         for (int r = 1; r < P; r++) static_cast<char*>(bufs.p[(root + r) % P])[i] = c;

@@ -31,6 +31,7 @@ Tuning& tuning() {
     x.maxBlocks = static_cast<int>(envInt("CUDA_BLOCKS", x.maxBlocks));
     x.oneShotBlocks = static_cast<int>(envInt("CUDA_ONESHOT_BLOCKS", x.oneShotBlocks));
     x.copyBlocks = static_cast<int>(envInt("CUDA_COPY_BLOCKS", x.copyBlocks));
+    x.nvlsReduceScatter = envFlag("CUDA_NVLS_REDUCE_SCATTER", x.nvlsReduceScatter);
     setOneShotPush(envFlag("CUDA_ONESHOT_PUSH", true));
     x.bcastDirectMaxBytes = static_cast<size_t>(envInt("CUDA_BCAST_DIRECT_MAX", static_cast<long>(x.bcastDirectMaxBytes)));
     return x;
@@ -240,7 +241,8 @@ void broadcast(PeerContext& pc, const PeerBuffer& buf, size_t byteOffset, size_t
   DeviceGuard g(pc.device);
   const bool vec = buf.vectorOk && byteOffset % 16 == 0;
   int mode = 0;
-  if (buf.mc != nullptr && vec && bytes >= tuning().bcastDirectMaxBytes) {
+  // multimem.st pays off when the root would otherwise send P-1 copies: P > 2.
+  if (buf.mc != nullptr && vec && pc.size > 2 && bytes >= tuning().bcastDirectMaxBytes) {
     mode = 2;
   } else if (bytes > tuning().bcastDirectMaxBytes && pc.size > 2) {
     mode = 1;
@@ -264,7 +266,7 @@ void broadcast(PeerContext& pc, void* ptr, size_t bytes, int root, cudaStream_t 
     char* p = static_cast<char*>(ptr) + done;
     if (pc.rank == root) GLB_CUDA_CHECK(cudaMemcpyAsync(mine, p, n, cudaMemcpyDeviceToDevice, stream));
     int mode = 0;
-    if (pc.nvlsAvailable() && n >= tuning().bcastDirectMaxBytes) {
+    if (pc.nvlsAvailable() && pc.size > 2 && n >= tuning().bcastDirectMaxBytes) {
       mode = 2;
     } else if (n > tuning().bcastDirectMaxBytes && pc.size > 2) {
       mode = 1;
@@ -300,8 +302,10 @@ void allgatherv(PeerContext& pc, const void* in, const PeerBuffer& out, size_t o
     if (dst != in && off.back() > 0) GLB_CUDA_CHECK(cudaMemcpyAsync(dst, in, off.back(), cudaMemcpyDeviceToDevice, stream));
     return;
   }
-  gatherCommon(pc, in, out.ptrsAt(outOffset), out.mc ? static_cast<char*>(out.mc) + outOffset : nullptr,
-               out.vectorOk && outOffset % 16 == 0, bytesPerRank, -1, stream);
+  // No multicast here: an allgather's bottleneck is what every GPU RECEIVES ((P-1)/P of the
+  // output either way); multimem.st would only relieve the uplink and additionally deliver
+  // each block back to its sender (measured at P=2: 312 GB/s with, 540 GB/s without).
+  gatherCommon(pc, in, out.ptrsAt(outOffset), nullptr, out.vectorOk && outOffset % 16 == 0, bytesPerRank, -1, stream);
 }
 
 void allgatherv(PeerContext& pc, const void* in, void* out, const std::vector<size_t>& bytesPerRank,
@@ -313,7 +317,7 @@ void allgatherv(PeerContext& pc, const void* in, void* out, const std::vector<si
     return;
   }
   auto st = stagedBulk(pc, off.back(), "allgather");
-  gatherCommon(pc, in, st.ptrs, st.mc, true, bytesPerRank, -1, stream);
+  gatherCommon(pc, in, st.ptrs, nullptr, true, bytesPerRank, -1, stream);
   if (off.back() > 0) GLB_CUDA_CHECK(cudaMemcpyAsync(out, st.mine, off.back(), cudaMemcpyDeviceToDevice, stream));
 }
 
@@ -436,7 +440,9 @@ void reducePullCommon(PeerContext& pc, const PeerPtrs& ins, void* mcIn, bool vec
   GLB_ENFORCE(op != ReduceOp::CUSTOM, "custom reductions run on the host path only");
   auto off = prefix(counts);
   const size_t es = elementSize(dt);
-  const bool useMc = mcIn != nullptr && nvlsSupports(dt, op) && counts[pc.rank] * es >= tuning().nvlsMinBytes;
+  // In-switch reduction only for P > 2 (at P = 2 it doubles the uplink traffic).
+  const bool useMc = mcIn != nullptr && pc.size > 2 && tuning().nvlsReduceScatter && nvlsSupports(dt, op) &&
+                     counts[pc.rank] * es >= tuning().nvlsMinBytes;
   pc.launchGuard();
   launchReducePull(pc.comm(), ins, mcIn, out, off.data(), counts.data(), dt, op, vecIn, useMc,
                    blocksFor(pc, counts[pc.rank] * es / 16, 1, tuning().maxBlocks), stream);

@@ -142,6 +142,7 @@ void registerCuda(py::module_& root) {
     if (d.contains("nvls_min_bytes")) t.nvlsMinBytes = d["nvls_min_bytes"].cast<size_t>();
     if (d.contains("max_blocks")) t.maxBlocks = d["max_blocks"].cast<int>();
     if (d.contains("one_shot_blocks")) t.oneShotBlocks = d["one_shot_blocks"].cast<int>();
+    if (d.contains("nvls_reduce_scatter")) t.nvlsReduceScatter = d["nvls_reduce_scatter"].cast<bool>();
     if (d.contains("copy_blocks")) t.copyBlocks = d["copy_blocks"].cast<int>();
     if (d.contains("one_shot_push")) setOneShotPush(d["one_shot_push"].cast<bool>());
   });

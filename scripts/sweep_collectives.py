@@ -116,6 +116,10 @@ def main():
                     inp.fill_(1)
                     out = torch.empty(per, device="cuda")
                     row["ours_us"] = timed(lambda: cc.reduce_scatter(out, inp, [per] * P, stream=stream), iters)
+                    if world > 2 and cc.nvls_available():
+                        gb._C.cuda.set_tuning({"nvls_reduce_scatter": False})
+                        row["ours_p2p_us"] = round(timed(lambda: cc.reduce_scatter(out, inp, [per] * P, stream=stream), iters), 2)
+                        gb._C.cuda.set_tuning({"nvls_reduce_scatter": True})
                     if nccl:
                         i2 = torch.ones(n, device="cuda")
                         row["nccl_us"] = timed(lambda: nccl.reduce_scatter(i2.data_ptr(), out.data_ptr(), per, F32, 1, stream.cuda_stream), iters)

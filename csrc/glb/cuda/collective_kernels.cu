@@ -257,7 +257,7 @@ void launchGatherPush(const CommArgs& a, const void* in, const PeerPtrs& outs, v
 // symmetry of the exchange tables) is where MY chunk lands in rank r's output.
 __global__ void __launch_bounds__(kThreads)
 alltoallPushKernel(CommArgs a, const char* __restrict__ in, PeerPtrs outs, VArgs send, VArgs dstOff, VArgs myRecv,
-                   bool exchange, int onlySrc, bool vec) {
+                   VArgs blk, bool exchange, int onlySrc, bool vec) {
   const uint32_t e = loadEpoch(a);
   const int P = a.nranks;
   // v-variant: publish where I expect each source's chunk; peers read it after the
@@ -265,20 +265,19 @@ alltoallPushKernel(CommArgs a, const char* __restrict__ in, PeerPtrs outs, VArgs
   if (exchange && threadIdx.x < P) a.sig[a.rank]->xchg[threadIdx.x] = myRecv.off[threadIdx.x];
   blockBarrier(a, e + 1);
   if (onlySrc < 0 || onlySrc == a.rank) {
-    // Blocks are dealt round-robin to destinations so all links are busy at once.
-    const int perDst = max(1, static_cast<int>(gridDim.x) / P);
+    // CTAs are dealt to destinations in proportion to the bytes each one gets (the host
+    // fills blk.off = first CTA, blk.len = CTA count per destination), so every link is
+    // busy at once and uneven (v-variant) splits stay balanced. With fewer CTAs than
+    // destinations every CTA walks all destinations.
+    const bool partitioned = blk.len[0] + blk.off[P - 1] > 0 && static_cast<size_t>(gridDim.x) >= static_cast<size_t>(P);
     for (int i = 0; i < P; i++) {
       const int dst = (a.rank + i) % P;
-      // blocks assigned to this destination
-      const int lane = static_cast<int>(blockIdx.x) - i * perDst;
-      const bool mineStrict = static_cast<int>(gridDim.x) >= P;
       size_t tid, nthreads;
-      if (mineStrict) {
-        const bool last = (i == P - 1);
-        const int nb = last ? static_cast<int>(gridDim.x) - i * perDst : perDst;
-        if (lane < 0 || lane >= nb) continue;
-        tid = static_cast<size_t>(lane) * blockDim.x + threadIdx.x;
-        nthreads = static_cast<size_t>(nb) * blockDim.x;
+      if (partitioned) {
+        const size_t b0 = blk.off[dst], nb = blk.len[dst];
+        if (blockIdx.x < b0 || blockIdx.x >= b0 + nb) continue;
+        tid = (blockIdx.x - b0) * blockDim.x + threadIdx.x;
+        nthreads = nb * blockDim.x;
       } else {
         tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
         nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -287,8 +286,7 @@ alltoallPushKernel(CommArgs a, const char* __restrict__ in, PeerPtrs outs, VArgs
       const size_t dofs = exchange ? static_cast<size_t>(*reinterpret_cast<volatile unsigned long long*>(
                                          &a.sig[dst]->xchg[a.rank]))
                                    : dstOff.off[dst];
-      const bool v16 = vec && so % 16 == 0 && dofs % 16 == 0;
-      gridCopy(static_cast<char*>(outs.p[dst]) + dofs, in + so, sl, v16, tid, nthreads);
+      gridCopy(static_cast<char*>(outs.p[dst]) + dofs, in + so, sl, vec, tid, nthreads);
     }
   }
   blockBarrier(a, e + 2);
@@ -307,7 +305,22 @@ void launchAlltoallPush(const CommArgs& a, const void* in, const PeerPtrs& outs,
     rcv.off[i] = (recvOffTable != nullptr && i < a.nranks) ? recvOffTable[i] : 0;
     rcv.len[i] = 0;
   }
-  alltoallPushKernel<<<blocks, kThreads, 0, stream>>>(a, static_cast<const char*>(in), outs, s, d, rcv,
+  // CTA ranges per destination, proportional to payload (at least one each).
+  VArgs blk;
+  for (int i = 0; i < kMaxRanks; i++) blk.off[i] = blk.len[i] = 0;
+  if (blocks >= a.nranks) {
+    size_t total = 0;
+    for (int i = 0; i < a.nranks; i++) total += s.len[i];
+    size_t used = 0;
+    int spare = blocks - a.nranks;
+    for (int i = 0; i < a.nranks; i++) {
+      size_t extra = total > 0 ? static_cast<size_t>(spare) * s.len[i] / total : 0;
+      blk.off[i] = used;
+      blk.len[i] = 1 + extra;
+      used += blk.len[i];
+    }
+  }
+  alltoallPushKernel<<<blocks, kThreads, 0, stream>>>(a, static_cast<const char*>(in), outs, s, d, rcv, blk,
                                                       recvOffTable != nullptr, onlySrc, vec);
 }
 

@@ -247,6 +247,10 @@ void broadcast(PeerContext& pc, const PeerBuffer& buf, size_t byteOffset, size_t
   } else if (bytes > tuning().bcastDirectMaxBytes && pc.size > 2) {
     mode = 1;
   }
+  {
+    long forced = envInt("CUDA_BCAST_MODE", -1);
+    if (forced >= 0 && forced <= 2 && (forced != 2 || (buf.mc != nullptr && vec))) mode = static_cast<int>(forced);
+  }
   const int blocks = bwBlocks(pc, mode == 1 ? bytes / pc.size * 2 : bytes);
   pc.launchGuard();
   launchBroadcast(pc.comm(), buf.ptrsAt(byteOffset), buf.mc ? static_cast<char*>(buf.mc) + byteOffset : nullptr,

@@ -602,9 +602,10 @@ std::shared_ptr<PeerBuffer> PeerContext::allocVmm(size_t bytes, bool wantMc) {
     }
     if (!all1) {
       if (!mcErr.empty()) GLB_WARN("NVLS multicast setup failed on rank ", rank, ": ", mcErr, " - continuing without NVLS");
+      // Not sticky: running out of multicast objects for one allocation must not disable
+      // NVLS for the rest of the job.
       buf->mc = nullptr;
       if (haveMc) d.cuMemRelease(mc);
-      nvlsPossible_ = false;
     }
   }
   return buf;

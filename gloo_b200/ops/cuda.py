@@ -12,6 +12,7 @@ and must be called in the same order on every rank.
 """
 from __future__ import annotations
 
+import weakref
 from typing import Any, Dict, List, Optional, Sequence, Tuple
 
 from .. import _C
@@ -71,8 +72,8 @@ class CudaContext:
             # recognised by CudaAllreduce* / CudaBroadcastOneToAll and get the NVLS path.
             self.pc = _cu.peer_context_for(ctx, self.device, stage_bytes, use_vmm, use_nvls)
         self.rank, self.size = self.pc.rank, self.pc.size
-        self._reg: Dict[int, Tuple[Any, int]] = {}  # base ptr -> (PeerBuffer, nbytes)
-        self._keep: List[Any] = []
+        # base ptr -> (PeerBuffer | weakref to the symmetric storage, nbytes)
+        self._reg: Dict[int, Tuple[Any, int]] = {}
 
     # ---- memory -------------------------------------------------------------------------
     def register(self, tensor):
@@ -98,21 +99,31 @@ class CudaContext:
         store = _SymmetricStorage(buf, nbytes)
         flat = torch.as_tensor(store, device=f"cuda:{self.device}")
         t = flat[: n * es].view(dtype).view(shape)
-        self._reg[buf.ptr] = (buf, nbytes)
-        self._keep.append(store)
+        # The tensor keeps `store` (and through it the PeerBuffer) alive; when the last view
+        # dies the symmetric memory and its multicast binding are released.
+        self._reg[buf.ptr] = (weakref.ref(store), nbytes)
         return t
 
     def lookup(self, tensor) -> Tuple[Optional[Any], int]:
         """(PeerBuffer, byte offset) if ``tensor`` lies inside a registered region."""
         ptr = tensor.data_ptr()
-        hit = self._reg.get(ptr)
         nbytes = tensor.numel() * tensor.element_size()
-        if hit is not None and nbytes <= hit[1]:
-            return hit[0], 0
-        for base, (buf, size) in self._reg.items():
+        dead = []
+        found = (None, 0)
+        for base, (ref, size) in self._reg.items():
+            buf = ref
+            if isinstance(ref, weakref.ref):
+                store = ref()
+                if store is None:
+                    dead.append(base)
+                    continue
+                buf = store.buf
             if base <= ptr and ptr + nbytes <= base + size:
-                return buf, ptr - base
-        return None, 0
+                found = (buf, ptr - base)
+                break
+        for b in dead:
+            del self._reg[b]
+        return found
 
     # ---- info ---------------------------------------------------------------------------
     def describe(self) -> str:

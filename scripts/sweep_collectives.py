@@ -70,7 +70,14 @@ def main():
         sizes.append(args.max_bytes)
     ops = [o for o in args.ops.split(",") if o]
     P = world
+    import gc
+
+    maxn = max(P, sizes[-1] // 4 // P * P)
     for op in ops:
+        # One symmetric buffer per op, sliced per size: every allocation binds a multicast
+        # object, so allocating per size would exhaust them (and waste memory).
+        big = cc.empty(maxn, torch.float32)
+        big.fill_(1)
         for total in sizes:
             # `total` = bytes each rank ends up holding (allgather/alltoall output, broadcast
             # buffer, reduce_scatter input), i.e. the size that bounds the traffic.
@@ -80,7 +87,7 @@ def main():
             row = {"op": op, "bytes": n * 4}
             try:
                 if op == "allgather":
-                    out = cc.empty(n, torch.float32)
+                    out = big[:n]
                     inp = torch.ones(per, device="cuda")
                     row["ours_us"] = timed(lambda: cc.allgather(out, inp, stream=stream), iters)
                     if nccl:
@@ -88,7 +95,7 @@ def main():
                         row["nccl_us"] = timed(lambda: nccl.allgather(inp.data_ptr(), o2.data_ptr(), per, F32, stream.cuda_stream), iters)
                     factor = (P - 1) / P
                 elif op in ("alltoall", "alltoall_v"):
-                    out = cc.empty(n, torch.float32)
+                    out = big[:n]
                     inp = torch.ones(n, device="cuda")
                     if op == "alltoall":
                         row["ours_us"] = timed(lambda: cc.alltoall(out, inp, stream=stream), iters)
@@ -98,22 +105,26 @@ def main():
                         send = [n * x // sum(w) for x in w]
                         send[-1] += n - sum(send)
                         recv = [send[rank]] * P
-                        out_v = cc.empty(sum(recv), torch.float32)
+                        out_v = big[:sum(recv)] if sum(recv) <= maxn else cc.empty(sum(recv), torch.float32)
                         row["ours_us"] = timed(lambda: cc.alltoallv(out_v, recv, inp, send, stream=stream), iters)
                     if nccl and op == "alltoall":
                         o2 = torch.empty(n, device="cuda")
                         row["nccl_us"] = timed(lambda: nccl.alltoall(inp.data_ptr(), o2.data_ptr(), per, F32, stream.cuda_stream), iters)
                     factor = (P - 1) / P
                 elif op == "broadcast":
-                    buf = cc.empty(n, torch.float32)
+                    buf = big[:n]
                     row["ours_us"] = timed(lambda: cc.broadcast(buf, root=0, stream=stream), iters)
+                    if world > 2 and cc.nvls_available() and n * 4 >= (1 << 20):
+                        for m in (0, 1):
+                            os.environ["GLB_CUDA_BCAST_MODE"] = str(m)
+                            row[f"ours_mode{m}_us"] = round(timed(lambda: cc.broadcast(buf, root=0, stream=stream), iters), 2)
+                        os.environ.pop("GLB_CUDA_BCAST_MODE", None)
                     if nccl:
                         o2 = torch.empty(n, device="cuda")
                         row["nccl_us"] = timed(lambda: nccl.broadcast(o2.data_ptr(), o2.data_ptr(), n, F32, 0, stream.cuda_stream), iters)
                     factor = 1.0
                 elif op == "reduce_scatter":
-                    inp = cc.empty(n, torch.float32)
-                    inp.fill_(1)
+                    inp = big[:n]
                     out = torch.empty(per, device="cuda")
                     row["ours_us"] = timed(lambda: cc.reduce_scatter(out, inp, [per] * P, stream=stream), iters)
                     if world > 2 and cc.nvls_available():
@@ -139,6 +150,8 @@ def main():
                 print(json.dumps(row), flush=True)
             torch.cuda.synchronize()
             gb.barrier(ctx)
+        del big
+        gc.collect()
     if args.schedules:
         for dtype, name in ((torch.float16, "float16"),):
             for n in (1 << 10, 1 << 16, 1 << 20, 1 << 24, 1 << 27):

@@ -100,12 +100,14 @@ def main():
                     if op == "alltoall":
                         row["ours_us"] = timed(lambda: cc.alltoall(out, inp, stream=stream), iters)
                     else:
-                        # uneven split: rank r sends (2*per*(j+1))/(P+1) elements to rank j (sums to n)
-                        w = [j + 1 for j in range(P)]
-                        send = [n * x // sum(w) for x in w]
-                        send[-1] += n - sum(send)
-                        recv = [send[rank]] * P
-                        out_v = big[:sum(recv)] if sum(recv) <= maxn else cc.empty(sum(recv), torch.float32)
+                        # uneven but balanced split: rank r sends weight w[(j - r) % P] to rank j, so
+                        # every rank sends and receives n elements in chunks of very different sizes.
+                        w = [k + 1 for k in range(P)]
+                        unit = [n * x // sum(w) for x in w]
+                        unit[-1] += n - sum(unit)
+                        send = [unit[(j - rank) % P] for j in range(P)]
+                        recv = [unit[(rank - i) % P] for i in range(P)]
+                        out_v = big[:n]
                         row["ours_us"] = timed(lambda: cc.alltoallv(out_v, recv, inp, send, stream=stream), iters)
                     if nccl and op == "alltoall":
                         o2 = torch.empty(n, device="cuda")

@@ -39,7 +39,8 @@ struct Tuning {
   size_t nvlsMinBytes = 32 * 1024;      // >= : NVLS when the buffer has a multicast alias (and P > 2)
   int maxBlocks = 64;                   // CTAs for the bandwidth kernels (clamped to co-residency cap)
   int oneShotBlocks = 8;
-  bool nvlsReduceScatter = true;        // multimem.ld_reduce in reduce_scatter / reduce (P > 2)
+  bool nvlsReduceScatter = false;       // multimem.ld_reduce in reduce_scatter / reduce: measured slower than the
+                                        // P2P pull at P=4 (403 vs 343 us @256 MB) and equal at P=8, so off by default
   int copyBlocks = 296;                 // CTAs for the store-only kernels (40 regs: 2-3 CTAs per SM)
   size_t bcastDirectMaxBytes = 256 * 1024;  // <= : root pushes everything itself
 };

@@ -74,12 +74,12 @@ def write_ninja(verbose: bool) -> Path:
     mpi_def = "-DGLB_USE_MPI=1 " if have_mpi else "-DGLB_USE_MPI=0 "
     cxxflags = (
         mpi_def + "-std=c++17 -O2 -g1 -fPIC -Wall -Wextra -Wno-unused-parameter -Wno-missing-field-initializers "
-        "-fvisibility=hidden -pthread -DGLB_USE_CUDA=1 " + common_inc
+        "-pthread -DGLB_USE_CUDA=1 " + common_inc
     )
     nvccflags = (
         " ".join(ARCH_FLAGS)
         + f" -ccbin {CXX}"
-        + " -std=c++17 -O3 -lineinfo --expt-relaxed-constexpr -Xcompiler -fPIC,-fvisibility=hidden,-Wall "
+        + " -std=c++17 -O3 -lineinfo --expt-relaxed-constexpr -Xcompiler -fPIC,-Wall "
         + "-DGLB_USE_CUDA=1 "
         + common_inc
     )
@@ -137,7 +137,7 @@ def write_ninja(verbose: bool) -> Path:
         o = obj(p)
         py_objs.append(o)
         w(f"build {o}: cxx {p}")
-        w("  extra = $pyflags")
+        w("  extra = $pyflags -fvisibility=hidden")
 
     targets = []
     ext = PKG / f"_C{ext_suffix()}"

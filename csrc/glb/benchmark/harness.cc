@@ -8,6 +8,7 @@
 #include <cstring>
 #include <iostream>
 #include <numeric>
+#include <thread>
 
 #include "glb/barrier.h"
 #include "glb/broadcast.h"
@@ -253,16 +254,26 @@ void Runner::printRow(size_t elements, size_t elementSize, const Distribution& h
 }
 
 void Runner::runSize(const BenchmarkFactory& factory, size_t elements) {
-  auto context = factory_->makeContext(device_);
-  context->base = options_.base;
-  if (options_.sync) {
-    for (int i = 0; i < context->size; i++) {
-      auto& pair = context->getPair(i);
-      if (pair) pair->setSync(true, options_.busyPoll);
+  // One derived context + benchmark instance per thread (reference: --threads,
+  // runner.cc:282-369). Contexts are minted sequentially (the factory is collective),
+  // then the threads run concurrently and their samples are merged.
+  const int nthreads = std::max(1, options_.threads);
+  std::vector<std::shared_ptr<Context>> contexts;
+  std::vector<Benchmark> benches;
+  for (int t = 0; t < nthreads; t++) {
+    auto context = factory_->makeContext(device_);
+    context->base = options_.base;
+    if (options_.sync) {
+      for (int i = 0; i < context->size; i++) {
+        auto& pair = context->getPair(i);
+        if (pair) pair->setSync(true, options_.busyPoll);
+      }
     }
+    contexts.push_back(context);
+    benches.push_back(factory(context, options_));
+    benches.back().initialize(elements);
   }
-  Benchmark b = factory(context, options_);
-  b.initialize(elements);
+  Benchmark& b = benches[0];
 
   auto hostBarrier = [&] {
     BarrierOptions o(backing_);
@@ -271,8 +282,10 @@ void Runner::runSize(const BenchmarkFactory& factory, size_t elements) {
   };
 
   if (options_.verify && b.verify) {
-    b.run();
-    b.verify();
+    for (auto& x : benches) {
+      x.run();
+      x.verify();
+    }
     hostBarrier();
   }
   // Warm-up; its median decides the iteration count (agreed through rank 0).
@@ -281,6 +294,9 @@ void Runner::runSize(const BenchmarkFactory& factory, size_t elements) {
     Timer t;
     b.run();
     warm.add(t.ns());
+  }
+  for (size_t t = 1; t < benches.size(); t++) {
+    for (int i = 0; i < options_.warmupIterationCount; i++) benches[t].run();
   }
   long iterations = options_.iterationCount;
   if (iterations <= 0) {
@@ -291,11 +307,25 @@ void Runner::runSize(const BenchmarkFactory& factory, size_t elements) {
   hostBarrier();
   Timer total;
   while (true) {
-    for (long i = 0; i < iterations; i++) {
-      Timer t;
-      b.run();
-      host.add(t.ns());
-      if (b.deviceNs) dev.add(static_cast<long>(b.deviceNs()));
+    std::vector<Distribution> th(nthreads), td(nthreads);
+    auto body = [&](int t) {
+      for (long i = 0; i < iterations; i++) {
+        Timer tm;
+        benches[t].run();
+        th[t].add(tm.ns());
+        if (benches[t].deviceNs) td[t].add(static_cast<long>(benches[t].deviceNs()));
+      }
+    };
+    if (nthreads == 1) {
+      body(0);
+    } else {
+      std::vector<std::thread> workers;
+      for (int t = 0; t < nthreads; t++) workers.emplace_back(body, t);
+      for (auto& w : workers) w.join();
+    }
+    for (int t = 0; t < nthreads; t++) {
+      host.merge(th[t]);
+      dev.merge(td[t]);
     }
     if (options_.iterationCount > 0) break;
     // Keep going (x1.2) until the minimum run time has been reached on rank 0.
@@ -305,7 +335,8 @@ void Runner::runSize(const BenchmarkFactory& factory, size_t elements) {
   }
   hostBarrier();
   printRow(elements, b.elementSize, host, dev, b.busFactor);
-  context->closeConnections();
+  benches.clear();
+  for (auto& c : contexts) c->closeConnections();
 }
 
 void Runner::run() {

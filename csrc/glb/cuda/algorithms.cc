@@ -8,6 +8,7 @@
 #include "glb/common/utils.h"
 #include "glb/cuda/kernels.h"
 #include "glb/cuda/schedules.h"
+#include "glb/cuda/trace.h"
 
 namespace glb {
 namespace cuda {
@@ -159,6 +160,7 @@ AllreduceAlgo CudaAllreduceCore::resolvedAlgo() const {
 
 void CudaAllreduceCore::run() {
   if (count_ == 0) return;
+  GLB_TRACE_RANGE("glb::CudaAllreduce::run");
   CudaStream& s0 = streams_[0];
   const size_t bytes = count_ * elementSize(dt_);
   DeviceGuard g(s0.getDeviceID());
@@ -253,6 +255,7 @@ CudaBroadcastCore::~CudaBroadcastCore() {
 
 void CudaBroadcastCore::run() {
   if (count_ == 0) return;
+  GLB_TRACE_RANGE("glb::CudaBroadcastOneToAll::run");
   const size_t bytes = count_ * elementSize(dt_);
   const bool isRoot = ctx_->rank == root_;
   const int idx = isRoot ? rootPtr_ : 0;

@@ -5,6 +5,7 @@
 
 #include "glb/common/utils.h"
 #include "glb/cuda/kernels.h"
+#include "glb/cuda/trace.h"
 
 namespace glb {
 namespace cuda {
@@ -92,6 +93,7 @@ AllreduceAlgo chooseAllreduce(const PeerContext& pc, size_t bytes, DataType dt, 
 }
 
 void barrier(PeerContext& pc, cudaStream_t stream) {
+  GLB_TRACE_RANGE("glb::cuda::barrier");
   DeviceGuard g(pc.device);
   pc.launchGuard();
   launchBarrier(pc.comm(), stream);
@@ -100,6 +102,7 @@ void barrier(PeerContext& pc, cudaStream_t stream) {
 
 void allreduce(PeerContext& pc, const PeerBuffer& buf, size_t byteOffset, size_t count, DataType dt, ReduceOp op,
                AllreduceAlgo algo, cudaStream_t stream) {
+  GLB_TRACE_RANGE("glb::cuda::allreduce");
   if (count == 0) return;
   const size_t es = elementSize(dt);
   const size_t bytes = count * es;
@@ -145,6 +148,7 @@ void allreduce(PeerContext& pc, const PeerBuffer& buf, size_t byteOffset, size_t
 
 void allreduce(PeerContext& pc, const void* in, void* out, size_t count, DataType dt, ReduceOp op,
                AllreduceAlgo algo, cudaStream_t stream) {
+  GLB_TRACE_RANGE("glb::cuda::allreduce(staged)");
   if (count == 0) return;
   GLB_ENFORCE(op != ReduceOp::CUSTOM, "custom reductions run on the host path only");
   DeviceGuard g(pc.device);
@@ -235,6 +239,7 @@ int bwBlocks(const PeerContext& pc, size_t bytes) {
 
 void broadcast(PeerContext& pc, const PeerBuffer& buf, size_t byteOffset, size_t bytes, int root,
                cudaStream_t stream) {
+  GLB_TRACE_RANGE("glb::cuda::broadcast");
   if (bytes == 0 || pc.size == 1) return;
   GLB_ENFORCE(root >= 0 && root < pc.size, "broadcast: invalid root ", root);
   GLB_ENFORCE_LE(byteOffset + bytes, buf.bytes, "broadcast range exceeds the registered buffer");
@@ -259,6 +264,7 @@ void broadcast(PeerContext& pc, const PeerBuffer& buf, size_t byteOffset, size_t
 }
 
 void broadcast(PeerContext& pc, void* ptr, size_t bytes, int root, cudaStream_t stream) {
+  GLB_TRACE_RANGE("glb::cuda::broadcast(staged)");
   if (bytes == 0 || pc.size == 1) return;
   DeviceGuard g(pc.device);
   const auto l = layoutOf(pc);
@@ -286,6 +292,7 @@ void broadcast(PeerContext& pc, void* ptr, size_t bytes, int root, cudaStream_t 
 namespace {
 void gatherCommon(PeerContext& pc, const void* in, const PeerPtrs& outs, void* mcOut, bool vecOut,
                   const std::vector<size_t>& bytesPerRank, int onlyDst, cudaStream_t stream) {
+  GLB_TRACE_RANGE("glb::cuda::allgather/gather");
   GLB_ENFORCE_EQ(static_cast<int>(bytesPerRank.size()), pc.size, "need one byte count per rank");
   auto off = prefix(bytesPerRank);
   const bool vec = vecOut && reinterpret_cast<uintptr_t>(in) % 16 == 0;
@@ -355,6 +362,7 @@ void gatherv(PeerContext& pc, const void* in, void* out, const std::vector<size_
 namespace {
 void alltoallCommon(PeerContext& pc, const void* in, const std::vector<size_t>& sendBytes, const PeerPtrs& outs,
                     bool vecOut, const std::vector<size_t>& recvBytes, cudaStream_t stream) {
+  GLB_TRACE_RANGE("glb::cuda::alltoall");
   GLB_ENFORCE_EQ(static_cast<int>(sendBytes.size()), pc.size, "alltoall: need one send size per rank");
   GLB_ENFORCE_EQ(static_cast<int>(recvBytes.size()), pc.size, "alltoall: need one recv size per rank");
   auto soff = prefix(sendBytes);
@@ -440,6 +448,7 @@ void scatter(PeerContext& pc, const void* in, void* out, size_t bytes, int root,
 namespace {
 void reducePullCommon(PeerContext& pc, const PeerPtrs& ins, void* mcIn, bool vecIn, void* out,
                       const std::vector<size_t>& counts, DataType dt, ReduceOp op, cudaStream_t stream) {
+  GLB_TRACE_RANGE("glb::cuda::reduce_scatter/reduce");
   GLB_ENFORCE_EQ(static_cast<int>(counts.size()), pc.size, "need one element count per rank");
   GLB_ENFORCE(op != ReduceOp::CUSTOM, "custom reductions run on the host path only");
   auto off = prefix(counts);

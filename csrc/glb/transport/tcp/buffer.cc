@@ -59,6 +59,7 @@ void Buffer::waitRecv() {
   if (pair_->isSync()) {
     pair_->syncWait(lock, pred, pair_->timeout(), "recv");
   } else {
+    pair_->spinWait(lock, pred);
     auto timeout = pair_->timeout();
     if (timeout == kNoTimeout) {
       recvCv_.wait(lock, pred);

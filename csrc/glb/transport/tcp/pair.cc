@@ -1,5 +1,7 @@
 #include "glb/transport/tcp/pair.h"
 
+#include <cstdlib>
+
 #include <netinet/in.h>
 #include <netinet/tcp.h>
 #include <poll.h>
@@ -745,6 +747,56 @@ void Pair::syncWait(std::unique_lock<std::mutex>& lock, const std::function<bool
       signalException(strcat_all("Timed out waiting ", timeout.count(), "ms for ", what, " operation to complete"));
       return;
     }
+  }
+}
+
+int64_t Pair::spinBudgetNanos() {
+  static const int64_t ns = [] {
+    const char* v = std::getenv("GLB_TCP_SPIN_US");
+    long us = v != nullptr ? std::strtol(v, nullptr, 10) : 100;
+    if (us < 0) us = 0;
+    return static_cast<int64_t>(us) * 1000;
+  }();
+  return ns;
+}
+
+namespace {
+inline void cpuRelax() {
+#if defined(__x86_64__) || defined(__i386__)
+  __builtin_ia32_pause();
+#elif defined(__aarch64__)
+  asm volatile("yield" ::: "memory");
+#endif
+}
+}  // namespace
+
+void Pair::spinWait(std::unique_lock<std::mutex>& lock, const std::function<bool()>& pred) {
+  const int64_t budget = spinBudgetNanos();
+  if (budget == 0 || sync_) return;
+  const auto deadline = std::chrono::steady_clock::now() + std::chrono::nanoseconds(budget);
+  while (!failed_ && state_ == CONNECTED && !pred()) {
+    try {
+      readLoop(kReadBudget);
+    } catch (const std::exception& e) {
+      signalException(e.what());
+      return;
+    }
+    if (failed_ || pred()) return;
+    // Let the loop thread / senders in, then look again.
+    lock.unlock();
+    for (int i = 0; i < 16; i++) cpuRelax();
+    lock.lock();
+    if (std::chrono::steady_clock::now() >= deadline) return;
+  }
+}
+
+void Pair::tryProgress() {
+  std::unique_lock<std::mutex> lock(mu_, std::try_to_lock);
+  if (!lock.owns_lock() || sync_ || failed_ || state_ != CONNECTED) return;
+  try {
+    readLoop(kReadBudget);
+  } catch (const std::exception& e) {
+    signalException(e.what());
   }
 }
 

@@ -112,6 +112,17 @@ class Pair : public ::glb::transport::Pair, private Handler {
   // `lock` must hold mu() on entry and holds it on return.
   void syncWait(std::unique_lock<std::mutex>& lock, const std::function<bool()>& pred,
                 std::chrono::milliseconds timeout, const char* what);
+  // Async mode, spin-then-block: for a bounded time (GLB_TCP_SPIN_US, default 100,
+  // 0 disables) the waiting user thread pulls bytes off the socket itself instead of
+  // sleeping on a condvar until the loop thread has done so. That removes two thread
+  // wake-ups (epoll thread, then waiter) from the small-message critical path while
+  // the loop thread remains the fallback for everything the waiter does not get to.
+  // `lock` must hold mu() on entry and holds it on return.
+  void spinWait(std::unique_lock<std::mutex>& lock, const std::function<bool()>& pred);
+  // Same, for waiters that do not own mu_: one non-blocking read pass if the pair
+  // mutex is free. Never throws, never blocks.
+  void tryProgress();
+  static int64_t spinBudgetNanos();
   std::mutex& mu() { return mu_; }
   void throwIfException();  // requires mu_
 

@@ -41,10 +41,36 @@ void UnboundBuffer::signalException(const std::string& msg) {
   sendCv_.notify_all();
 }
 
+void UnboundBuffer::noteSource(int rank) {
+  std::lock_guard<std::mutex> g(m_);
+  for (int r : spinRanks_) {
+    if (r == rank) return;
+  }
+  spinRanks_.push_back(rank);
+}
+
+void UnboundBuffer::spinRecv(std::unique_lock<std::mutex>& lock) {
+  const int64_t budget = Pair::spinBudgetNanos();
+  if (budget == 0 || spinRanks_.empty()) return;
+  const std::vector<int> ranks = spinRanks_;
+  const auto deadline = std::chrono::steady_clock::now() + std::chrono::nanoseconds(budget);
+  while (recvRanks_.empty() && !abortWaitRecv_ && !failed_) {
+    // Pair mutex before m_ is the completion path's order, so m_ is dropped here.
+    lock.unlock();
+    for (int r : ranks) {
+      auto* p = static_cast<Pair*>(context_->peekPair(r));
+      if (p != nullptr) p->tryProgress();
+    }
+    lock.lock();
+    if (std::chrono::steady_clock::now() >= deadline) return;
+  }
+}
+
 bool UnboundBuffer::waitRecv(int* rank, std::chrono::milliseconds timeout) {
   if (timeout == kUnsetTimeout) timeout = context_->getTimeout();
   std::unique_lock<std::mutex> lock(m_);
   throwIfException();
+  if (recvRanks_.empty()) spinRecv(lock);
   if (recvRanks_.empty()) {
     auto pred = [&] { return abortWaitRecv_ || !recvRanks_.empty() || failed_; };
     bool done = true;
@@ -134,6 +160,7 @@ void UnboundBuffer::recv(std::vector<int> srcRanks, uint64_t slot, size_t offset
     nbytes = size - offset;
   }
   GLB_ENFORCE_LE(offset + nbytes, size, "recv range exceeds buffer");
+  for (int r : srcRanks) noteSource(r);
   context_->postRecv(this, std::move(srcRanks), slot, offset, nbytes);
 }
 
@@ -159,6 +186,7 @@ void UnboundBuffer::get(const ::glb::transport::RemoteKey& key, uint64_t /*slot*
   GLB_ENFORCE_LE(offset + nbytes, size, "get: local range exceeds buffer");
   GLB_ENFORCE_LE(roffset + nbytes, k->size, "get: remote range exceeds region");
   GLB_ENFORCE_NE(k->rank, context_->rank, "get from self");
+  noteSource(k->rank);
   uint64_t req = context_->registerPendingGet(this, offset, nbytes);
   context_->tcpPair(k->rank)->sendGetRequest(req, k->regionId, roffset, nbytes);
 }

@@ -5,6 +5,7 @@
 #include <deque>
 #include <memory>
 #include <mutex>
+#include <vector>
 
 #include "glb/common/memory.h"
 #include "glb/transport/unbound_buffer.h"
@@ -46,6 +47,10 @@ class UnboundBuffer : public ::glb::transport::UnboundBuffer {
 
  private:
   void throwIfException();  // requires m_
+  void noteSource(int rank);  // requires no lock
+  // Spin-then-block (see Pair::spinWait): poll the pairs this buffer receives from
+  // for a bounded time. `lock` holds m_ on entry and on return.
+  void spinRecv(std::unique_lock<std::mutex>& lock);
 
   std::shared_ptr<Context> context_;
   std::mutex m_;
@@ -55,6 +60,7 @@ class UnboundBuffer : public ::glb::transport::UnboundBuffer {
   bool abortWaitSend_ = false;
   std::deque<int> recvRanks_;  // one entry per completed recv
   std::deque<int> sendRanks_;  // one entry per completed send
+  std::vector<int> spinRanks_;  // peers a recv/get was ever posted for (sticky, small)
   bool failed_ = false;
   std::string exMsg_;
   mutable uint64_t regionId_ = 0;

@@ -70,7 +70,8 @@ void Buffer::waitRecv() {
       GLB_THROW_TIMEOUT(msg);
     }
   }
-  throwIfException();
+  // A write that landed before the pair failed is still delivered.
+  if (recvCompletions_ == 0) throwIfException();
   recvCompletions_--;
 }
 
@@ -83,6 +84,7 @@ void Buffer::waitSend() {
   if (pair_->isSync()) {
     pair_->syncWait(lock, pred, pair_->timeout(), "send");
   } else {
+    pair_->spinWait(lock, pred);
     auto timeout = pair_->timeout();
     if (timeout == kNoTimeout) {
       sendCv_.wait(lock, pred);

@@ -173,8 +173,30 @@ void Context::postRecv(UnboundBuffer* buf, std::vector<int> srcRanks, uint64_t s
   GLB_ENFORCE(!srcRanks.empty(), "recv needs at least one source rank");
   for (int r : srcRanks) {
     GLB_ENFORCE(r >= 0 && r < size && r != rank, "invalid source rank ", r);
-    // Make sure the connection exists so the message can arrive (lazy mode).
-    tcpPair(r);
+  }
+  // A message that already arrived is delivered even if its pair has since seen the
+  // peer close (a rank that finished its part of a collective may exit while slower
+  // ranks still have its data parked here). Only when nothing is waiting do the
+  // connections have to be alive — and, in lazy mode, created.
+  bool waiting = false;
+  auto somethingWaiting = [&] {
+    std::lock_guard<std::mutex> g(matchMu_);
+    for (int r : srcRanks) {
+      auto it = unexpected_[r].find(slot);
+      if (it != unexpected_[r].end() && !it->second.empty()) return true;
+    }
+    return false;
+  };
+  waiting = somethingWaiting();
+  if (!waiting) {
+    try {
+      for (int r : srcRanks) tcpPair(r);
+    } catch (const IoException&) {
+      // The liveness check can block behind the read that delivers the very message
+      // this recv is for, followed by the peer's EOF. Nothing more can arrive after
+      // that, so a second look at the queue is conclusive.
+      if (!somethingWaiting()) throw;
+    }
   }
   int matchedRank = -1;
   {

@@ -1,5 +1,6 @@
 #include "glb/transport/tcp/pair.h"
 
+#include <cstdio>
 #include <cstdlib>
 
 #include <netinet/in.h>
@@ -26,6 +27,41 @@ namespace tcp {
 namespace {
 constexpr size_t kReadBudget = 8u << 20;  // bytes read per epoll callback before yielding
 constexpr int kSocketBuffer = 4 << 20;
+
+// Same-host single-copy path (see pair.h).
+bool cmaEnabled() {
+  static const bool on = [] {
+    const char* v = std::getenv("GLB_TCP_CMA");
+    return v == nullptr || std::atoi(v) != 0;
+  }();
+  return on;
+}
+size_t cmaMinBytes() {
+  static const size_t n = [] {
+    const char* v = std::getenv("GLB_TCP_CMA_MIN");
+    long long b = v != nullptr ? std::atoll(v) : (256 << 10);
+    return static_cast<size_t>(b < 1 ? 1 : b);
+  }();
+  return n;
+}
+std::atomic<uint64_t> g_cmaMessages{0};
+std::atomic<uint64_t> g_cmaBytes{0};
+
+// The word a peer must be able to read before it is allowed to pull from us.
+uint64_t* probeWord() {
+  static uint64_t word = [] {
+    uint64_t v = 0;
+    FILE* f = std::fopen("/dev/urandom", "rb");
+    if (f != nullptr) {
+      if (std::fread(&v, sizeof(v), 1, f) != 1) v = 0;
+      std::fclose(f);
+    }
+    if (v == 0) v = 0x9e3779b97f4a7c15ull ^ (static_cast<uint64_t>(::getpid()) << 32) ^
+                    static_cast<uint64_t>(std::chrono::steady_clock::now().time_since_epoch().count());
+    return v;
+  }();
+  return &word;
+}
 
 bool retryableConnectError(int err) {
   return err == ECONNREFUSED || err == ETIMEDOUT || err == EHOSTUNREACH || err == ENETUNREACH ||
@@ -213,6 +249,18 @@ void Pair::attachSocket(Socket sock, bool initiator) {
   }
   state_ = CONNECTED;
   if (!sync_) armEvents(false);
+  if (cmaEnabled() && allowCma()) {
+    TxOp caps;
+    caps.hdr.opcode = OP_CAPS;
+    caps.hdr.slot = static_cast<uint64_t>(::getpid());
+    caps.hdr.aux = reinterpret_cast<uint64_t>(probeWord());
+    caps.hdr.length = *probeWord();
+    try {
+      enqueue(std::move(caps));
+    } catch (const std::exception& e) {
+      signalException(e.what());
+    }
+  }
   cv_.notify_all();
 }
 
@@ -298,6 +346,13 @@ void Pair::signalException(const std::string& msg) {
     }
   }
   tx_.clear();
+  for (auto& op : awaitingFin_) {
+    if (op.bbuf != nullptr) op.bbuf->signalException(exMsg_);
+    if (op.hasUbuf && op.notify) {
+      if (auto l = op.ubuf.lock()) l->signalException(exMsg_);
+    }
+  }
+  awaitingFin_.clear();
   if (rx_.ubuf) rx_.ubuf->signalException(exMsg_);
   rx_.reset();
   for (auto& kv : recvBuffers_) kv.second->signalException(exMsg_);
@@ -344,6 +399,9 @@ void Pair::unregisterBuffer(Buffer* buf) {
   for (auto& op : tx_) {
     if (op.bbuf == buf) poisoned = true;
   }
+  for (auto& op : awaitingFin_) {
+    if (op.bbuf == buf) poisoned = true;
+  }
   if (poisoned) signalException("bound buffer destroyed while a send was still queued");
 }
 
@@ -352,6 +410,9 @@ void Pair::forgetUnbound(UnboundBuffer* buf) {
   bool poisoned = false;
   for (auto& op : tx_) {
     if (op.hasUbuf && op.ubufRaw == buf) poisoned = true;
+  }
+  for (auto& op : awaitingFin_) {
+    if (op.hasUbuf && op.notify && op.ubufRaw == buf) poisoned = true;
   }
   if (poisoned) signalException("unbound buffer destroyed while a send was still queued");
 }
@@ -365,10 +426,9 @@ void Pair::sendBound(Buffer* buf, size_t offset, size_t length, size_t roffset) 
   op.hdr.slot = static_cast<uint64_t>(buf->slot());
   op.hdr.nbytes = length;
   op.hdr.roffset = roffset;
-  op.data = static_cast<const char*>(buf->ptr()) + offset;
-  op.nbytes = length;
   op.bbuf = buf;
   std::lock_guard<std::mutex> g(mu_);
+  setPayload(op, static_cast<const char*>(buf->ptr()) + offset, length);
   enqueue(std::move(op));
 }
 
@@ -377,12 +437,11 @@ void Pair::sendUnbound(UnboundBuffer* buf, uint64_t slot, size_t offset, size_t 
   op.hdr.opcode = OP_SEND_UNBOUND;
   op.hdr.slot = slot;
   op.hdr.nbytes = nbytes;
-  op.data = static_cast<const char*>(buf->ptr) + offset;
-  op.nbytes = nbytes;
   op.hasUbuf = true;
   op.ubuf = buf->weak();
   op.ubufRaw = buf;
   std::lock_guard<std::mutex> g(mu_);
+  setPayload(op, static_cast<const char*>(buf->ptr) + offset, nbytes);
   enqueue(std::move(op));
 }
 
@@ -392,12 +451,11 @@ void Pair::sendPut(UnboundBuffer* buf, uint64_t regionId, size_t offset, size_t 
   op.hdr.aux = regionId;
   op.hdr.nbytes = nbytes;
   op.hdr.roffset = roffset;
-  op.data = static_cast<const char*>(buf->ptr) + offset;
-  op.nbytes = nbytes;
   op.hasUbuf = true;
   op.ubuf = buf->weak();
   op.ubufRaw = buf;
   std::lock_guard<std::mutex> g(mu_);
+  setPayload(op, static_cast<const char*>(buf->ptr) + offset, nbytes);
   enqueue(std::move(op));
 }
 
@@ -425,6 +483,28 @@ void Pair::recv(::glb::transport::UnboundBuffer* tbuf, uint64_t tag, size_t offs
   context_->postRecv(buf, {peerRank_}, tag, offset, nbytes);
 }
 
+void Pair::setPayload(TxOp& op, const char* data, size_t nbytes) {
+  op.hdr.nbytes = nbytes;
+  op.data = data;
+  if (peerCanPull_ && nbytes >= cmaMinBytes()) {
+    // Header only; the receiver pulls the bytes and answers FIN.
+    op.cma = true;
+    op.hdr.flags |= F_CMA;
+    op.hdr.length = reinterpret_cast<uint64_t>(data);
+    op.nbytes = 0;
+  } else {
+    op.nbytes = nbytes;
+  }
+}
+
+void Pair::wroteTx(TxOp&& op) {
+  if (op.cma) {
+    awaitingFin_.push_back(std::move(op));
+  } else {
+    completeTx(op);
+  }
+}
+
 void Pair::enqueue(TxOp&& op) {
   throwIfException();
   GLB_ENFORCE(state_ == CONNECTED, "pair to rank ", peerRank_, " is not connected");
@@ -435,11 +515,11 @@ void Pair::enqueue(TxOp&& op) {
       struct pollfd pfd = {fd_, POLLOUT, 0};
       if (!busyPoll_) ::poll(&pfd, 1, 100);
     }
-    completeTx(op);
+    wroteTx(std::move(op));
     return;
   }
   if (tx_.empty() && tryWrite(op)) {
-    completeTx(op);
+    wroteTx(std::move(op));
     return;
   }
   throwIfException();
@@ -500,7 +580,7 @@ void Pair::flushTx() {
     if (!tryWrite(tx_.front())) return;  // EAGAIN (or failure, which cleared tx_)
     TxOp op = std::move(tx_.front());
     tx_.pop_front();
-    completeTx(op);
+    wroteTx(std::move(op));
   }
   if (wantWrite_ && state_ == CONNECTED) armEvents(false);
 }
@@ -555,6 +635,10 @@ void Pair::readLoop(size_t budget) {
         return;
       }
     }
+    if ((rx_.hdr.flags & F_CMA) != 0 && rx_.payloadRead < rx_.hdr.nbytes) {
+      if (!pullPayload()) return;
+      consumed += rx_.hdr.nbytes;
+    }
     if (rx_.payloadRead < rx_.hdr.nbytes) {
       ssize_t n = ioRecv(rx_.dst + rx_.payloadRead, rx_.hdr.nbytes - rx_.payloadRead);
       if (n > 0) {
@@ -573,11 +657,45 @@ void Pair::readLoop(size_t budget) {
       }
     }
     if (rx_.payloadRead == rx_.hdr.nbytes) {
+      const bool fin = (rx_.hdr.flags & F_CMA) != 0;
       finishMessage();
       rx_.reset();
+      if (fin && state_ == CONNECTED) {
+        TxOp op;
+        op.hdr.opcode = OP_FIN;
+        enqueue(std::move(op));
+      }
     }
   }
 }
+
+bool Pair::pullPayload() {
+  if (!canPull_) {
+    signalException("protocol error: peer used the single-copy path without permission");
+    return false;
+  }
+  const char* src = reinterpret_cast<const char*>(rx_.hdr.length);
+  while (rx_.payloadRead < rx_.hdr.nbytes) {
+    struct iovec local = {rx_.dst + rx_.payloadRead, rx_.hdr.nbytes - rx_.payloadRead};
+    struct iovec remote = {const_cast<char*>(src) + rx_.payloadRead, rx_.hdr.nbytes - rx_.payloadRead};
+    ssize_t n = ::process_vm_readv(peerPid_, &local, 1, &remote, 1, 0);
+    if (n > 0) {
+      rx_.payloadRead += static_cast<size_t>(n);
+    } else if (n == -1 && errno == EINTR) {
+      continue;
+    } else {
+      signalException(strcat_all("process_vm_readv from rank ", peerRank_, " (pid ", peerPid_, "): ",
+                                 n == 0 ? "short read" : std::strerror(errno)));
+      return false;
+    }
+  }
+  g_cmaMessages.fetch_add(1, std::memory_order_relaxed);
+  g_cmaBytes.fetch_add(rx_.hdr.nbytes, std::memory_order_relaxed);
+  return true;
+}
+
+uint64_t Pair::cmaMessages() { return g_cmaMessages.load(std::memory_order_relaxed); }
+uint64_t Pair::cmaBytes() { return g_cmaBytes.load(std::memory_order_relaxed); }
 
 void Pair::beginMessage() {
   const auto& h = rx_.hdr;
@@ -643,16 +761,14 @@ void Pair::beginMessage() {
       op.hdr.opcode = OP_GET_RESP;
       op.hdr.slot = h.slot;
       if (context_->lookupRegion(h.aux, &lease) && h.roffset + h.length <= lease->size) {
-        op.hdr.nbytes = h.length;
-        op.data = static_cast<const char*>(lease->ptr) + h.roffset;
-        op.nbytes = h.length;
+        setPayload(op, static_cast<const char*>(lease->ptr) + h.roffset, h.length);
         op.hasUbuf = true;
         op.notify = false;
         op.ubuf = lease->weak();
         op.ubufRaw = lease.get();
       } else {
         GLB_WARN("get from unknown or too small region ", h.aux, " by rank ", peerRank_);
-        op.hdr.flags = 1;  // error marker, no payload
+        op.hdr.flags = F_ERROR;  // no payload
       }
       lease.release();
       rx_.kind = RX_NONE;
@@ -662,7 +778,7 @@ void Pair::beginMessage() {
     case OP_GET_RESP: {
       Context::Match m;
       if (context_->takePendingGet(h.slot, &m)) {
-        if (h.flags != 0 || h.nbytes != m.capacity) {
+        if ((h.flags & F_ERROR) != 0 || h.nbytes != m.capacity) {
           m.buf->signalException("one-sided get failed on the remote side (bad key or range)");
           rx_.kind = RX_DISCARD;
           rx_.stash.resize(h.nbytes);
@@ -677,6 +793,39 @@ void Pair::beginMessage() {
         rx_.stash.resize(h.nbytes);
         rx_.dst = rx_.stash.data();
       }
+      break;
+    }
+    case OP_CAPS: {
+      rx_.kind = RX_NONE;
+      if (!cmaEnabled() || !allowCma()) break;
+      peerPid_ = static_cast<int>(h.slot);
+      uint64_t seen = 0;
+      struct iovec local = {&seen, sizeof(seen)};
+      struct iovec remote = {reinterpret_cast<void*>(h.aux), sizeof(seen)};
+      ssize_t n = ::process_vm_readv(peerPid_, &local, 1, &remote, 1, 0);
+      if (n == static_cast<ssize_t>(sizeof(seen)) && seen == h.length) {
+        canPull_ = true;
+        TxOp op;
+        op.hdr.opcode = OP_CAPS_OK;
+        enqueue(std::move(op));
+      } else {
+        GLB_DEBUG("single-copy path to rank ", peerRank_, " unavailable (different host or no ptrace permission)");
+      }
+      break;
+    }
+    case OP_CAPS_OK:
+      rx_.kind = RX_NONE;
+      peerCanPull_ = cmaEnabled() && allowCma();
+      break;
+    case OP_FIN: {
+      rx_.kind = RX_NONE;
+      if (awaitingFin_.empty()) {
+        signalException("protocol error: FIN without a pending single-copy send");
+        return;
+      }
+      TxOp op = std::move(awaitingFin_.front());
+      awaitingFin_.pop_front();
+      completeTx(op);
       break;
     }
     default:
@@ -792,7 +941,7 @@ void Pair::spinWait(std::unique_lock<std::mutex>& lock, const std::function<bool
 
 void Pair::tryProgress() {
   std::unique_lock<std::mutex> lock(mu_, std::try_to_lock);
-  if (!lock.owns_lock() || sync_ || failed_ || state_ != CONNECTED) return;
+  if (!lock.owns_lock() || failed_ || state_ != CONNECTED) return;
   try {
     readLoop(kReadBudget);
   } catch (const std::exception& e) {

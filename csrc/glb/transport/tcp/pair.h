@@ -16,6 +16,17 @@
 //                 software one-sided access to a region exported through
 //                 UnboundBuffer::getRemoteKey() — served entirely by the remote
 //                 I/O thread, the remote user thread is not involved.
+//   CAPS / CAPS_OK / FIN
+//                 same-host single-copy path. Each side announces (pid, address of a
+//                 per-process random probe word). A receiver that can read that word
+//                 with process_vm_readv answers CAPS_OK; from then on the peer sends
+//                 payloads of >= GLB_TCP_CMA_MIN bytes as a header only (flag F_CMA,
+//                 `length` = source address) and the receiver pulls the bytes straight
+//                 from the sender's address space into the destination — one copy, no
+//                 socket buffers — then answers FIN, which completes the send. Pulls
+//                 happen where socket reads would (loop thread or spinning waiter), so
+//                 delivery stays eager: it never depends on the receiving user thread.
+//                 FINs come back in send order, so they carry no id.
 //
 // Threading: all pair state is guarded by `mu_`. In async mode the device loop
 // thread performs reads and flushes queued writes; writes are attempted inline
@@ -68,6 +79,14 @@ enum Opcode : uint16_t {
   OP_PUT = 3,
   OP_GET_REQ = 4,
   OP_GET_RESP = 5,
+  OP_CAPS = 6,
+  OP_CAPS_OK = 7,
+  OP_FIN = 8,
+};
+
+enum WireFlags : uint16_t {
+  F_ERROR = 0x1,  // GET_RESP: remote lookup failed
+  F_CMA = 0x2,    // payload is not inline; pull `nbytes` from `length` in the sender's address space
 };
 
 class Pair : public ::glb::transport::Pair, private Handler {
@@ -93,6 +112,7 @@ class Pair : public ::glb::transport::Pair, private Handler {
   int peerRank() const { return peerRank_; }
   std::chrono::milliseconds timeout() const { return timeout_; }
   bool isSync() const { return sync_; }
+  bool isBusyPoll() const { return busyPoll_; }
 
   // Dial / wait for the inbound connection if that has not happened yet (lazy mode).
   void ensureConnected();
@@ -123,6 +143,9 @@ class Pair : public ::glb::transport::Pair, private Handler {
   // mutex is free. Never throws, never blocks.
   void tryProgress();
   static int64_t spinBudgetNanos();
+  // Process-wide counters of the single-copy path (tests and diagnostics).
+  static uint64_t cmaMessages();
+  static uint64_t cmaBytes();
   std::mutex& mu() { return mu_; }
   void throwIfException();  // requires mu_
 
@@ -135,6 +158,8 @@ class Pair : public ::glb::transport::Pair, private Handler {
   // Bytes already buffered above the socket (TLS): the read loop must not yield to
   // epoll while this is true, the fd would not become readable again.
   virtual bool ioPending() { return false; }
+  // Whether payloads may bypass the socket on the same host (the TLS pair says no).
+  virtual bool allowCma() const { return true; }
 
   int fd() const { return fd_; }
 
@@ -146,6 +171,7 @@ class Pair : public ::glb::transport::Pair, private Handler {
     size_t sent = 0;
     bool hasUbuf = false;
     bool notify = true;
+    bool cma = false;  // header-only on the wire; completion on FIN
     WeakAnchor<UnboundBuffer> ubuf;
     UnboundBuffer* ubufRaw = nullptr;
     Buffer* bbuf = nullptr;
@@ -194,6 +220,9 @@ class Pair : public ::glb::transport::Pair, private Handler {
   void enqueue(TxOp&& op);      // requires mu_
   bool tryWrite(TxOp& op);      // requires mu_; true when fully written
   void completeTx(TxOp& op);    // requires mu_
+  void wroteTx(TxOp&& op);      // requires mu_; completes now, or parks until FIN
+  void setPayload(TxOp& op, const char* data, size_t nbytes);  // requires mu_
+  bool pullPayload();           // requires mu_; false after signalException
   void flushTx();               // requires mu_
   void readLoop(size_t budget); // requires mu_
   void beginMessage();          // requires mu_
@@ -225,6 +254,10 @@ class Pair : public ::glb::transport::Pair, private Handler {
   bool failed_ = false;
 
   std::deque<TxOp> tx_;
+  std::deque<TxOp> awaitingFin_;  // CMA sends written to the wire, in order
+  bool peerCanPull_ = false;      // peer answered CAPS_OK
+  bool canPull_ = false;          // we can read the peer's memory
+  int peerPid_ = -1;
   Rx rx_;
   std::unordered_map<int, Buffer*> recvBuffers_;
   std::unordered_map<int, std::deque<ParkedBound>> parkedBound_;

@@ -110,6 +110,10 @@ void Pair::ioHandshake(bool isInitiator) {
 ssize_t Pair::ioRecv(void* buf, size_t len) {
   const auto& o = openssl();
   if (len == 0) return 0;
+  // SSL_get_error consults the calling thread's error queue and errno; reads come from
+  // the loop thread and from spinning waiters, so both start clean every time.
+  o.ERR_clear_error();
+  errno = 0;
   int n = o.SSL_read(ssl_, buf, static_cast<int>(std::min<size_t>(len, 1 << 30)));
   if (n > 0) return n;
   int err = o.SSL_get_error(ssl_, n);
@@ -129,6 +133,8 @@ ssize_t Pair::ioSend(const struct iovec* iov, int iovcnt) {
   for (int i = 0; i < iovcnt; i++) {
     size_t off = 0;
     while (off < iov[i].iov_len) {
+      o.ERR_clear_error();
+      errno = 0;
       int n = o.SSL_write(ssl_, static_cast<const char*>(iov[i].iov_base) + off,
                           static_cast<int>(std::min<size_t>(iov[i].iov_len - off, 1 << 30)));
       if (n > 0) {

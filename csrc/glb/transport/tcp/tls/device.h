@@ -54,6 +54,7 @@ class Pair : public ::glb::transport::tcp::Pair {
   ssize_t ioSend(const struct iovec* iov, int iovcnt) override;
   void ioHandshake(bool isInitiator) override;
   void ioShutdown() override;
+  bool allowCma() const override { return false; }  // payloads stay inside the TLS session
   bool ioPending() override { return ssl_ != nullptr && openssl().SSL_pending(ssl_) > 0; }
 
  private:

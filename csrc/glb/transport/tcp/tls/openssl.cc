@@ -65,6 +65,7 @@ void load() {
   GLB_SSL(ssl, SSL_shutdown);
   GLB_SSL(ssl, SSL_pending);
   GLB_SSL(crypto, ERR_get_error);
+  GLB_SSL(crypto, ERR_clear_error);
   GLB_SSL(crypto, ERR_error_string_n);
 #undef GLB_SSL
   gLoaded = ok;

@@ -37,6 +37,7 @@ struct OpenSSL {
   int (*SSL_shutdown)(SSL*);
   int (*SSL_pending)(const SSL*);
   unsigned long (*ERR_get_error)();
+  void (*ERR_clear_error)();
   void (*ERR_error_string_n)(unsigned long, char*, size_t);
 };
 

@@ -41,7 +41,7 @@ void UnboundBuffer::signalException(const std::string& msg) {
   sendCv_.notify_all();
 }
 
-void UnboundBuffer::noteSource(int rank) {
+void UnboundBuffer::notePeer(int rank) {
   std::lock_guard<std::mutex> g(m_);
   for (int r : spinRanks_) {
     if (r == rank) return;
@@ -49,12 +49,13 @@ void UnboundBuffer::noteSource(int rank) {
   spinRanks_.push_back(rank);
 }
 
-void UnboundBuffer::spinRecv(std::unique_lock<std::mutex>& lock) {
+template <typename Pred>
+void UnboundBuffer::spinUntil(std::unique_lock<std::mutex>& lock, Pred done) {
   const int64_t budget = Pair::spinBudgetNanos();
   if (budget == 0 || spinRanks_.empty()) return;
   const std::vector<int> ranks = spinRanks_;
   const auto deadline = std::chrono::steady_clock::now() + std::chrono::nanoseconds(budget);
-  while (recvRanks_.empty() && !abortWaitRecv_ && !failed_) {
+  while (!done()) {
     // Pair mutex before m_ is the completion path's order, so m_ is dropped here.
     lock.unlock();
     for (int r : ranks) {
@@ -66,15 +67,43 @@ void UnboundBuffer::spinRecv(std::unique_lock<std::mutex>& lock) {
   }
 }
 
+template <typename Pred>
+bool UnboundBuffer::driveSyncPairs(std::unique_lock<std::mutex>& lock, Pred done,
+                                   std::chrono::milliseconds timeout) {
+  std::vector<Pair*> pairs;
+  bool busy = true;
+  for (int r : spinRanks_) {
+    auto* p = static_cast<Pair*>(context_->peekPair(r));
+    if (p != nullptr && p->isSync()) {
+      pairs.push_back(p);
+      busy = busy && p->isBusyPoll();
+    }
+  }
+  if (pairs.empty()) return true;
+  const auto start = std::chrono::steady_clock::now();
+  while (!done()) {
+    lock.unlock();
+    for (auto* p : pairs) p->tryProgress();
+    lock.lock();
+    if (done()) break;
+    if (timeout != kNoTimeout && std::chrono::steady_clock::now() - start > timeout) return false;
+    // Completions from async pairs still arrive through the condvar.
+    if (!busy) recvCv_.wait_for(lock, std::chrono::microseconds(200));
+  }
+  return true;
+}
+
 bool UnboundBuffer::waitRecv(int* rank, std::chrono::milliseconds timeout) {
   if (timeout == kUnsetTimeout) timeout = context_->getTimeout();
   std::unique_lock<std::mutex> lock(m_);
-  throwIfException();
-  if (recvRanks_.empty()) spinRecv(lock);
+  // Completions that landed before a failure are still handed out.
+  if (recvRanks_.empty()) throwIfException();
+  if (recvRanks_.empty()) spinUntil(lock, [&] { return abortWaitRecv_ || !recvRanks_.empty() || failed_; });
   if (recvRanks_.empty()) {
     auto pred = [&] { return abortWaitRecv_ || !recvRanks_.empty() || failed_; };
-    bool done = true;
-    if (timeout == kNoTimeout) {
+    bool done = driveSyncPairs(lock, pred, timeout);
+    if (!done) {
+    } else if (timeout == kNoTimeout) {
       recvCv_.wait(lock, pred);
     } else {
       done = recvCv_.wait_for(lock, timeout, pred);
@@ -87,7 +116,7 @@ bool UnboundBuffer::waitRecv(int* rank, std::chrono::milliseconds timeout) {
       context_->signalException("Application timeout caused pair closure");
       GLB_THROW_TIMEOUT("Timed out waiting ", timeout.count(), "ms for recv operation to complete");
     }
-    throwIfException();
+    if (recvRanks_.empty()) throwIfException();
   }
   if (abortWaitRecv_ && recvRanks_.empty()) {
     abortWaitRecv_ = false;
@@ -103,10 +132,12 @@ bool UnboundBuffer::waitSend(int* rank, std::chrono::milliseconds timeout) {
   if (timeout == kUnsetTimeout) timeout = context_->getTimeout();
   std::unique_lock<std::mutex> lock(m_);
   throwIfException();
+  if (sendRanks_.empty()) spinUntil(lock, [&] { return abortWaitSend_ || !sendRanks_.empty() || failed_; });
   if (sendRanks_.empty()) {
     auto pred = [&] { return abortWaitSend_ || !sendRanks_.empty() || failed_; };
-    bool done = true;
-    if (timeout == kNoTimeout) {
+    bool done = driveSyncPairs(lock, pred, timeout);
+    if (!done) {
+    } else if (timeout == kNoTimeout) {
       sendCv_.wait(lock, pred);
     } else {
       done = sendCv_.wait_for(lock, timeout, pred);
@@ -147,6 +178,7 @@ void UnboundBuffer::send(int dstRank, uint64_t slot, size_t offset, size_t nbyte
     nbytes = size - offset;
   }
   GLB_ENFORCE_LE(offset + nbytes, size, "send range exceeds buffer");
+  notePeer(dstRank);
   context_->tcpPair(dstRank)->sendUnbound(this, slot, offset, nbytes);
 }
 
@@ -160,7 +192,7 @@ void UnboundBuffer::recv(std::vector<int> srcRanks, uint64_t slot, size_t offset
     nbytes = size - offset;
   }
   GLB_ENFORCE_LE(offset + nbytes, size, "recv range exceeds buffer");
-  for (int r : srcRanks) noteSource(r);
+  for (int r : srcRanks) notePeer(r);
   context_->postRecv(this, std::move(srcRanks), slot, offset, nbytes);
 }
 
@@ -176,6 +208,7 @@ void UnboundBuffer::put(const ::glb::transport::RemoteKey& key, uint64_t /*slot*
   GLB_ENFORCE_LE(offset + nbytes, size, "put: local range exceeds buffer");
   GLB_ENFORCE_LE(roffset + nbytes, k->size, "put: remote range exceeds region");
   GLB_ENFORCE_NE(k->rank, context_->rank, "put to self");
+  notePeer(k->rank);
   context_->tcpPair(k->rank)->sendPut(this, k->regionId, offset, roffset, nbytes);
 }
 
@@ -186,7 +219,7 @@ void UnboundBuffer::get(const ::glb::transport::RemoteKey& key, uint64_t /*slot*
   GLB_ENFORCE_LE(offset + nbytes, size, "get: local range exceeds buffer");
   GLB_ENFORCE_LE(roffset + nbytes, k->size, "get: remote range exceeds region");
   GLB_ENFORCE_NE(k->rank, context_->rank, "get from self");
-  noteSource(k->rank);
+  notePeer(k->rank);
   uint64_t req = context_->registerPendingGet(this, offset, nbytes);
   context_->tcpPair(k->rank)->sendGetRequest(req, k->regionId, roffset, nbytes);
 }

@@ -47,10 +47,17 @@ class UnboundBuffer : public ::glb::transport::UnboundBuffer {
 
  private:
   void throwIfException();  // requires m_
-  void noteSource(int rank);  // requires no lock
-  // Spin-then-block (see Pair::spinWait): poll the pairs this buffer receives from
-  // for a bounded time. `lock` holds m_ on entry and on return.
-  void spinRecv(std::unique_lock<std::mutex>& lock);
+  void notePeer(int rank);  // requires no lock
+  // Spin-then-block (see Pair::spinWait): poll the pairs this buffer talks to for a
+  // bounded time or until done() holds. `lock` holds m_ on entry and on return.
+  template <typename Pred>
+  void spinUntil(std::unique_lock<std::mutex>& lock, Pred done);
+  // Pairs in sync mode are detached from the loop thread, so the waiter has to read
+  // them itself for as long as it waits (the reference rejects unbound buffers on
+  // sync pairs outright). Returns false on timeout; true when done() holds or when
+  // no peer of this buffer is in sync mode (then the caller blocks on the condvar).
+  template <typename Pred>
+  bool driveSyncPairs(std::unique_lock<std::mutex>& lock, Pred done, std::chrono::milliseconds timeout);
 
   std::shared_ptr<Context> context_;
   std::mutex m_;
@@ -60,7 +67,7 @@ class UnboundBuffer : public ::glb::transport::UnboundBuffer {
   bool abortWaitSend_ = false;
   std::deque<int> recvRanks_;  // one entry per completed recv
   std::deque<int> sendRanks_;  // one entry per completed send
-  std::vector<int> spinRanks_;  // peers a recv/get was ever posted for (sticky, small)
+  std::vector<int> spinRanks_;  // peers this buffer ever sent to / received from (sticky, small)
   bool failed_ = false;
   std::string exMsg_;
   mutable uint64_t regionId_ = 0;

@@ -34,6 +34,19 @@ def main():
             buf = np.full(1000, rank + 1, np.float64)
             gb.allreduce(ctx, buf)
             assert buf[0] == size * (size + 1) / 2, buf[0]
+        elif mode == "large_once":
+            # Above GLB_TCP_CMA_MIN: payloads are pulled with process_vm_readv between
+            # real processes; the result and the counter are both checked.
+            n = int(args[0]) if args else (1 << 20)
+            before = gb._C.tcp_stats()["cma_messages"]
+            buf = np.full(n, rank + 1, np.float32)
+            for _ in range(3):
+                buf[:] = rank + 1
+                gb.allreduce(ctx, buf)
+                assert buf[0] == size * (size + 1) / 2 and buf[-1] == buf[0], (buf[0], buf[-1])
+            want = os.environ.get("GLB_TCP_CMA", "1") != "0"
+            got = gb._C.tcp_stats()["cma_messages"] > before
+            assert got == want, (got, want)
         elif mode == "sendrecv_loop":
             peer = (rank + 1) % size
             src = (rank - 1) % size
@@ -50,6 +63,9 @@ def main():
             raise SystemExit(f"unknown mode {mode}")
     except gb.IoError as e:
         print(f"rank {rank}: IoError: {e}", file=sys.stderr)
+        if os.environ.get("GLB_TEST_TRACEBACK"):
+            import traceback
+            traceback.print_exc()
         sys.exit(10)
     sys.exit(0)
 

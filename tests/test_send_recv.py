@@ -245,24 +245,26 @@ def test_put_get_remote_key():
     assert all(gb.spawn_threads(size, fn))
 
 
-def test_bound_buffers_and_sync_mode():
+@pytest.mark.parametrize("half", [32, 1 << 17])  # small: eager; large: single-copy path
+def test_bound_buffers_and_sync_mode(half):
     for sync, busy in ((False, False), (True, False), (True, True)):
         def fn(ctx):
             peer = 1 - ctx.rank
             pair = ctx.get_pair(peer)
             if sync:
                 pair.set_sync(True, busy)
-            src = np.arange(32, dtype=np.float32) + ctx.rank
-            dst = np.zeros(64, np.float32)
+            src = np.arange(half, dtype=np.float32) + ctx.rank
+            dst = np.zeros(2 * half, np.float32)
             slot = ctx.next_slot()
             sb = pair.create_send_buffer(slot, src.ctypes.data, src.nbytes)
             rb = pair.create_recv_buffer(slot, dst.ctypes.data, dst.nbytes)
             # write into the second half of the peer's buffer (remote offset)
-            sb.send(0, src.nbytes, 32 * 4)
-            rb.wait_recv()
-            sb.wait_send()
-            np.testing.assert_array_equal(dst[32:], np.arange(32, dtype=np.float32) + peer)
-            np.testing.assert_array_equal(dst[:32], np.zeros(32, np.float32))
+            for _ in range(3):
+                sb.send(0, src.nbytes, half * 4)
+                rb.wait_recv()
+                sb.wait_send()
+            np.testing.assert_array_equal(dst[half:], np.arange(half, dtype=np.float32) + peer)
+            np.testing.assert_array_equal(dst[:half], np.zeros(half, np.float32))
             return True
 
         assert all(gb.spawn_threads(2, fn))
@@ -276,3 +278,98 @@ def test_lazy_device_and_shared_device():
 
     assert gb.spawn_threads(4, fn, lazy=True) == [10.0] * 4
     assert gb.spawn_threads(4, fn, shared_device=True) == [10.0] * 4
+
+
+def test_large_messages_take_the_single_copy_path():
+    """>= GLB_TCP_CMA_MIN bytes: header on the wire, payload pulled from the sender's address
+    space (here: the same process) — unbound send/recv incl. unexpected arrival, bound
+    buffers with a remote offset, put and get."""
+    n = 1 << 18  # 1 MiB of float32
+    before = _C.tcp_stats()["cma_messages"]
+
+    def fn(ctx):
+        peer = 1 - ctx.rank
+        gb.barrier(ctx)  # the capability handshake has long finished after a round trip
+        time.sleep(0.05)
+        # unbound, posted first on rank 0, unexpected on rank 1
+        src = np.arange(n, dtype=np.float32) + ctx.rank
+        dst = np.zeros(n, np.float32)
+        us, ud = ub(ctx, src), ub(ctx, dst)
+        if ctx.rank == 0:
+            ud.recv(peer, 7)
+            gb.barrier(ctx)
+            us.send(peer, 7)
+        else:
+            gb.barrier(ctx)
+            us.send(peer, 7)
+            time.sleep(0.1)
+            ud.recv(peer, 7)
+        assert ud.wait_recv() == peer
+        assert us.wait_send() == peer
+        np.testing.assert_array_equal(dst, np.arange(n, dtype=np.float32) + peer)
+        # bound, remote offset
+        pair = ctx.get_pair(peer)
+        big = np.zeros(2 * n, np.float32)
+        slot = ctx.next_slot()
+        sb = pair.create_send_buffer(slot, src.ctypes.data, src.nbytes)
+        rb = pair.create_recv_buffer(slot, big.ctypes.data, big.nbytes)
+        sb.send(0, src.nbytes, n * 4)
+        rb.wait_recv()
+        sb.wait_send()
+        np.testing.assert_array_equal(big[n:], np.arange(n, dtype=np.float32) + peer)
+        assert not big[:n].any()
+        # one-sided
+        window = np.full(n, ctx.rank + 10, np.float32)
+        uw = ub(ctx, window)
+        key = uw.get_remote_key().encode()
+        keys = np.zeros(128, np.uint8)
+        mine = np.zeros(64, np.uint8)
+        mine[:len(key)] = np.frombuffer(key, np.uint8)
+        gb.allgather(ctx, keys, mine)
+        peer_key = bytes(keys[peer * 64:(peer + 1) * 64]).rstrip(b"\0").decode()
+        got = np.zeros(n, np.float32)
+        ug = ub(ctx, got)
+        ug.get(ctx, peer_key, 0, 0, 0, got.nbytes)
+        assert ug.wait_recv() == peer
+        np.testing.assert_array_equal(got, np.full(n, peer + 10, np.float32))
+        gb.barrier(ctx)
+        us.put(ctx, peer_key, 0, 0, 0, src.nbytes)
+        us.wait_send()
+        ug.get(ctx, peer_key, 0, 0, 0, got.nbytes)  # ordered behind the put
+        ug.wait_recv()
+        np.testing.assert_array_equal(got, src)
+        gb.barrier(ctx)
+        return True
+
+    assert all(gb.spawn_threads(2, fn))
+    assert _C.tcp_stats()["cma_messages"] - before >= 10
+
+
+@pytest.mark.parametrize("busy", [False, True])
+def test_unbound_buffers_on_sync_pairs(busy):
+    """Pairs switched to sync mode are detached from the loop thread; unbound-buffer waits
+    then read the socket themselves, so the new-style collectives keep working (the
+    reference rejects unbound buffers on sync pairs, tcp/pair.cc)."""
+    size = 3
+
+    def fn(ctx):
+        for r in range(size):
+            if r != ctx.rank:
+                ctx.get_pair(r).set_sync(True, busy)
+        x = np.full(1000, ctx.rank + 1, np.float32)
+        for _ in range(5):
+            x[:] = ctx.rank + 1
+            gb.allreduce(ctx, x)
+            assert x[0] == 6
+        big = np.full(1 << 18, ctx.rank + 1, np.float32)  # single-copy path, FIN read by the waiter
+        gb.allreduce(ctx, big)
+        assert big[0] == 6 and big[-1] == 6
+        out = np.zeros(size * 4, np.int64)
+        gb.allgather(ctx, out, np.full(4, ctx.rank, np.int64))
+        np.testing.assert_array_equal(out, np.repeat(np.arange(size), 4))
+        gb.barrier(ctx)
+        return True
+
+    t0 = time.time()
+    assert all(gb.spawn_threads(size, fn))
+    assert time.time() - t0 < 8  # the closing barrier of spawn_threads must not time out

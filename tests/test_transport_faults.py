@@ -13,9 +13,9 @@ import pytest
 WORKER = os.path.join(os.path.dirname(os.path.abspath(__file__)), "multiproc_worker.py")
 
 
-def launch(size, mode, *args, timeout_ms=3000):
+def launch(size, mode, *args, timeout_ms=3000, extra_env=None):
     d = tempfile.mkdtemp(prefix="glb_mp_")
-    env = dict(os.environ, GLB_TEST_TIMEOUT_MS=str(timeout_ms))
+    env = dict(os.environ, GLB_TEST_TIMEOUT_MS=str(timeout_ms), **(extra_env or {}))
     procs = [subprocess.Popen([sys.executable, WORKER, d, str(r), str(size), mode, *map(str, args)], env=env,
                               stderr=subprocess.PIPE, text=True) for r in range(size)]
     return d, procs
@@ -48,11 +48,24 @@ def test_healthy_run(size):
     assert reap(procs, 60) == [0] * size
 
 
+@pytest.mark.parametrize("cma", ["1", "0"])
+@pytest.mark.parametrize("size", [2, 3])
+def test_large_messages_between_processes(size, cma):
+    """Same-host single-copy path (process_vm_readv) on and off; the worker asserts the
+    path it expected was the one that carried the payload."""
+    d, procs = launch(size, "large_once", 1 << 20, timeout_ms=20000, extra_env={"GLB_TCP_CMA": cma})
+    codes = reap(procs, 90)
+    assert codes == [0] * size, (codes, [p.stderr.read()[-400:] for p in procs])
+
+
 @pytest.mark.parametrize("size", [2, 3, 4])
-@pytest.mark.parametrize("mode", ["allreduce_loop", "sendrecv_loop"])
+@pytest.mark.parametrize("mode", ["allreduce_loop", "sendrecv_loop", "allreduce_loop_large"])
 def test_sigkill_is_detected(size, mode):
     timeout_ms = 3000
-    d, procs = launch(size, mode, timeout_ms=timeout_ms)
+    args = ()
+    if mode == "allreduce_loop_large":  # dies while peers pull from / wait for FIN of its memory
+        mode, args = "allreduce_loop", (1 << 19,)
+    d, procs = launch(size, mode, *args, timeout_ms=timeout_ms)
     wait_ready(d, size)
     time.sleep(0.3)
     t0 = time.time()

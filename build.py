@@ -11,7 +11,10 @@ Everything CUDA is compiled with  -gencode arch=compute_100a,code=sm_100a -linei
 cudart is linked statically and the driver API / NCCL are resolved at run time
 (cudaGetDriverEntryPoint / dlopen), so the extension imports on a CPU-only box.
 
-Usage: python build.py [-j N] [--verbose] [--clean]
+Usage: python build.py [-j N] [--verbose] [--clean] [--sanitize thread|address|undefined]
+
+--sanitize X builds only gloo_b200/bin/glb_benchmark_<X> (host code instrumented with
+-fsanitize=X, objects under build/san-X) - the reference's -DSANITIZE=<x> switch.
 """
 from __future__ import annotations
 
@@ -60,10 +63,13 @@ def collect():
     return lib_cc, lib_cu, py_cc, bins
 
 
-def write_ninja(verbose: bool) -> Path:
+def write_ninja(verbose: bool, sanitize: str = "") -> Path:
     import pybind11
 
-    BUILD.mkdir(exist_ok=True)
+    global BUILD
+    if sanitize:
+        BUILD = ROOT / "build" / f"san-{sanitize}"
+    BUILD.mkdir(parents=True, exist_ok=True)
     (PKG / "lib").mkdir(parents=True, exist_ok=True)
     (PKG / "bin").mkdir(parents=True, exist_ok=True)
     lib_cc, lib_cu, py_cc, bins = collect()
@@ -85,10 +91,14 @@ def write_ninja(verbose: bool) -> Path:
     )
     if verbose:
         nvccflags += " -Xptxas -v"
+    if sanitize:
+        cxxflags = cxxflags.replace("-O2 -g1", "-O1 -g") + f" -fsanitize={sanitize} -fno-omit-frame-pointer"
     pyflags = f"-I{py_inc} -I{pybind11.get_include()}"
     ldflags = (
         f"-L{CUDA_HOME}/lib64 -lcudart_static -ldl -lrt -pthread -Wl,--exclude-libs,libcudart_static.a"
     )
+    if sanitize:
+        ldflags += f" -fsanitize={sanitize}"
 
     out = []
     w = out.append
@@ -140,16 +150,17 @@ def write_ninja(verbose: bool) -> Path:
         w("  extra = $pyflags -fvisibility=hidden")
 
     targets = []
-    ext = PKG / f"_C{ext_suffix()}"
-    w(f"build {ext}: link_shared {' '.join(lib_objs + py_objs)}")
-    targets.append(str(ext))
-    lib = PKG / "lib" / "libglb.so"
-    w(f"build {lib}: link_shared {' '.join(lib_objs)}")
-    targets.append(str(lib))
+    if not sanitize:
+        ext = PKG / f"_C{ext_suffix()}"
+        w(f"build {ext}: link_shared {' '.join(lib_objs + py_objs)}")
+        targets.append(str(ext))
+        lib = PKG / "lib" / "libglb.so"
+        w(f"build {lib}: link_shared {' '.join(lib_objs)}")
+        targets.append(str(lib))
     for name, p in bins.items():
         o = obj(p)
         w(f"build {o}: cxx {p}")
-        exe = PKG / "bin" / f"glb_{name}"
+        exe = PKG / "bin" / (f"glb_{name}_{sanitize}" if sanitize else f"glb_{name}")
         w(f"build {exe}: link_exe {o} {' '.join(lib_objs)}")
         targets.append(str(exe))
     w("")
@@ -159,10 +170,10 @@ def write_ninja(verbose: bool) -> Path:
     return path
 
 
-def build(jobs: int | None = None, verbose: bool = False, clean: bool = False) -> None:
+def build(jobs: int | None = None, verbose: bool = False, clean: bool = False, sanitize: str = "") -> None:
     if clean and BUILD.exists():
         shutil.rmtree(BUILD)
-    ninja_file = write_ninja(verbose)
+    ninja_file = write_ninja(verbose, sanitize)
     cmd = [shutil.which("ninja") or "ninja", "-f", str(ninja_file)]
     if jobs:
         cmd += ["-j", str(jobs)]
@@ -176,5 +187,6 @@ if __name__ == "__main__":
     ap.add_argument("-j", type=int, default=None)
     ap.add_argument("--verbose", action="store_true")
     ap.add_argument("--clean", action="store_true")
+    ap.add_argument("--sanitize", default="", help="thread | address | undefined: build glb_benchmark_<x> only")
     a = ap.parse_args()
-    build(a.j, a.verbose, a.clean)
+    build(a.j, a.verbose, a.clean, a.sanitize)

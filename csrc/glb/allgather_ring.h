@@ -32,7 +32,7 @@ class AllgatherRing : public Algorithm {
     sendData_ = right->createSendBuffer(dataSlot, outPtr_, total);
     recvData_ = left->createRecvBuffer(dataSlot, outPtr_, total);
     sendAck_ = left->createSendBuffer(ackSlot, &token_, sizeof(token_));
-    recvAck_ = right->createRecvBuffer(ackSlot, &token_, sizeof(token_));
+    recvAck_ = right->createRecvBuffer(ackSlot, &tokenIn_, sizeof(tokenIn_));
   }
 
   void run() override {
@@ -64,7 +64,8 @@ class AllgatherRing : public Algorithm {
   const size_t count_;
   const size_t bytes_;
   const size_t inputStride_;
-  int token_ = 0;
+  int token_ = 0;    // ack source (never written)
+  int tokenIn_ = 0;  // where the neighbour's ack lands
   std::unique_ptr<transport::Buffer> sendData_, recvData_, sendAck_, recvAck_;
 };
 

@@ -31,7 +31,7 @@ class AllreduceRing : public Algorithm {
     sendData_ = right->createSendBuffer(dataSlot, outbox_.data(), bytes_);
     recvData_ = left->createRecvBuffer(dataSlot, inbox_.data(), bytes_);
     sendAck_ = left->createSendBuffer(ackSlot, &token_, sizeof(token_));
-    recvAck_ = right->createRecvBuffer(ackSlot, &token_, sizeof(token_));
+    recvAck_ = right->createRecvBuffer(ackSlot, &tokenIn_, sizeof(tokenIn_));
   }
 
   void run() override {
@@ -61,7 +61,8 @@ class AllreduceRing : public Algorithm {
   const ReductionFunction<T>* fn_;
   std::vector<T> inbox_;
   std::vector<T> outbox_;
-  int token_ = 0;
+  int token_ = 0;    // ack source (never written)
+  int tokenIn_ = 0;  // where the neighbour's ack lands
   std::unique_ptr<transport::Buffer> sendData_, recvData_, sendAck_, recvAck_;
 };
 

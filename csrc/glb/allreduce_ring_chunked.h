@@ -40,7 +40,7 @@ class AllreduceRingChunked : public Algorithm {
       rsSend_[l] = right->createSendBuffer(slot, ptrs_[0], bytes_);
       rsRecv_[l] = left->createRecvBuffer(slot, inbox_[l].data(), maxChunk_ * sizeof(T));
       ackSend_[l] = left->createSendBuffer(ackSlot, &token_, sizeof(token_));
-      ackRecv_[l] = right->createRecvBuffer(ackSlot, &token_, sizeof(token_));
+      ackRecv_[l] = right->createRecvBuffer(ackSlot, &tokenIn_[l], sizeof(token_));
       agSend_[l] = right->createSendBuffer(agSlot, ptrs_[0], bytes_);
       agRecv_[l] = left->createRecvBuffer(agSlot, ptrs_[0], bytes_);
     }
@@ -98,7 +98,8 @@ class AllreduceRingChunked : public Algorithm {
   const size_t bytes_;
   const ReductionFunction<T>* fn_;
   size_t maxChunk_ = 0;
-  int token_ = 0;
+  int token_ = 0;             // ack source (never written)
+  int tokenIn_[2] = {0, 0};   // where the right neighbour's acks land, per lane
   std::vector<T> inbox_[2];
   std::unique_ptr<transport::Buffer> rsSend_[2], rsRecv_[2], ackSend_[2], ackRecv_[2], agSend_[2], agRecv_[2];
 };

@@ -26,7 +26,7 @@ class BarrierAllToAll : public Barrier {
       auto& pair = getPair(i);
       GLB_ENFORCE(pair, "pair missing (rank ", i, ")");
       send_.push_back(pair->createSendBuffer(slot, &token_, sizeof(token_)));
-      recv_.push_back(pair->createRecvBuffer(slot, &token_, sizeof(token_)));
+      recv_.push_back(pair->createRecvBuffer(slot, sink(), sizeof(token_)));
     }
   }
   void run() override {
@@ -36,7 +36,14 @@ class BarrierAllToAll : public Barrier {
   }
 
  protected:
+  // Tokens are sent from token_ (never written) and land in one sink word per peer,
+  // so concurrent arrivals on different pairs never touch the same memory.
+  int* sink() {
+    sinks_.push_back(std::make_unique<int>(0));
+    return sinks_.back().get();
+  }
   int token_ = 0;
+  std::vector<std::unique_ptr<int>> sinks_;
   std::vector<std::unique_ptr<transport::Buffer>> send_;
   std::vector<std::unique_ptr<transport::Buffer>> recv_;
 };
@@ -54,13 +61,13 @@ class BarrierAllToOne : public Barrier {
         auto& pair = getPair(i);
         GLB_ENFORCE(pair, "pair missing (rank ", i, ")");
         send_.push_back(pair->createSendBuffer(slot, &token_, sizeof(token_)));
-        recv_.push_back(pair->createRecvBuffer(slot, &token_, sizeof(token_)));
+        recv_.push_back(pair->createRecvBuffer(slot, sink(), sizeof(token_)));
       }
     } else {
       auto& pair = getPair(rootRank_);
       GLB_ENFORCE(pair, "pair missing (rank ", rootRank_, ")");
       send_.push_back(pair->createSendBuffer(slot, &token_, sizeof(token_)));
-      recv_.push_back(pair->createRecvBuffer(slot, &token_, sizeof(token_)));
+      recv_.push_back(pair->createRecvBuffer(slot, sink(), sizeof(token_)));
     }
   }
   void run() override {
@@ -77,7 +84,14 @@ class BarrierAllToOne : public Barrier {
 
  protected:
   const int rootRank_;
+  // Tokens are sent from token_ (never written) and land in one sink word per peer,
+  // so concurrent arrivals on different pairs never touch the same memory.
+  int* sink() {
+    sinks_.push_back(std::make_unique<int>(0));
+    return sinks_.back().get();
+  }
   int token_ = 0;
+  std::vector<std::unique_ptr<int>> sinks_;
   std::vector<std::unique_ptr<transport::Buffer>> send_;
   std::vector<std::unique_ptr<transport::Buffer>> recv_;
 };

@@ -32,7 +32,8 @@ class BroadcastOneToAll : public Algorithm {
         if (i == rootRank_) continue;
         auto& pair = getPair(i);
         data_.push_back(pair->createSendBuffer(dataSlot, ptrs_[rootPointerRank_], bytes_));
-        cts_.push_back(pair->createRecvBuffer(ctsSlot, &token_, sizeof(token_)));
+        ctsSink_.push_back(std::make_unique<int>(0));
+        cts_.push_back(pair->createRecvBuffer(ctsSlot, ctsSink_.back().get(), sizeof(token_)));
       }
     } else {
       auto& pair = getPair(rootRank_);
@@ -68,7 +69,8 @@ class BroadcastOneToAll : public Algorithm {
   const size_t bytes_;
   const int rootRank_;
   const int rootPointerRank_;
-  int token_ = 0;
+  int token_ = 0;  // clear-to-send source; arrivals land in one sink word per peer
+  std::vector<std::unique_ptr<int>> ctsSink_;
   std::vector<std::unique_ptr<transport::Buffer>> data_;
   std::vector<std::unique_ptr<transport::Buffer>> cts_;
 };

@@ -13,6 +13,7 @@
 // after (used for non-power-of-two halving-doubling).
 #pragma once
 
+#include <cstdint>
 #include <cstring>
 #include <memory>
 #include <vector>
@@ -78,6 +79,7 @@ class MixedRadix {
     // algorithm instances on this context stay in step.
     const int rsSlot = context_->nextSlot(std::max(K, 1));
     const int agSlot = context_->nextSlot(std::max(K, 1));
+    const int ackSlot = context_->nextSlot(std::max(K, 1));
     if (isExtra_) return;
 
     stride_.resize(K);
@@ -112,6 +114,14 @@ class MixedRadix {
         if (doAllgather_) {
           p.agSend = pair->createSendBuffer(agSlot + i, data_, count_ * sizeof(T));
           p.agRecv = pair->createRecvBuffer(agSlot + i, data_, count_ * sizeof(T));
+        } else {
+          // Without the allgather phase nothing flows back to the sender, so a fast
+          // peer could start its next run and overwrite this rank's landing zone
+          // while it is still being reduced. One credit per (step, peer): the
+          // receiver returns it after consuming, the sender needs it to send again.
+          p.creditIn = std::make_unique<int>(0);
+          p.ackSend = pair->createSendBuffer(ackSlot + i, &credit_, sizeof(credit_));
+          p.ackRecv = pair->createRecvBuffer(ackSlot + i, p.creditIn.get(), sizeof(credit_));
         }
         st.peers.push_back(std::move(p));
         k++;
@@ -159,13 +169,21 @@ class MixedRadix {
     for (int i = 0; i < K; i++) {
       auto& st = steps_[i];
       const Range mine = blocks_[i + 1];
-      for (auto& p : st.peers) p.rsSend->send(p.theirs.off * sizeof(T), p.theirs.len * sizeof(T), 0);
+      for (auto& p : st.peers) {
+        if (!doAllgather_ && runs_ > 0) p.ackRecv->waitRecv();
+        p.rsSend->send(p.theirs.off * sizeof(T), p.theirs.len * sizeof(T), 0);
+      }
       for (auto& p : st.peers) {
         p.rsRecv->waitRecv();
         if (mine.len > 0) fn_->call(data_ + mine.off, st.scratch.data() + p.scratchOff, mine.len);
+        if (!doAllgather_) p.ackSend->send();
       }
-      for (auto& p : st.peers) p.rsSend->waitSend();
+      for (auto& p : st.peers) {
+        p.rsSend->waitSend();
+        if (!doAllgather_) p.ackSend->waitSend();
+      }
     }
+    runs_++;
   }
 
   void allgather() {
@@ -186,7 +204,10 @@ class MixedRadix {
   struct Peer {
     Range theirs;
     size_t scratchOff = 0;
-    std::unique_ptr<transport::Buffer> rsSend, rsRecv, agSend, agRecv;
+    // Declared before the buffers: members die in reverse order, and the landing
+    // word must outlive the recv buffer that points at it.
+    std::unique_ptr<int> creditIn;
+    std::unique_ptr<transport::Buffer> rsSend, rsRecv, agSend, agRecv, ackSend, ackRecv;
   };
   struct Step {
     std::vector<T> scratch;
@@ -202,6 +223,8 @@ class MixedRadix {
   const int r_;
   const int core_;
   const bool doAllgather_;
+  int credit_ = 0;     // credit source (never written)
+  uint64_t runs_ = 0;
   bool isExtra_ = false;
   bool hasExtra_ = false;
   std::vector<int> stride_, digit_;

@@ -1,0 +1,29 @@
+#!/bin/sh
+# Sanitizer pass over the host transport and collectives (the reference's -DSANITIZE=<x>):
+# P ranks as processes x 2 threads each, running the instrumented benchmark binary built by
+# `python build.py --sanitize <thread|address|undefined>`.
+# usage: scripts/sanitizer_run.sh <thread|address|undefined> [P] [benchmark ...]
+SAN=${1:-thread}; P=${2:-3}; shift; shift
+BIN=gloo_b200/bin/glb_benchmark_$SAN
+[ -x $BIN ] || python build.py --sanitize $SAN || exit 1
+[ $# -gt 0 ] || set -- allreduce_ring allreduce_ring_chunked allreduce_halving_doubling allreduce_bcube \
+  new_allreduce_ring new_allreduce_bcube reduce_scatter new_reduce_scatter allgather allgather_ring \
+  alltoall alltoall_v gather scatter reduce broadcast broadcast_one_to_all barrier_all_to_all \
+  barrier_all_to_one pairwise_exchange sendrecv_roundtrip sendrecv_stress
+OUT=$(mktemp -d /tmp/glb_san.XXXXXX)
+for NAME in "$@"; do
+  for EL in 1000 500000; do
+    D=$(mktemp -d /tmp/glb_san_rdv.XXXXXX)
+    r=0; while [ $r -lt $P ]; do
+      TSAN_OPTIONS="suppressions=$PWD/.tsan-suppressions halt_on_error=0 second_deadlock_stack=1 log_path=$OUT/$NAME.$EL.r$r" \
+      ASAN_OPTIONS="detect_leaks=1 log_path=$OUT/$NAME.$EL.r$r" \
+      UBSAN_OPTIONS="print_stacktrace=1 log_path=$OUT/$NAME.$EL.r$r" \
+        $BIN --size $P --rank $r --shared-path $D --transport tcp --iteration-count 30 --warmup-iters 2 \
+             --threads 2 --elements $EL $NAME >$OUT/$NAME.$EL.r$r.stdout 2>&1 &
+      r=$((r+1)); done
+    wait; rm -rf $D
+  done
+done
+n=$(cat $OUT/*.r[0-9]*.[0-9]* 2>/dev/null | grep -c "WARNING: ThreadSanitizer\|ERROR: AddressSanitizer\|ERROR: LeakSanitizer\|runtime error")
+echo "$SAN sanitizer reports: $n (logs in $OUT)"
+[ "$n" = 0 ]

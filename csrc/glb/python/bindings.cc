@@ -26,6 +26,7 @@
 #include "glb/rendezvous/file_store.h"
 #include "glb/rendezvous/hash_store.h"
 #include "glb/rendezvous/prefix_store.h"
+#include "glb/rendezvous/redis_store.h"
 #include "glb/scatter.h"
 #include "glb/transport/tcp/device.h"
 #include "glb/transport/tcp/tls/device.h"
@@ -199,6 +200,10 @@ PYBIND11_MODULE(_C, m) {
       .def_property_readonly("path", &rendezvous::FileStore::basePath);
   py::class_<rendezvous::PrefixStore, IStore, std::shared_ptr<rendezvous::PrefixStore>>(m, "PrefixStore")
       .def(py::init<const std::string&, std::shared_ptr<IStore>>());
+  py::class_<rendezvous::RedisStore, IStore, std::shared_ptr<rendezvous::RedisStore>>(m, "RedisStore")
+      .def(py::init<const std::string&, int>(), py::arg("host"), py::arg("port") = 6379,
+           py::call_guard<py::gil_scoped_release>())
+      .def("check", &rendezvous::RedisStore::check, py::call_guard<py::gil_scoped_release>());
 
   // ---- transport ------------------------------------------------------------------
   py::class_<transport::Device, std::shared_ptr<transport::Device>>(m, "Device")

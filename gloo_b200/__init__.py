@@ -46,6 +46,7 @@ from ._C import (  # noqa: E402
     FileStore,
     GlbError,
     HashStore,
+    RedisStore,
     InvalidOperationError,
     IoError,
     PrefixStore,
@@ -70,7 +71,7 @@ from .ops.host import (  # noqa: E402
 from .utils.launch import create_device, init_context, spawn_threads  # noqa: E402
 
 __all__ = [
-    "Context", "BaseContext", "ContextFactory", "Store", "HashStore", "FileStore", "PrefixStore",
+    "Context", "BaseContext", "ContextFactory", "Store", "HashStore", "FileStore", "PrefixStore", "RedisStore",
     "GlbError", "IoError", "TimeoutError", "InvalidOperationError", "EnforceError",
     "DataType", "ReduceOp", "Algorithm",
     "allreduce", "reduce", "reduce_scatter", "broadcast", "allgather", "allgatherv", "alltoall",

@@ -1,5 +1,7 @@
 """Old-style host algorithms — mirrors gloo/test/allreduce_test.cc:143-299,
 reduce_scatter_test.cc, allgather_test.cc, broadcast_test.cc, barrier_test.cc."""
+import time
+
 import numpy as np
 import pytest
 
@@ -102,6 +104,32 @@ def test_reduce_scatter_hd(size):
             alg.ReduceScatterHalvingDoubling(ctx, buf2, recv2).run()
             if ctx.rank == size - 1:
                 np.testing.assert_allclose(buf2[0], _expected(size, 1, count, np.float64))
+        return True
+
+    assert all(gb.spawn_threads(size, fn))
+
+
+@pytest.mark.parametrize("size", [2, 3, 6])
+def test_reduce_scatter_hd_rerun_flow_control(size):
+    """One instance, many runs, fresh data every run, ranks deliberately out of step.
+    Without the allgather phase nothing flows back to a sender, so the engine hands out
+    one credit per (step, peer): a fast rank must not refill a slow rank's landing zone
+    while that rank is still reducing the previous run (found with ThreadSanitizer)."""
+    count = 60000
+
+    def fn(ctx):
+        base, rem = divmod(count, size)
+        recv = [base + (1 if r < rem else 0) for r in range(size)]
+        off = int(np.sum(recv[:ctx.rank]))
+        buf = np.zeros(count, np.float64)
+        algo = alg.ReduceScatterHalvingDoubling(ctx, [buf], recv)
+        for it in range(25):
+            buf[:] = np.arange(count) * (it + 1) + ctx.rank
+            if ctx.rank == it % size:
+                time.sleep(0.002)  # this rank enters late; the others are already sending
+            algo.run()
+            want = np.arange(off, off + recv[ctx.rank]) * (it + 1) * size + size * (size - 1) / 2
+            np.testing.assert_allclose(buf[:recv[ctx.rank]], want)
         return True
 
     assert all(gb.spawn_threads(size, fn))

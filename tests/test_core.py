@@ -231,3 +231,58 @@ def test_linux_probes():
         assert _C.pci_distance(b, b) == 0
     assert _C.pci_distance("ffff:ff:ff.f", "ffff:ff:ff.e") == -1
     assert _C.hostname()
+
+
+def test_redis_store_against_resp_server():
+    """RedisStore speaks RESP itself (no hiredis): write-once SETNX keys, GET, EXISTS-polling
+    wait with timeout, binary-safe values, the v2 API, and a full-mesh rendezvous through it
+    (reference: gloo/rendezvous/redis_store.cc:35-119)."""
+    import subprocess
+    import sys
+
+    from fake_redis import resp_call
+
+    here = os.path.dirname(os.path.abspath(__file__))
+    srv = subprocess.Popen([sys.executable, os.path.join(here, "fake_redis.py")], stdout=subprocess.PIPE, text=True)
+    try:
+        port = int(srv.stdout.readline())
+        s = gb.RedisStore("127.0.0.1", port)
+        blob = bytes(range(256)) * 3 + b"\r\n$5\r\n"  # framing characters inside the value
+        s.set("k", blob)
+        assert s.get("k") == blob
+        with pytest.raises(gb.GlbError):
+            s.set("k", b"again")  # keys are write-once
+        assert s.check(["k"]) and not s.check(["k", "missing"])
+        t0 = time.time()
+        with pytest.raises(gb.IoError):
+            s.wait(["missing"], 150)
+        assert 0.1 < time.time() - t0 < 2.0
+        threading.Timer(0.1, lambda: resp_call(port, b"SET", b"late", b"x")).start()
+        s.wait(["late"], 5000)
+        assert s.has_extended_api()
+        assert s.add("ctr", 5) == 5 and s.add("ctr", -2) == 3
+        s.append("log", b"ab")
+        s.append("log", b"cd")
+        assert s.get("log") == b"abcd"
+        assert s.multi_get(["k", "log"]) == [blob, b"abcd"]
+
+        # rendezvous through the store, one client connection per rank, namespaced by PrefixStore
+        def rank(r, out):
+            store = gb.PrefixStore("job42", gb.RedisStore("127.0.0.1", port))
+            ctx = gb.Context(r, 3)
+            ctx.connect_full_mesh(store, gb.create_device())
+            x = np.full(16, r + 1, np.float32)
+            gb.allreduce(ctx, x)
+            out[r] = float(x[0])
+            gb.barrier(ctx)
+
+        out = [None] * 3
+        ths = [threading.Thread(target=rank, args=(r, out)) for r in range(3)]
+        [t.start() for t in ths]
+        [t.join(60) for t in ths]
+        assert out == [6.0, 6.0, 6.0]
+        assert any(k.startswith(b"job42/") for k in resp_call(port, b"KEYS", b"*"))
+        assert {b"SETNX", b"GET", b"EXISTS"} <= set(resp_call(port, b"_STATS"))
+    finally:
+        srv.kill()
+        srv.wait()

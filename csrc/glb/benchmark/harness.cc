@@ -16,7 +16,10 @@
 #include "glb/rendezvous/file_store.h"
 #include "glb/rendezvous/prefix_store.h"
 #include "glb/rendezvous/redis_store.h"
+#include "glb/transport/ibverbs/device.h"
 #include "glb/transport/tcp/device.h"
+#include "glb/transport/tcp/tls/device.h"
+#include "glb/transport/uv/device.h"
 
 namespace glb {
 namespace benchmark {
@@ -35,7 +38,9 @@ static void usage(const char* argv0) {
                "  -x, --prefix=PREFIX    Rendezvous prefix (unique for this run)\n"
                "      --shared-path=PATH File system rendezvous with this shared path\n\n"
                "Transport:\n"
-               "  -t, --transport=TRANSPORT Transport to use (tcp)\n"
+               "  -t, --transport=TRANSPORT Transport to use (tcp, tls, uv; ibverbs is probed and reported)\n"
+               "      --pkey=FILE --cert=FILE --ca-file=FILE --ca-path=DIR   Credentials for --transport=tls\n"
+               "      --ib-device=NAME --ib-index=N --ib-port=N              Accepted for --transport=ibverbs\n"
                "      --tcp-device=DEV[,DEV...]  Network interface(s) or address to use\n"
                "      --sync=BOOL           Switch pairs to sync mode (default: false)\n"
                "      --busy-poll=BOOL      Busy-poll in sync mode (default: false)\n\n"
@@ -84,7 +89,8 @@ Options parseOptions(int argc, char** argv) {
   enum {
     OPT_SHARED = 1000, OPT_SYNC, OPT_BUSY, OPT_TCPDEV, OPT_NOVERIFY, OPT_SHOWERR, OPT_INPUTS, OPT_ELEMENTS,
     OPT_WARMUP, OPT_ITERCOUNT, OPT_ITERTIME, OPT_THREADS, OPT_NANOS, OPT_GPUDIRECT, OPT_HALF, OPT_DEST, OPT_BASE,
-    OPT_MESSAGES, OPT_CUDAALGO, OPT_CUDADEV, OPT_EXTSWEEP, OPT_HELP
+    OPT_MESSAGES, OPT_CUDAALGO, OPT_CUDADEV, OPT_EXTSWEEP, OPT_PKEY, OPT_CERT, OPT_CAFILE, OPT_CAPATH,
+    OPT_IBDEV, OPT_IBINDEX, OPT_IBPORT, OPT_HELP
   };
   static struct option longopts[] = {
       {"size", required_argument, nullptr, 's'},       {"rank", required_argument, nullptr, 'r'},
@@ -102,6 +108,10 @@ Options parseOptions(int argc, char** argv) {
       {"destinations", required_argument, nullptr, OPT_DEST}, {"base", required_argument, nullptr, OPT_BASE},
       {"messages", required_argument, nullptr, OPT_MESSAGES}, {"cuda-algo", required_argument, nullptr, OPT_CUDAALGO},
       {"cuda-device", required_argument, nullptr, OPT_CUDADEV}, {"extended-sweep", no_argument, nullptr, OPT_EXTSWEEP},
+      {"pkey", required_argument, nullptr, OPT_PKEY},       {"cert", required_argument, nullptr, OPT_CERT},
+      {"ca-file", required_argument, nullptr, OPT_CAFILE},  {"ca-path", required_argument, nullptr, OPT_CAPATH},
+      {"ib-device", required_argument, nullptr, OPT_IBDEV}, {"ib-index", required_argument, nullptr, OPT_IBINDEX},
+      {"ib-port", required_argument, nullptr, OPT_IBPORT},
       {"help", no_argument, nullptr, OPT_HELP},         {nullptr, 0, nullptr, 0}};
   int c;
   while ((c = getopt_long(argc, argv, "s:r:h:p:x:t:", longopts, nullptr)) != -1) {
@@ -112,6 +122,13 @@ Options parseOptions(int argc, char** argv) {
       case 'p': o.redisPort = std::atoi(optarg); break;
       case 'x': o.prefix = optarg; break;
       case 't': o.transport = optarg; break;
+      case OPT_PKEY: o.pkey = optarg; break;
+      case OPT_CERT: o.cert = optarg; break;
+      case OPT_CAFILE: o.caFile = optarg; break;
+      case OPT_CAPATH: o.caPath = optarg; break;
+      case OPT_IBDEV: o.ibDevice = optarg; break;
+      case OPT_IBINDEX: o.ibIndex = std::atoi(optarg); break;
+      case OPT_IBPORT: o.ibPort = std::atoi(optarg); break;
       case OPT_SHARED: o.sharedPath = optarg; break;
       case OPT_SYNC: o.sync = parseBool(optarg); break;
       case OPT_BUSY: o.busyPoll = parseBool(optarg); break;
@@ -157,7 +174,12 @@ Options parseOptions(int argc, char** argv) {
   if (o.contextSize <= 0) GLB_THROW(Exception, "--size is required");
   if (o.contextRank < 0 || o.contextRank >= o.contextSize) GLB_THROW(Exception, "--rank out of range");
   if (o.sharedPath.empty() && o.redisHost.empty()) GLB_THROW(Exception, "need --shared-path or --redis-host");
-  if (o.transport != "tcp") GLB_THROW(Exception, "transport '", o.transport, "' is not built (available: tcp)");
+  if (o.transport != "tcp" && o.transport != "tls" && o.transport != "uv" && o.transport != "ibverbs") {
+    GLB_THROW(Exception, "unknown transport '", o.transport, "' (tcp, tls, uv, ibverbs)");
+  }
+  if (o.transport == "tls" && (o.pkey.empty() || o.cert.empty() || (o.caFile.empty() && o.caPath.empty()))) {
+    GLB_THROW(Exception, "--transport=tls needs --pkey, --cert and --ca-file or --ca-path");
+  }
   return o;
 }
 
@@ -192,7 +214,22 @@ Runner::Runner(const Options& options) : options_(options) {
       attr.hostname = d;
     }
   }
-  device_ = transport::tcp::CreateDevice(attr);
+  if (options_.transport == "tls") {
+    device_ = transport::tcp::tls::CreateDevice(attr, options_.pkey, options_.cert, options_.caFile, options_.caPath);
+  } else if (options_.transport == "uv") {
+    transport::uv::attr ua;
+    ua.hostname = attr.hostname;
+    ua.iface = attr.iface;
+    device_ = transport::uv::CreateDevice(ua);
+  } else if (options_.transport == "ibverbs") {
+    transport::ibverbs::attr ia;
+    ia.name = options_.ibDevice;
+    ia.index = options_.ibIndex;
+    ia.port = options_.ibPort;
+    device_ = transport::ibverbs::CreateDevice(ia);  // throws with the reason on this build
+  } else {
+    device_ = transport::tcp::CreateDevice(attr);
+  }
 
   std::shared_ptr<rendezvous::Store> store;
   if (!options_.redisHost.empty()) {

@@ -29,6 +29,9 @@ struct Options {
   // transport
   std::string transport = "tcp";
   std::vector<std::string> tcpDevice;
+  std::string pkey, cert, caFile, caPath;  // --transport=tls
+  std::string ibDevice;                     // --transport=ibverbs (probe only in this build)
+  int ibIndex = 0, ibPort = 1;
   bool sync = false;
   bool busyPoll = false;
   // parameters

@@ -2,7 +2,9 @@
 
 #if GLB_USE_MPI
 
+#include <cstring>
 #include <mutex>
+#include <vector>
 
 #include "glb/common/logging.h"
 #include "glb/transport/context.h"

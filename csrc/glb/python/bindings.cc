@@ -27,6 +27,8 @@
 #include "glb/rendezvous/hash_store.h"
 #include "glb/rendezvous/prefix_store.h"
 #include "glb/rendezvous/redis_store.h"
+#include "glb/transport/ibverbs/device.h"
+#include "glb/transport/uv/device.h"
 #include "glb/scatter.h"
 #include "glb/transport/tcp/device.h"
 #include "glb/transport/tcp/tls/device.h"
@@ -226,6 +228,30 @@ PYBIND11_MODULE(_C, m) {
     return transport::tcp::tls::CreateDevice(a, pkey, cert, caFile, caPath);
   }, py::arg("hostname"), py::arg("pkey"), py::arg("cert"), py::arg("ca_file") = "", py::arg("ca_path") = "");
   m.def("tls_available", &transport::tcp::tls::opensslAvailable);
+  m.def("create_uv_device", [](const std::string& hostname, const std::string& iface) {
+    transport::uv::attr a;
+    a.hostname = hostname;
+    a.iface = iface;
+    return transport::uv::CreateDevice(a);
+  }, py::arg("hostname") = "", py::arg("iface") = "",
+        "Reference-compatible name for the portable TCP transport; backed by the epoll transport here.");
+  m.def("create_ibverbs_device", [](const std::string& name, int port, int index) {
+    transport::ibverbs::attr a;
+    a.name = name;
+    a.port = port;
+    a.index = index;
+    return transport::ibverbs::CreateDevice(a);
+  }, py::arg("name") = "", py::arg("port") = 1, py::arg("index") = 0,
+        "Raises InvalidOperationError naming what is missing (library, HCA, or the verbs data path of this build).");
+  m.def("ibverbs_probe", [] {
+    auto p = transport::ibverbs::probe();
+    py::dict d;
+    d["library"] = p.libraryLoaded;
+    d["devices"] = p.devices;
+    d["peer_memory_module"] = p.peerMemoryModule;
+    d["detail"] = p.detail;
+    return d;
+  });
 
   py::class_<transport::RemoteKey>(m, "RemoteKey")
       .def_readonly("rank", &transport::RemoteKey::rank)

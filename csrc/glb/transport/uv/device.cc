@@ -1,0 +1,38 @@
+#include "glb/transport/uv/device.h"
+
+#include "glb/transport/context.h"
+#include "glb/transport/tcp/device.h"
+
+namespace glb {
+namespace transport {
+namespace uv {
+
+namespace {
+// Same device, different label, so logs and Device::str() show what the caller asked for.
+class Device : public ::glb::transport::Device {
+ public:
+  explicit Device(std::shared_ptr<::glb::transport::Device> inner) : inner_(std::move(inner)) {}
+  std::string str() const override { return "uv(" + inner_->str() + ")"; }
+  const std::string& getPCIBusID() const override { return inner_->getPCIBusID(); }
+  int getInterfaceSpeed() const override { return inner_->getInterfaceSpeed(); }
+  bool hasGPUDirect() const override { return inner_->hasGPUDirect(); }
+  std::shared_ptr<::glb::transport::Context> createContext(int rank, int size) override {
+    return inner_->createContext(rank, size);
+  }
+
+ private:
+  std::shared_ptr<::glb::transport::Device> inner_;
+};
+}  // namespace
+
+std::shared_ptr<::glb::transport::Device> CreateDevice(const struct attr& a) {
+  tcp::attr t;
+  t.hostname = a.hostname;
+  t.iface = a.iface;
+  t.ai_family = a.ai_family;
+  return std::make_shared<Device>(tcp::CreateDevice(t));
+}
+
+}  // namespace uv
+}  // namespace transport
+}  // namespace glb

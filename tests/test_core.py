@@ -286,3 +286,39 @@ def test_redis_store_against_resp_server():
     finally:
         srv.kill()
         srv.wait()
+
+
+def test_connect_timeouts():
+    """Reference tcp_test.cc:12 / base_test: (1) a peer that never publishes its address makes
+    rendezvous fail after the context timeout; (2) an address that is published but not served
+    (connection refused, retried) fails after the timeout as well, and with
+    connection retries disabled it fails on the first attempt."""
+    # (1) rank 1 never arrives
+    store = gb.HashStore()
+    ctx = gb.Context(0, 2)
+    ctx.set_timeout(300)
+    t0 = time.time()
+    with pytest.raises(gb.IoError):
+        ctx.connect_full_mesh(store, gb.create_device())
+    assert 0.25 < time.time() - t0 < 5
+
+    # (2) rank 0's blob from a finished run points at a port nobody listens on any more
+    d = tempfile.mkdtemp(prefix="glb_stale_")
+
+    def once(rank):
+        c = gb.init_context(rank, 2, path=d, timeout_ms=5000)
+        gb.barrier(c)
+        c.close_connections()
+
+    ths = [threading.Thread(target=once, args=(r,)) for r in range(2)]
+    [t.start() for t in ths]
+    [t.join(30) for t in ths]
+    # a fresh rank 1 finds rank 0's stale address in its store and dials a dead port
+    stale = gb.HashStore()
+    stale.set("0", gb.FileStore(d).get("0"))
+    c1 = gb.Context(1, 2)
+    c1.set_timeout(400)
+    t0 = time.time()
+    with pytest.raises(gb.IoError):
+        c1.connect_full_mesh(stale, gb.create_device())
+    assert time.time() - t0 < 10

@@ -1,0 +1,116 @@
+"""Transport names a reference user may ask for besides tcp: uv (alias of the epoll transport),
+ibverbs (probe + precise error), MPI bootstrap (run against a thread-world MPI), and the
+benchmark CLI's --transport switch (reference: gloo/benchmark/options.cc:149-180)."""
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+
+import numpy as np
+import pytest
+
+import gloo_b200 as gb
+from gloo_b200 import _C
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BENCH = os.path.join(ROOT, "gloo_b200", "bin", "glb_benchmark")
+
+
+def test_uv_device_runs_new_style_collectives():
+    store = gb.HashStore()
+    import threading
+
+    out = [None] * 3
+
+    def rank(r):
+        dev = _C.create_uv_device("127.0.0.1")
+        assert str(dev).startswith("uv(")
+        ctx = gb.Context(r, 3)
+        ctx.connect_full_mesh(store, dev)
+        x = np.full(100, r + 1, np.float64)
+        gb.allreduce(ctx, x)
+        got = np.zeros(3, np.int32)
+        gb.allgather(ctx, got, np.array([r], np.int32))
+        gb.barrier(ctx)
+        out[r] = (float(x[0]), got.tolist())
+
+    ths = [threading.Thread(target=rank, args=(r,)) for r in range(3)]
+    [t.start() for t in ths]
+    [t.join(60) for t in ths]
+    assert out == [(6.0, [0, 1, 2])] * 3
+
+
+def test_ibverbs_probe_and_error():
+    p = _C.ibverbs_probe()
+    assert set(p) == {"library", "devices", "peer_memory_module", "detail"} and p["detail"]
+    with pytest.raises(gb.InvalidOperationError) as e:
+        _C.create_ibverbs_device()
+    assert "ibverbs" in str(e.value) and ("tcp" in str(e.value))
+
+
+def run_bench(size, *args, env=None, timeout=120):
+    d = tempfile.mkdtemp(prefix="glb_cli_")
+    procs = [subprocess.Popen([BENCH, "--size", str(size), "--rank", str(r), "--shared-path", d, *args],
+                              stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True, env=env)
+             for r in range(size)]
+    outs = [p.communicate(timeout=timeout)[0] for p in procs]
+    return [p.returncode for p in procs], outs
+
+
+@pytest.mark.skipif(not os.path.exists(BENCH), reason="benchmark binary not built")
+@pytest.mark.parametrize("transport", ["tcp", "uv"])
+def test_benchmark_cli(transport):
+    codes, outs = run_bench(2, "--transport", transport, "--elements", "1000", "--iteration-count", "20",
+                            "allreduce_ring_chunked")
+    assert codes == [0, 0], outs
+    row = [l for l in outs[0].splitlines() if l.strip().startswith("4000")]
+    assert row, outs[0]  # size (B) = 1000 float32
+    assert int(row[0].split()[-1]) == 20  # iterations column
+
+
+@pytest.mark.skipif(not os.path.exists(BENCH), reason="benchmark binary not built")
+def test_benchmark_cli_sync_threads_and_errors():
+    codes, outs = run_bench(2, "--sync=true", "--busy-poll=true", "--threads", "2", "--elements", "500",
+                            "--iteration-count", "10", "allreduce_halving_doubling")
+    assert codes == [0, 0], outs
+    codes, outs = run_bench(1, "--transport", "ibverbs", "--elements", "10", "allreduce_ring")
+    assert codes[0] != 0 and "ibverbs transport" in outs[0]
+    codes, outs = run_bench(1, "--transport", "carrier-pigeon", "--elements", "10", "allreduce_ring")
+    assert codes[0] != 0 and "unknown transport" in outs[0]
+
+
+@pytest.mark.skipif(not os.path.exists(BENCH) or shutil.which("openssl") is None or not _C.tls_available(),
+                    reason="needs the benchmark binary and OpenSSL")
+def test_benchmark_cli_tls():
+    from test_tls import make_ca, make_cert
+
+    d = tempfile.mkdtemp(prefix="glb_cli_tls_")
+    ca_key, ca_crt = make_ca(d, "bench")
+    key, crt = make_cert(d, "rank", ca_key, ca_crt)
+    codes, outs = run_bench(2, "--transport", "tls", "--pkey", key, "--cert", crt, "--ca-file", ca_crt,
+                            "--elements", "1000", "--iteration-count", "10", "new_allreduce_ring")
+    assert codes == [0, 0], outs
+    codes, outs = run_bench(1, "--transport", "tls", "--elements", "10", "allreduce_ring")
+    assert codes[0] != 0 and "--pkey" in outs[0]
+
+
+@pytest.mark.skipif(shutil.which("g++") is None and not os.path.exists("/usr/bin/g++"), reason="no host compiler")
+def test_mpi_bootstrap_against_thread_world_mpi():
+    """csrc/glb/mpi/context.cc is only compiled when mpi.h exists (not in this image). Build it
+    here against tests/fake_mpi (threads as the MPI world) and run the whole bootstrap:
+    MPI_Allreduce(MAX) + MPI_Allgather of the rendezvous blobs -> TCP full mesh -> allreduce."""
+    lib = os.path.join(ROOT, "gloo_b200", "lib")
+    if not os.path.exists(os.path.join(lib, "libglb.so")):
+        pytest.skip("libglb.so not built")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    exe = os.path.join(tempfile.mkdtemp(prefix="glb_mpi_"), "mpi_bootstrap")
+    fm = os.path.join(ROOT, "tests", "fake_mpi")
+    subprocess.check_call([cxx, "-std=c++17", "-O1", "-pthread", "-DGLB_USE_MPI=1", "-DGLB_USE_CUDA=1",
+                           f"-I{fm}", f"-I{os.path.join(ROOT, 'csrc')}", "-I/usr/local/cuda/include",
+                           os.path.join(fm, "mpi_bootstrap_main.cc"), os.path.join(fm, "fake_mpi.cc"),
+                           os.path.join(ROOT, "csrc", "glb", "mpi", "context.cc"),
+                           f"-L{lib}", "-lglb", f"-Wl,-rpath,{lib}", "-o", exe])
+    for p in (2, 5):
+        out = subprocess.run([exe, str(p)], capture_output=True, text=True, timeout=60)
+        assert out.returncode == 0 and out.stdout.startswith(f"OK {p * (p + 1) // 2}"), (out.stdout, out.stderr)

@@ -15,6 +15,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <functional>
+#include <csignal>
 #include <iostream>
 #include <map>
 #include <memory>
@@ -29,6 +30,7 @@ using namespace glb;
 using namespace glb::benchmark;
 
 int main(int argc, char** argv) {
+  std::signal(SIGPIPE, SIG_IGN);  // a vanished peer is an IoException, not a signal (reference: test/main.cc:38-41)
   try {
     Options opts = parseOptions(argc, argv);
     Runner runner(opts);

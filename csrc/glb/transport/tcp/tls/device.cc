@@ -1,5 +1,7 @@
 #include "glb/transport/tcp/tls/device.h"
 
+#include <csignal>
+
 #include <poll.h>
 #include <sys/uio.h>
 
@@ -27,6 +29,14 @@ std::shared_ptr<::glb::transport::Device> CreateDevice(const struct attr& src, c
 
 Device::Device(const struct attr& attr, std::string pkey, std::string cert, std::string caFile, std::string caPath)
     : ::glb::transport::tcp::Device(attr, /*lazy=*/false) {
+  // OpenSSL writes through plain write(2), which cannot carry MSG_NOSIGNAL the way the
+  // tcp transport's sendmsg does: a peer that went away would kill the process with
+  // SIGPIPE instead of surfacing as an IoException. Only the default disposition is
+  // replaced; an application handler is left alone.
+  {
+    struct sigaction cur;
+    if (::sigaction(SIGPIPE, nullptr, &cur) == 0 && cur.sa_handler == SIG_DFL) ::signal(SIGPIPE, SIG_IGN);
+  }
   const auto& o = openssl();
   ctx_ = o.SSL_CTX_new(o.TLS_method());
   GLB_ENFORCE(ctx_ != nullptr, "SSL_CTX_new: ", opensslLastError());

@@ -63,6 +63,18 @@ uint64_t* probeWord() {
   return &word;
 }
 
+// Not every mapping can be read with process_vm_readv: device-driver mappings (VM_IO /
+// VM_PFNMAP, which is what pinned CUDA host allocations may be) make get_user_pages fail.
+// The sender finds out by reading the first and last byte of the region from itself; if
+// that does not work the payload goes through the socket as usual.
+bool pullable(const char* data, size_t nbytes) {
+  const pid_t self = ::getpid();  // not cached: a forked child must not read its parent
+  char probe[2];
+  struct iovec local[2] = {{&probe[0], 1}, {&probe[1], 1}};
+  struct iovec remote[2] = {{const_cast<char*>(data), 1}, {const_cast<char*>(data) + nbytes - 1, 1}};
+  return ::process_vm_readv(self, local, 2, remote, 2, 0) == 2;
+}
+
 bool retryableConnectError(int err) {
   return err == ECONNREFUSED || err == ETIMEDOUT || err == EHOSTUNREACH || err == ENETUNREACH ||
          err == ECONNRESET || err == EADDRNOTAVAIL || err == EINTR;
@@ -486,7 +498,7 @@ void Pair::recv(::glb::transport::UnboundBuffer* tbuf, uint64_t tag, size_t offs
 void Pair::setPayload(TxOp& op, const char* data, size_t nbytes) {
   op.hdr.nbytes = nbytes;
   op.data = data;
-  if (peerCanPull_ && nbytes >= cmaMinBytes()) {
+  if (peerCanPull_ && nbytes >= cmaMinBytes() && pullable(data, nbytes)) {
     // Header only; the receiver pulls the bytes and answers FIN.
     op.cma = true;
     op.hdr.flags |= F_CMA;

@@ -19,6 +19,13 @@ def main():
     args = sys.argv[5:]
     timeout_ms = int(os.environ.get("GLB_TEST_TIMEOUT_MS", "3000"))
     ctx = gb.init_context(rank, size, path=store_dir, timeout_ms=timeout_ms)
+    # GLB_TEST_SYNC: 1 = blocking sync pairs, 2 = busy-polling sync pairs (reference
+    # transport_test.cc runs every fault case as Async / Blocking / Polling)
+    sync_mode = int(os.environ.get("GLB_TEST_SYNC", "0"))
+    if sync_mode:
+        for r in range(size):
+            if r != rank:
+                ctx.get_pair(r).set_sync(True, sync_mode == 2)
     # tell the parent we are connected
     open(os.path.join(store_dir, f"ready_{rank}"), "w").close()
     try:

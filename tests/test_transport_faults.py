@@ -77,6 +77,30 @@ def test_sigkill_is_detected(size, mode):
     assert elapsed < 2 * timeout_ms / 1000 + 5
 
 
+@pytest.mark.parametrize("sync", ["1", "2"])
+@pytest.mark.parametrize("mode", ["allreduce_loop", "sendrecv_loop"])
+def test_sigkill_is_detected_in_sync_modes(mode, sync):
+    """Blocking (poll) and busy-polling pairs: the waiting user thread reads the socket itself
+    and must notice the dead peer just like the loop thread does in async mode."""
+    size, timeout_ms = 3, 3000
+    d, procs = launch(size, mode, timeout_ms=timeout_ms, extra_env={"GLB_TEST_SYNC": sync})
+    wait_ready(d, size)
+    time.sleep(0.3)
+    t0 = time.time()
+    procs[0].send_signal(signal.SIGKILL)
+    codes = reap(procs, 2 * timeout_ms / 1000 + 10)
+    assert codes[0] == -signal.SIGKILL
+    assert all(c == 10 for c in codes[1:]), (codes, [p.stderr.read()[-300:] for p in procs[1:]])
+    assert time.time() - t0 < 2 * timeout_ms / 1000 + 5
+
+
+@pytest.mark.parametrize("sync", ["1", "2"])
+def test_healthy_run_in_sync_modes(sync):
+    d, procs = launch(3, "large_once", 1 << 18, timeout_ms=20000, extra_env={"GLB_TEST_SYNC": sync})
+    codes = reap(procs, 90)
+    assert codes == [0] * 3, (codes, [p.stderr.read()[-400:] for p in procs])
+
+
 @pytest.mark.parametrize("size", [2, 3])
 def test_sigstop_hits_timeout(size):
     timeout_ms = 1500

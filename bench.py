@@ -195,16 +195,17 @@ def run_ours(args):
     resolved = algo.resolved_algo()
 
     # ---- end to end: pinned host -> device, allreduce, device -> pinned host, every step ----
-    hin = torch.empty(E, dtype=torch.float32).pin_memory()
-    hin.fill_(1.0)
+    # The call a user with host-resident data makes: gcu.CudaHostAllreduce, which pipelines
+    # the PCIe legs with the NVLink reduction piece by piece (same kernels as above).
+    del ts, algo
+    hins = [torch.empty(E, dtype=torch.float32).pin_memory() for _ in range(inputs)]
+    for h in hins:
+        h.fill_(1.0)
     hout = torch.empty(E, dtype=torch.float32).pin_memory()
+    e2e = gcu.CudaHostAllreduce(ctx, cc, hins, hout, chunks=args.e2e_chunks)
     def e2e_step():
         with torch.cuda.stream(stream):
-            ts[0].copy_(hin, non_blocking=True)
-            if inputs > 1:
-                ts[1].copy_(hin, non_blocking=True)
-            algo.run()
-            hout.copy_(ts[0], non_blocking=True)
+            e2e.run()
     for _ in range(min(3, args.warmup)):
         e2e_step()
     sync_all()
@@ -221,7 +222,8 @@ def run_ours(args):
     assert abs(float(hout[0]) - world * inputs) < 1e-3, "e2e result mismatch"
     e2e_algbw = size_bytes / (e2e_ms * 1e-3) / 1e9
     e2e_val = e2e_algbw * 2 * (world - 1) / world if world > 1 else e2e_algbw
-    del hin, hout, ts, algo
+    e2e_launches = e2e.launches_per_run
+    del hins, hout, e2e
 
     # ---- same size on plain cudaMalloc'ed buffers (cudaIpc-registered) and the NCCL comparator ----
     def time_k(fn):
@@ -308,7 +310,9 @@ def run_ours(args):
                          "frac_of_measured": round(busbw / 770, 3) if busbw else None},
             "clocks": clocks,
             "e2e": {"value": round(e2e_val, 3), "unit": "GB/s", "ms_per_step": round(e2e_ms, 4),
-                    "h2d_bytes_per_step": size_bytes * inputs, "d2h_bytes_per_step": size_bytes},
+                    "h2d_bytes_per_step": size_bytes * inputs, "d2h_bytes_per_step": size_bytes,
+                    "api": "gloo_b200.ops.cuda.CudaHostAllreduce (chunked H2D | allreduce | D2H pipeline)",
+                    "pieces": int(e2e_launches), "gpu_launches_per_step": int(e2e_launches)},
             "gpu_launches": int(launches),
             **extra,
             "sweep": sweep,
@@ -408,6 +412,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--elements", type=int, default=HEADLINE_ELEMENTS)
     ap.add_argument("--no-sweep", action="store_true")
+    ap.add_argument("--e2e-chunks", type=int, default=16, help="pieces of the host<->device pipeline in the e2e run")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

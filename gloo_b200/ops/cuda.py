@@ -276,6 +276,80 @@ CudaAllreduceHalvingDoublingPipelined = _make_allreduce_class("CudaAllreduceHalv
 CudaAllreduceBcube = _make_allreduce_class("CudaAllreduceBcube", "bcube")
 
 
+class CudaHostAllreduce:
+    """Allreduce of pinned *host* buffers through the GPUs, as a three-stage pipeline.
+
+    The reference reaches host-resident data with ``CudaHostWorkspace`` (device <-> pinned host
+    staging around a CPU reduction, gloo/cuda_workspace.h:17-40). Here the reduction stays on
+    NVLink and the PCIe legs are overlapped with it: the vector is cut into ``chunks`` pieces and
+    piece c is copied host->device on one stream while piece c-1 is being reduced across the
+    GPUs (one fused kernel per piece, same ``CudaAllreduceRingChunked`` class a user would
+    call) and piece c-2 is copied device->host on a third stream. PCIe is full duplex, so a
+    step costs about max(H2D, D2H) + one piece instead of H2D + allreduce + D2H.
+
+    ``host_inputs``: one pinned tensor per local input (they are summed first when there are
+    several, like the multi-pointer classes); ``host_output``: pinned tensor for the result.
+    ``run()`` is asynchronous with respect to the host: the caller's current stream (or
+    ``stream``) is made to wait for the last device->host copy, so ``stream.synchronize()``
+    or any later work on that stream sees ``host_output`` complete. Collective: construct
+    and run in the same order on every rank.
+    """
+
+    def __init__(self, ctx, cuda_ctx: "CudaContext", host_inputs, host_output, chunks: int = 16,
+                 op: ReduceOp = ReduceOp.SUM):
+        import torch
+
+        host_inputs = list(host_inputs) if isinstance(host_inputs, (list, tuple)) else [host_inputs]
+        n = host_output.numel()
+        for h in host_inputs + [host_output]:
+            assert h.is_pinned() and h.is_contiguous() and h.numel() == n and h.dtype == host_output.dtype, \
+                "CudaHostAllreduce needs contiguous pinned host tensors of one shape and dtype"
+        self.cc = cuda_ctx
+        self.hin, self.hout = host_inputs, host_output
+        dev = cuda_ctx.device
+        with torch.cuda.device(dev):
+            self.dev = [cuda_ctx.empty(n, host_output.dtype) for _ in host_inputs]
+            self.h2d, self.comp, self.d2h = new_stream(dev), new_stream(dev, True), new_stream(dev)
+            # piece boundaries on 4 KiB so every piece keeps the vector alignment of the kernels
+            align = max(1, 4096 // host_output.element_size())
+            per = -(-n // max(1, chunks))
+            per = -(-per // align) * align
+            self.bounds = [(lo, min(n, lo + per)) for lo in range(0, n, per)] if n else []
+            self.algos = []
+            for lo, hi in self.bounds:
+                self.algos.append(CudaAllreduceRingChunked(ctx, [d[lo:hi] for d in self.dev],
+                                                           streams=[self.comp] * len(self.dev), op=op))
+            self.ev_in = [torch.cuda.Event() for _ in self.bounds]
+            self.ev_red = [torch.cuda.Event() for _ in self.bounds]
+            self.ev_start, self.ev_done = torch.cuda.Event(), torch.cuda.Event()
+        self.launches_per_run = len(self.bounds)
+
+    def run(self, stream=None):
+        import torch
+
+        caller = torch.cuda.current_stream(self.cc.device) if stream is None else stream
+        self.ev_start.record(caller)
+        self.h2d.wait_event(self.ev_start)
+        self.d2h.wait_event(self.ev_start)
+        for c, (lo, hi) in enumerate(self.bounds):
+            with torch.cuda.stream(self.h2d):
+                for d, h in zip(self.dev, self.hin):
+                    d[lo:hi].copy_(h[lo:hi], non_blocking=True)
+                self.ev_in[c].record(self.h2d)
+            self.comp.wait_event(self.ev_in[c])
+            self.algos[c].run()
+            self.ev_red[c].record(self.comp)
+            self.d2h.wait_event(self.ev_red[c])
+            with torch.cuda.stream(self.d2h):
+                self.hout[lo:hi].copy_(self.dev[0][lo:hi], non_blocking=True)
+        self.ev_done.record(self.d2h)
+        caller.wait_event(self.ev_done)
+        return self.hout
+
+    def resolved_algo(self) -> str:
+        return self.algos[0].resolved_algo() if self.algos else "none"
+
+
 class CudaBroadcastOneToAll:
     def __init__(self, ctx, tensors, root: int = 0, root_pointer: int = 0, streams=None, host_workspace: bool = False):
         tensors = list(tensors) if isinstance(tensors, (list, tuple)) else [tensors]

@@ -183,3 +183,32 @@ def test_literal_schedules(size):
         return True
 
     assert all(gb.spawn_threads(size, fn, cuda_device=0))
+
+
+@pytest.mark.parametrize("size,inputs", [(1, 2), (1, 1), (2, 1), (3, 2)])
+def test_host_allreduce_pipeline(size, inputs):
+    """CudaHostAllreduce: pinned host -> (H2D | fused allreduce | D2H pipeline) -> pinned host,
+    checked against an fp64 sum on the host; run twice to cover buffer reuse across runs and
+    with a piece count that does not divide the length."""
+    count = 300_003
+
+    def fn(ctx):
+        cc = gcu.CudaContext(ctx, 0, stage_bytes=8 << 20)
+        hins = [torch.empty(count, dtype=torch.float32).pin_memory() for _ in range(inputs)]
+        hout = torch.empty(count, dtype=torch.float32).pin_memory()
+        op = gcu.CudaHostAllreduce(ctx, cc, hins, hout, chunks=5)
+        assert len(op.bounds) >= 5 and op.bounds[-1][1] == count
+        base = torch.arange(count, dtype=torch.float64) % 1000
+        for it in range(2):
+            for i, h in enumerate(hins):
+                h.copy_((base + (ctx.rank * inputs + i) * (it + 1)).float())
+            hout.fill_(-1.0)
+            op.run()
+            torch.cuda.current_stream().synchronize()
+            total = size * inputs
+            want = base * total + (it + 1) * total * (total - 1) / 2
+            torch.testing.assert_close(hout.double(), want, rtol=1e-6, atol=0)
+        cc.pc.host_barrier()
+        return True
+
+    assert all(gb.spawn_threads(size, fn, cuda_device=0))

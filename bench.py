@@ -116,6 +116,10 @@ def run_ours(args):
     assert world == args.gpus, f"--gpus {args.gpus} but WORLD_SIZE={world}"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # Keep this rank (its pinned staging buffers and the transport's I/O thread) on the
+    # socket its GPU hangs off.
+    from gloo_b200.utils.affinity import bind_to_gpu
+    cpus = bind_to_gpu(local)
 
     store = gb.FileStore(rendezvous_dir("ours"))
     ctx = gb.init_context(rank, world, store=store, device=gb.create_device("127.0.0.1"), timeout_ms=120000)
@@ -301,7 +305,7 @@ def run_ours(args):
             "impl": "gloo_b200",
             "config": {"model": "cuda_allreduce_ring_chunked", "elements": E, "bytes_per_gpu": size_bytes,
                        "inputs_per_rank": inputs, "global_batch": world * inputs, "seq_len": E,
-                       "parallelism": f"allreduce x{world}", "kernel_variant": resolved,
+                       "parallelism": f"allreduce x{world}", "cpu_affinity_cpus": len(cpus), "kernel_variant": resolved,
                        "buffers": "library symmetric allocator (peer-mapped; NVLS multicast-bound when >2 GPUs)",
                        "l2": "inputs larger than L2 (400 MB > 126 MB) for the headline; 256 MB flush between sweep iterations",
                        "timing": "CUDA events on the launching stream, max over ranks"},

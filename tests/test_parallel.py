@@ -105,3 +105,18 @@ def test_tp_ulysses_ring():
         return True
 
     assert all(gb.spawn_threads(size, fn))
+
+
+def test_affinity_helpers_are_best_effort():
+    """CPU placement never raises: without a GPU (or on a single-node box) it leaves the
+    affinity untouched and reports what is in effect."""
+    import os
+
+    from gloo_b200.utils.affinity import _parse_cpulist, bind_to_gpu
+
+    assert _parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert _parse_cpulist("") == []
+    before = os.sched_getaffinity(0)
+    got = bind_to_gpu(0)
+    assert isinstance(got, list)
+    assert os.sched_getaffinity(0) == before or set(got) <= before

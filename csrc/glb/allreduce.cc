@@ -92,46 +92,109 @@ void ringReduceScatter(const std::shared_ptr<Context>& context, UnboundBuffer* b
 
 namespace {
 
-void ringAllgather(const std::shared_ptr<Context>& context, UnboundBuffer* buf, size_t elements,
-                   size_t elementSize, size_t maxSegmentSize, uint64_t slot, std::chrono::milliseconds timeout) {
+// Streaming ring. Reduce-scatter and allgather form one pipeline of segments: a segment is
+// forwarded the moment it has been reduced (or, in the allgather half, received) instead
+// of after the whole step, so the cost is (2P-3) segment latencies plus one pass over the
+// vector rather than 2(P-1) chunk latencies. `src` is where this rank's contribution is
+// read from: with a single out-of-place input the first touch of every chunk reads the
+// input directly (step-0 sends come from it, reductions compute out = in + received), so
+// the up-front copy of the whole vector disappears.
+void ring(const AllreduceOptions& opts, UnboundBuffer* out0, UnboundBuffer* src) {
+  const auto& context = opts.context;
   const int P = context->size;
   const int r = context->rank;
   const int right = (r + 1) % P;
   const int left = (r - 1 + P) % P;
-  const Range all{0, elements};
-  const size_t maxChunkElems = ceilDiv(elements, static_cast<size_t>(P));
-  const size_t segElems = std::max<size_t>(1, std::min(maxChunkElems, maxSegmentSize / elementSize));
-  const size_t nseg = ceilDiv(maxChunkElems, segElems);
-  auto segOf = [&](const Range& chunk, size_t j) {
-    Range s;
-    s.off = chunk.off + std::min(chunk.len, j * segElems);
-    s.len = std::min(segElems, chunk.len - std::min(chunk.len, j * segElems));
-    return s;
-  };
-  // After reduce-scatter rank r owns chunk (r + 1) % P.
-  for (int s = 0; s < P - 1; s++) {
-    const Range sendChunk = subRange(all, P, (r + 1 - s + P) % P);
-    const Range recvChunk = subRange(all, P, (r - s + P) % P);
-    // Receives land straight in the output; post them all, then stream the sends.
-    for (size_t j = 0; j < nseg; j++) {
-      Range seg = segOf(recvChunk, j);
-      buf->recv(left, slot, seg.off * elementSize, seg.len * elementSize);
-    }
-    for (size_t j = 0; j < nseg; j++) {
-      Range seg = segOf(sendChunk, j);
-      buf->send(right, slot, seg.off * elementSize, seg.len * elementSize);
-    }
-    for (size_t j = 0; j < nseg; j++) buf->waitRecv(timeout);
-    for (size_t j = 0; j < nseg; j++) buf->waitSend(timeout);
-  }
-}
+  const size_t es = opts.elementSize;
+  const auto rsSlot = Slot::build(kAllreduceSlotPrefix, opts.tag);
+  const auto agSlot = rsSlot + 1;
+  const auto timeout = opts.timeout;
+  const Range all{0, opts.elements};
+  char* outBase = static_cast<char*>(out0->ptr);
+  const char* srcBase = static_cast<const char*>(src->ptr);
 
-void ring(const AllreduceOptions& opts, UnboundBuffer* out0) {
-  const auto slot = Slot::build(kAllreduceSlotPrefix, opts.tag);
-  detail::ringReduceScatter(opts.context, out0, opts.elements, opts.elementSize, opts.reduce,
-                            opts.maxSegmentSize, slot, opts.timeout);
-  ringAllgather(opts.context, out0, opts.elements, opts.elementSize, opts.maxSegmentSize, slot + 1,
-                opts.timeout);
+  const size_t maxChunkElems = ceilDiv(opts.elements, static_cast<size_t>(P));
+  // maxSegmentSize is an upper bound. Below it, aim for four segments per chunk so that the
+  // arrival of one segment overlaps the reduction of the previous one, but not smaller
+  // than 256 KiB (per-message cost, and the same-host single-copy threshold).
+  size_t segBytes = std::min(opts.maxSegmentSize, std::max<size_t>(256u << 10, maxChunkElems * es / 4));
+  const size_t segElems = std::max<size_t>(1, std::min(maxChunkElems, segBytes / es));
+  const size_t nseg = ceilDiv(maxChunkElems, segElems);
+  auto chunk = [&](int c) { return subRange(all, P, static_cast<size_t>(((c % P) + P) % P)); };
+  auto segOf = [&](const Range& ch, size_t j) {
+    Range sg;
+    sg.off = ch.off + std::min(ch.len, j * segElems);
+    sg.len = std::min(segElems, ch.len - std::min(ch.len, j * segElems));
+    return sg;
+  };
+
+  // Landing zones for the reduce-scatter half; a zone is re-posted as soon as it is reduced.
+  constexpr size_t kDepth = 4;
+  std::vector<char> tmpStorage(kDepth * segElems * es);
+  auto tmp = context->createUnboundBuffer(tmpStorage.data(), tmpStorage.size());
+  const size_t total = static_cast<size_t>(P - 1) * nseg;
+  auto postRs = [&](size_t k) {
+    const size_t s = k / nseg, j = k % nseg;
+    Range sg = segOf(chunk(r - static_cast<int>(s) - 1), j);
+    tmp->recv(left, rsSlot, (k % kDepth) * segElems * es, sg.len * es);
+  };
+  for (size_t k = 0; k < std::min(kDepth, total); k++) postRs(k);
+
+  // Sends of the allgather half go through their own handle on the output memory, so
+  // that "the reduce-scatter sends are done" can be waited for separately: a rank must
+  // not wait for its allgather sends before posting its allgather receives (the peer's
+  // receive may only be posted after that peer has seen *its* sends complete).
+  auto agOut = context->createUnboundBuffer(out0->ptr, out0->size);
+  size_t srcSends = 0, outSends = 0, agSends = 0;
+  for (size_t j = 0; j < nseg; j++) {  // step 0: this rank's own chunk, unreduced
+    Range sg = segOf(chunk(r), j);
+    src->send(right, rsSlot, sg.off * es, sg.len * es);
+    srcSends++;
+  }
+  for (size_t k = 0; k < total; k++) {
+    const size_t s = k / nseg, j = k % nseg;
+    tmp->waitRecv(timeout);
+    Range sg = segOf(chunk(r - static_cast<int>(s) - 1), j);
+    if (sg.len > 0) {
+      opts.reduce(outBase + sg.off * es, srcBase + sg.off * es, tmpStorage.data() + (k % kDepth) * segElems * es,
+                  sg.len);
+    }
+    if (k + kDepth < total) postRs(k + kDepth);
+    // Reduced: pass it on. After the last step it is final and opens the allgather half.
+    if (s + 2 < static_cast<size_t>(P)) {
+      out0->send(right, rsSlot, sg.off * es, sg.len * es);
+      outSends++;
+    } else {
+      agOut->send(right, agSlot, sg.off * es, sg.len * es);
+      agSends++;
+    }
+  }
+  // The allgather half overwrites regions the reduce-scatter sends still read (in place:
+  // all of them; out of place: the forwarded partial sums), so those have to be done first.
+  if (src != out0) {
+    for (size_t k = 0; k < srcSends; k++) src->waitSend(timeout);
+  } else {
+    outSends += srcSends;
+  }
+  for (size_t k = 0; k < outSends; k++) out0->waitSend(timeout);
+  outSends = 0;
+
+  // Allgather half: step s receives chunk (r - s) straight into the output and forwards it.
+  for (size_t k = 0; k < total; k++) {
+    const size_t s = k / nseg, j = k % nseg;
+    Range sg = segOf(chunk(r - static_cast<int>(s)), j);
+    out0->recv(left, agSlot, sg.off * es, sg.len * es);
+  }
+  for (size_t k = 0; k < total; k++) {
+    const size_t s = k / nseg, j = k % nseg;
+    out0->waitRecv(timeout);
+    if (s + 2 < static_cast<size_t>(P)) {
+      Range sg = segOf(chunk(r - static_cast<int>(s)), j);
+      agOut->send(right, agSlot, sg.off * es, sg.len * es);
+      agSends++;
+    }
+  }
+  for (size_t k = 0; k < agSends; k++) agOut->waitSend(timeout);
 }
 
 void bcube(const AllreduceOptions& opts, UnboundBuffer* out0) {
@@ -227,7 +290,11 @@ void allreduce(const AllreduceOptions& opts) {
 
   // Local phase 1: fold every input into out[0].
   UnboundBuffer* out0 = opts.out[0].get();
-  if (!opts.in.empty()) {
+  UnboundBuffer* src = out0;
+  const bool isRing = opts.algorithm == AllreduceOptions::UNSPECIFIED || opts.algorithm == AllreduceOptions::RING;
+  if (isRing && context->size > 1 && opts.in.size() == 1 && opts.in[0]->ptr != out0->ptr) {
+    src = opts.in[0].get();  // the ring reads the input in place: no up-front copy
+  } else if (!opts.in.empty()) {
     if (opts.in[0]->ptr != out0->ptr) std::memcpy(out0->ptr, opts.in[0]->ptr, bytes);
     for (size_t i = 1; i < opts.in.size(); i++) {
       opts.reduce(out0->ptr, out0->ptr, opts.in[i]->ptr, opts.elements);
@@ -243,7 +310,7 @@ void allreduce(const AllreduceOptions& opts) {
     switch (opts.algorithm) {
       case AllreduceOptions::UNSPECIFIED:
       case AllreduceOptions::RING:
-        ring(opts, out0);
+        ring(opts, out0, src);
         break;
       case AllreduceOptions::BCUBE:
         bcube(opts, out0);

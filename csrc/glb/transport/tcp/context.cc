@@ -199,6 +199,8 @@ void Context::postRecv(UnboundBuffer* buf, std::vector<int> srcRanks, uint64_t s
     }
   }
   int matchedRank = -1;
+  bool deferred = false;
+  RemotePayload pull;
   {
     std::lock_guard<std::mutex> g(matchMu_);
     // An already-arrived message wins; rotate the scan start for fairness.
@@ -208,10 +210,15 @@ void Context::postRecv(UnboundBuffer* buf, std::vector<int> srcRanks, uint64_t s
       int r = srcRanks[(start + k) % n];
       auto it = unexpected_[r].find(slot);
       if (it == unexpected_[r].end() || it->second.empty()) continue;
-      auto& data = it->second.front();
-      GLB_ENFORCE_LE(data.size(), nbytes, "distributed collective mismatch: rank ", r,
+      auto& u = it->second.front();
+      GLB_ENFORCE_LE(u.size(), nbytes, "distributed collective mismatch: rank ", r,
                      " sent more bytes on slot ", slot, " than the posted recv holds");
-      if (!data.empty()) std::memcpy(static_cast<char*>(buf->ptr) + offset, data.data(), data.size());
+      if (u.deferred) {
+        pull = u.remote;
+        deferred = true;
+      } else if (!u.data.empty()) {
+        std::memcpy(static_cast<char*>(buf->ptr) + offset, u.data.data(), u.data.size());
+      }
       it->second.pop_front();
       if (it->second.empty()) unexpected_[r].erase(it);
       matchedRank = r;
@@ -221,7 +228,47 @@ void Context::postRecv(UnboundBuffer* buf, std::vector<int> srcRanks, uint64_t s
       return;
     }
   }
+  if (deferred) {
+    // The sender's bytes are still in its address space: fetch them straight into the
+    // destination from this (the posting) thread, then release the sender.
+    auto* pair = static_cast<Pair*>(pairs_[matchedRank].get());
+    pair->pullDeferred(static_cast<char*>(buf->ptr) + offset, pull.srcAddr, pull.nbytes, pull.id);
+  }
   buf->handleRecvCompletion(matchedRank);
+}
+
+bool Context::matchOrDefer(int srcRank, uint64_t slot, const RemotePayload& payload, Match* out) {
+  std::lock_guard<std::mutex> g(matchMu_);
+  auto& uq = unexpected_[srcRank][slot];
+  if (uq.empty()) {
+    auto it = posted_.find(slot);
+    if (it != posted_.end()) {
+      auto& q = it->second;
+      for (auto p = q.begin(); p != q.end();) {
+        if (!p->accepts(srcRank)) {
+          ++p;
+          continue;
+        }
+        auto lease = p->buf.lock();
+        if (!lease) {
+          p = q.erase(p);
+          continue;
+        }
+        out->dst = static_cast<char*>(lease->ptr) + p->offset;
+        out->capacity = p->nbytes;
+        out->buf = std::move(lease);
+        q.erase(p);
+        if (q.empty()) posted_.erase(it);
+        if (uq.empty()) unexpected_[srcRank].erase(slot);
+        return true;
+      }
+    }
+  }
+  Unexpected u;
+  u.deferred = true;
+  u.remote = payload;
+  unexpected_[srcRank][slot].push_back(std::move(u));
+  return false;
 }
 
 bool Context::matchIncoming(int srcRank, uint64_t slot, Match* out) {
@@ -280,7 +327,9 @@ void Context::deliverUnexpected(int srcRank, uint64_t slot, std::vector<char>&& 
       }
     }
     if (!lease) {
-      uq.push_back(std::move(data));
+      Unexpected u;
+      u.data = std::move(data);
+      uq.push_back(std::move(u));
       return;
     }
     if (uq.empty()) unexpected_[srcRank].erase(slot);

@@ -63,6 +63,14 @@ class Context : public ::glb::transport::Context, public std::enable_shared_from
   bool matchIncoming(int srcRank, uint64_t slot, Match* out);
   // Loop thread, unexpected payload fully read.
   void deliverUnexpected(int srcRank, uint64_t slot, std::vector<char>&& data);
+  // Single-copy message (header only on the wire): match it like matchIncoming, or park
+  // its descriptor so that the recv, once posted, pulls the bytes straight into place.
+  struct RemotePayload {
+    uint64_t srcAddr = 0;
+    size_t nbytes = 0;
+    uint64_t id = 0;  // echoed in the FIN that completes the sender's operation
+  };
+  bool matchOrDefer(int srcRank, uint64_t slot, const RemotePayload& payload, Match* out);
   void cancelPostedRecvs(UnboundBuffer* buf);
   void failPostedRecvs(int srcRank, const std::string& msg);
 
@@ -102,8 +110,15 @@ class Context : public ::glb::transport::Context, public std::enable_shared_from
 
   std::mutex matchMu_;
   std::unordered_map<uint64_t, std::deque<PostedRecv>> posted_;
-  // unexpected_[src][slot] -> FIFO of fully received payloads
-  std::vector<std::unordered_map<uint64_t, std::deque<std::vector<char>>>> unexpected_;
+  // unexpected_[src][slot] -> FIFO of messages that arrived before their recv: either the
+  // payload itself or, for single-copy messages, where to pull it from.
+  struct Unexpected {
+    std::vector<char> data;
+    bool deferred = false;
+    RemotePayload remote;
+    size_t size() const { return deferred ? remote.nbytes : data.size(); }
+  };
+  std::vector<std::unordered_map<uint64_t, std::deque<Unexpected>>> unexpected_;
   uint64_t anyCursor_ = 0;  // rotates the scan start of recv-from-any for fairness
 
   std::mutex regionMu_;

@@ -6,6 +6,7 @@
 #include <netinet/in.h>
 #include <netinet/tcp.h>
 #include <poll.h>
+#include <sched.h>
 #include <sys/socket.h>
 #include <sys/uio.h>
 #include <unistd.h>
@@ -501,8 +502,15 @@ void Pair::setPayload(TxOp& op, const char* data, size_t nbytes) {
   if (peerCanPull_ && nbytes >= cmaMinBytes() && pullable(data, nbytes)) {
     // Header only; the receiver pulls the bytes and answers FIN.
     op.cma = true;
+    op.cmaId = ++cmaSeq_;
     op.hdr.flags |= F_CMA;
     op.hdr.length = reinterpret_cast<uint64_t>(data);
+    // The id travels in whichever header field the opcode leaves free.
+    if (op.hdr.opcode == OP_PUT) {
+      op.hdr.slot = op.cmaId;
+    } else {
+      op.hdr.aux = op.cmaId;
+    }
     op.nbytes = 0;
   } else {
     op.nbytes = nbytes;
@@ -648,8 +656,12 @@ void Pair::readLoop(size_t budget) {
       }
     }
     if ((rx_.hdr.flags & F_CMA) != 0 && rx_.payloadRead < rx_.hdr.nbytes) {
-      if (!pullPayload()) return;
-      consumed += rx_.hdr.nbytes;
+      if (rx_.deferred) {
+        rx_.payloadRead = rx_.hdr.nbytes;  // parked: the posting thread pulls it later
+      } else {
+        if (!pullPayload()) return;
+        consumed += rx_.hdr.nbytes;
+      }
     }
     if (rx_.payloadRead < rx_.hdr.nbytes) {
       ssize_t n = ioRecv(rx_.dst + rx_.payloadRead, rx_.hdr.nbytes - rx_.payloadRead);
@@ -669,16 +681,40 @@ void Pair::readLoop(size_t budget) {
       }
     }
     if (rx_.payloadRead == rx_.hdr.nbytes) {
-      const bool fin = (rx_.hdr.flags & F_CMA) != 0;
+      const bool fin = (rx_.hdr.flags & F_CMA) != 0 && !rx_.deferred;
+      const uint64_t finId = rx_.hdr.opcode == OP_PUT ? rx_.hdr.slot : rx_.hdr.aux;
       finishMessage();
       rx_.reset();
       if (fin && state_ == CONNECTED) {
         TxOp op;
         op.hdr.opcode = OP_FIN;
+        op.hdr.slot = finId;
         enqueue(std::move(op));
       }
     }
   }
+}
+
+bool Pair::copyFrom(char* dst, uint64_t srcAddr, size_t nbytes, std::string* err) {
+  const char* src = reinterpret_cast<const char*>(srcAddr);
+  size_t done = 0;
+  while (done < nbytes) {
+    struct iovec local = {dst + done, nbytes - done};
+    struct iovec remote = {const_cast<char*>(src) + done, nbytes - done};
+    ssize_t n = ::process_vm_readv(peerPid_, &local, 1, &remote, 1, 0);
+    if (n > 0) {
+      done += static_cast<size_t>(n);
+    } else if (n == -1 && errno == EINTR) {
+      continue;
+    } else {
+      *err = strcat_all("process_vm_readv from rank ", peerRank_, " (pid ", peerPid_, "): ",
+                        n == 0 ? "short read" : std::strerror(errno));
+      return false;
+    }
+  }
+  g_cmaMessages.fetch_add(1, std::memory_order_relaxed);
+  g_cmaBytes.fetch_add(nbytes, std::memory_order_relaxed);
+  return true;
 }
 
 bool Pair::pullPayload() {
@@ -686,24 +722,31 @@ bool Pair::pullPayload() {
     signalException("protocol error: peer used the single-copy path without permission");
     return false;
   }
-  const char* src = reinterpret_cast<const char*>(rx_.hdr.length);
-  while (rx_.payloadRead < rx_.hdr.nbytes) {
-    struct iovec local = {rx_.dst + rx_.payloadRead, rx_.hdr.nbytes - rx_.payloadRead};
-    struct iovec remote = {const_cast<char*>(src) + rx_.payloadRead, rx_.hdr.nbytes - rx_.payloadRead};
-    ssize_t n = ::process_vm_readv(peerPid_, &local, 1, &remote, 1, 0);
-    if (n > 0) {
-      rx_.payloadRead += static_cast<size_t>(n);
-    } else if (n == -1 && errno == EINTR) {
-      continue;
-    } else {
-      signalException(strcat_all("process_vm_readv from rank ", peerRank_, " (pid ", peerPid_, "): ",
-                                 n == 0 ? "short read" : std::strerror(errno)));
-      return false;
-    }
+  std::string err;
+  if (!copyFrom(rx_.dst + rx_.payloadRead, rx_.hdr.length + rx_.payloadRead, rx_.hdr.nbytes - rx_.payloadRead, &err)) {
+    signalException(err);
+    return false;
   }
-  g_cmaMessages.fetch_add(1, std::memory_order_relaxed);
-  g_cmaBytes.fetch_add(rx_.hdr.nbytes, std::memory_order_relaxed);
+  rx_.payloadRead = rx_.hdr.nbytes;
   return true;
+}
+
+void Pair::pullDeferred(char* dst, uint64_t srcAddr, size_t nbytes, uint64_t id) {
+  // peerPid_ / canPull_ were fixed by the CAPS exchange long before any single-copy
+  // message could exist; the copy itself touches no pair state, so it runs unlocked and
+  // the loop thread keeps serving this pair meanwhile.
+  std::string err;
+  const bool ok = copyFrom(dst, srcAddr, nbytes, &err);
+  std::lock_guard<std::mutex> g(mu_);
+  if (!ok) {
+    signalException(err);
+    throwIfException();
+  }
+  throwIfException();
+  TxOp op;
+  op.hdr.opcode = OP_FIN;
+  op.hdr.slot = id;
+  enqueue(std::move(op));
 }
 
 uint64_t Pair::cmaMessages() { return g_cmaMessages.load(std::memory_order_relaxed); }
@@ -714,7 +757,26 @@ void Pair::beginMessage() {
   switch (h.opcode) {
     case OP_SEND_UNBOUND: {
       Context::Match m;
-      if (context_->matchIncoming(peerRank_, h.slot, &m)) {
+      bool matched;
+      if ((h.flags & F_CMA) != 0) {
+        if (!canPull_) {
+          signalException("protocol error: peer used the single-copy path without permission");
+          return;
+        }
+        Context::RemotePayload rp;
+        rp.srcAddr = h.length;
+        rp.nbytes = h.nbytes;
+        rp.id = h.aux;
+        matched = context_->matchOrDefer(peerRank_, h.slot, rp, &m);
+        if (!matched) {
+          rx_.kind = RX_NONE;
+          rx_.deferred = true;
+          break;
+        }
+      } else {
+        matched = context_->matchIncoming(peerRank_, h.slot, &m);
+      }
+      if (matched) {
         if (h.nbytes > m.capacity) {
           m.buf->signalException(strcat_all("distributed collective mismatch: rank ", peerRank_, " sent ",
                                             h.nbytes, " bytes on slot ", h.slot, " but the posted recv holds ",
@@ -835,8 +897,14 @@ void Pair::beginMessage() {
         signalException("protocol error: FIN without a pending single-copy send");
         return;
       }
-      TxOp op = std::move(awaitingFin_.front());
-      awaitingFin_.pop_front();
+      auto it = awaitingFin_.begin();
+      while (it != awaitingFin_.end() && it->cmaId != h.slot) ++it;
+      if (it == awaitingFin_.end()) {
+        signalException("protocol error: FIN for an unknown single-copy send");
+        return;
+      }
+      TxOp op = std::move(*it);
+      awaitingFin_.erase(it);
       completeTx(op);
       break;
     }
@@ -914,7 +982,7 @@ void Pair::syncWait(std::unique_lock<std::mutex>& lock, const std::function<bool
 int64_t Pair::spinBudgetNanos() {
   static const int64_t ns = [] {
     const char* v = std::getenv("GLB_TCP_SPIN_US");
-    long us = v != nullptr ? std::strtol(v, nullptr, 10) : 100;
+    long us = v != nullptr ? std::strtol(v, nullptr, 10) : 1000;
     if (us < 0) us = 0;
     return static_cast<int64_t>(us) * 1000;
   }();
@@ -935,6 +1003,7 @@ void Pair::spinWait(std::unique_lock<std::mutex>& lock, const std::function<bool
   const int64_t budget = spinBudgetNanos();
   if (budget == 0 || sync_) return;
   const auto deadline = std::chrono::steady_clock::now() + std::chrono::nanoseconds(budget);
+  unsigned spins = 0;
   while (!failed_ && state_ == CONNECTED && !pred()) {
     try {
       readLoop(kReadBudget);
@@ -943,9 +1012,15 @@ void Pair::spinWait(std::unique_lock<std::mutex>& lock, const std::function<bool
       return;
     }
     if (failed_ || pred()) return;
-    // Let the loop thread / senders in, then look again.
+    // Let the loop thread / senders in, then look again. On a saturated machine the
+    // thread that has to produce what we are waiting for may be runnable but not
+    // running: give the core away now and then instead of burning the whole time slice.
     lock.unlock();
-    for (int i = 0; i < 16; i++) cpuRelax();
+    if ((++spins & 31) == 0) {
+      ::sched_yield();
+    } else {
+      for (int i = 0; i < 16; i++) cpuRelax();
+    }
     lock.lock();
     if (std::chrono::steady_clock::now() >= deadline) return;
   }

@@ -25,8 +25,12 @@
 //                 from the sender's address space into the destination — one copy, no
 //                 socket buffers — then answers FIN, which completes the send. Pulls
 //                 happen where socket reads would (loop thread or spinning waiter), so
-//                 delivery stays eager: it never depends on the receiving user thread.
-//                 FINs come back in send order, so they carry no id.
+//                 a matched or bound message never depends on the receiving user thread.
+//                 An unbound message whose recv is not posted yet is parked as a
+//                 descriptor and pulled by the thread that posts the recv (no staging
+//                 copy); its sender completes then - the reference's rendezvous
+//                 semantics, which its eager small messages do not have. FIN carries the
+//                 id the sender put in the header.
 //
 // Threading: all pair state is guarded by `mu_`. In async mode the device loop
 // thread performs reads and flushes queued writes; writes are attempted inline
@@ -126,13 +130,18 @@ class Pair : public ::glb::transport::Pair, private Handler {
   // Drop queued sends that reference `buf` (it is being destroyed).
   void forgetUnbound(UnboundBuffer* buf);
 
+  // A recv was posted for a single-copy message that had been parked: fetch `nbytes` from
+  // `srcAddr` in the peer's address space into `dst` and release the sender (FIN `id`).
+  // Called from the posting thread; throws IoException if the bytes cannot be read.
+  void pullDeferred(char* dst, uint64_t srcAddr, size_t nbytes, uint64_t id);
+
   // Poison this pair: all pending and future operations throw IoException(msg).
   void signalExceptionExternal(const std::string& msg);
   // In sync mode: drive the socket from the calling thread until pred() holds.
   // `lock` must hold mu() on entry and holds it on return.
   void syncWait(std::unique_lock<std::mutex>& lock, const std::function<bool()>& pred,
                 std::chrono::milliseconds timeout, const char* what);
-  // Async mode, spin-then-block: for a bounded time (GLB_TCP_SPIN_US, default 100,
+  // Async mode, spin-then-block: for a bounded time (GLB_TCP_SPIN_US, default 1000,
   // 0 disables) the waiting user thread pulls bytes off the socket itself instead of
   // sleeping on a condvar until the loop thread has done so. That removes two thread
   // wake-ups (epoll thread, then waiter) from the small-message critical path while
@@ -172,6 +181,7 @@ class Pair : public ::glb::transport::Pair, private Handler {
     bool hasUbuf = false;
     bool notify = true;
     bool cma = false;  // header-only on the wire; completion on FIN
+    uint64_t cmaId = 0;
     WeakAnchor<UnboundBuffer> ubuf;
     UnboundBuffer* ubufRaw = nullptr;
     Buffer* bbuf = nullptr;
@@ -195,6 +205,7 @@ class Pair : public ::glb::transport::Pair, private Handler {
     char* dst = nullptr;
     Lease<UnboundBuffer> ubuf;
     Buffer* bbuf = nullptr;
+    bool deferred = false;  // single-copy message parked for its recv: nothing to read, no FIN yet
     std::vector<char> stash;
     void reset() {
       hdrRead = 0;
@@ -203,6 +214,7 @@ class Pair : public ::glb::transport::Pair, private Handler {
       dst = nullptr;
       ubuf.release();
       bbuf = nullptr;
+      deferred = false;
       std::vector<char>().swap(stash);
     }
   };
@@ -254,7 +266,9 @@ class Pair : public ::glb::transport::Pair, private Handler {
   bool failed_ = false;
 
   std::deque<TxOp> tx_;
-  std::deque<TxOp> awaitingFin_;  // CMA sends written to the wire, in order
+  std::deque<TxOp> awaitingFin_;  // CMA sends written to the wire, completed by FIN(id)
+  uint64_t cmaSeq_ = 0;
+  bool copyFrom(char* dst, uint64_t srcAddr, size_t nbytes, std::string* err);  // no lock needed
   bool peerCanPull_ = false;      // peer answered CAPS_OK
   bool canPull_ = false;          // we can read the peer's memory
   int peerPid_ = -1;

@@ -1,5 +1,7 @@
 #include "glb/transport/tcp/unbound_buffer.h"
 
+#include <sched.h>
+
 #include "glb/common/logging.h"
 #include "glb/transport/tcp/context.h"
 #include "glb/transport/tcp/pair.h"
@@ -55,6 +57,7 @@ void UnboundBuffer::spinUntil(std::unique_lock<std::mutex>& lock, Pred done) {
   if (budget == 0 || spinRanks_.empty()) return;
   const std::vector<int> ranks = spinRanks_;
   const auto deadline = std::chrono::steady_clock::now() + std::chrono::nanoseconds(budget);
+  unsigned spins = 0;
   while (!done()) {
     // Pair mutex before m_ is the completion path's order, so m_ is dropped here.
     lock.unlock();
@@ -62,6 +65,7 @@ void UnboundBuffer::spinUntil(std::unique_lock<std::mutex>& lock, Pred done) {
       auto* p = static_cast<Pair*>(context_->peekPair(r));
       if (p != nullptr) p->tryProgress();
     }
+    if ((++spins & 31) == 0) ::sched_yield();  // see Pair::spinWait
     lock.lock();
     if (std::chrono::steady_clock::now() >= deadline) return;
   }
@@ -70,9 +74,13 @@ void UnboundBuffer::spinUntil(std::unique_lock<std::mutex>& lock, Pred done) {
 template <typename Pred>
 bool UnboundBuffer::driveSyncPairs(std::unique_lock<std::mutex>& lock, Pred done,
                                    std::chrono::milliseconds timeout) {
+  // Every sync pair of the context, not only this buffer's peers: with no loop thread,
+  // whatever arrives anywhere (acknowledgements for another buffer's sends, messages that
+  // belong in the unexpected queue) is only ever read by a waiting thread.
   std::vector<Pair*> pairs;
   bool busy = true;
-  for (int r : spinRanks_) {
+  for (int r = 0; r < context_->size; r++) {
+    if (r == context_->rank) continue;
     auto* p = static_cast<Pair*>(context_->peekPair(r));
     if (p != nullptr && p->isSync()) {
       pairs.push_back(p);

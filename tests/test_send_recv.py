@@ -373,3 +373,44 @@ def test_unbound_buffers_on_sync_pairs(busy):
     t0 = time.time()
     assert all(gb.spawn_threads(size, fn))
     assert time.time() - t0 < 8  # the closing barrier of spawn_threads must not time out
+
+
+def test_parked_large_messages_complete_out_of_order():
+    """Large unbound messages whose recv is not posted yet are parked as descriptors and
+    pulled by the thread that posts the recv. Post the recvs in the opposite order of the
+    sends: each FIN must complete its own send (ids, not FIFO), the sender's memory must stay
+    untouched until then, and a small eager message in between is unaffected."""
+    n = 1 << 17  # 512 KiB
+
+    def fn(ctx):
+        peer = 1 - ctx.rank
+        gb.barrier(ctx)
+        time.sleep(0.05)
+        if ctx.rank == 0:
+            a = np.full(n, 1.0, np.float32)
+            b = np.full(n, 2.0, np.float32)
+            c = np.full(4, 3.0, np.float32)
+            ua, ub_, uc = ub(ctx, a), ub(ctx, b), ub(ctx, c)
+            ua.send(peer, 11)
+            ub_.send(peer, 22)
+            uc.send(peer, 33)
+            assert uc.wait_send() == peer          # eager: completes at once
+            # the receiver takes slot 22 first, so b's FIN arrives before a's
+            assert ub_.wait_send() == peer
+            assert ua.wait_send() == peer
+        else:
+            time.sleep(0.2)                         # both large messages are parked by now
+            a, b, c = np.zeros(n, np.float32), np.zeros(n, np.float32), np.zeros(4, np.float32)
+            ua, ub_, uc = ub(ctx, a), ub(ctx, b), ub(ctx, c)
+            ub_.recv(peer, 22)
+            assert ub_.wait_recv() == peer and b[0] == 2.0 and b[-1] == 2.0
+            uc.recv(peer, 33)
+            assert uc.wait_recv() == peer and c[0] == 3.0
+            ua.recv(peer, 11)
+            assert ua.wait_recv() == peer and a[0] == 1.0 and a[-1] == 1.0
+        gb.barrier(ctx)
+        return True
+
+    before = _C.tcp_stats()["cma_messages"]
+    assert all(gb.spawn_threads(2, fn))
+    assert _C.tcp_stats()["cma_messages"] - before >= 2

@@ -15,7 +15,6 @@ import importlib
 import os
 import sys
 
-__version__ = "0.1.0"
 
 
 def _load_native():
@@ -54,6 +53,9 @@ from ._C import (  # noqa: E402
     TimeoutError,
 )
 from .types import DataType, ReduceOp, Algorithm  # noqa: E402
+
+__version__ = _C.__version__
+build_config = _C.build_config
 from .ops.host import (  # noqa: E402
     allgather,
     allgatherv,

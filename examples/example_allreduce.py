@@ -6,7 +6,10 @@ import sys
 
 import numpy as np
 
-import gloo_b200 as gb
+import os
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # run from a checkout
+
+import gloo_b200 as gb  # noqa: E402
 
 rank, size, path = int(sys.argv[1]), int(sys.argv[2]), sys.argv[3]
 ctx = gb.init_context(rank, size, path=path)            # FileStore rendezvous + full TCP mesh

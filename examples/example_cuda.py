@@ -3,11 +3,14 @@
   torchrun --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 examples/example_cuda.py
 """
 import os
+import sys
 
 import torch
 
-import gloo_b200 as gb
-from gloo_b200.ops import cuda as gcu
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))  # run from a checkout
+
+import gloo_b200 as gb  # noqa: E402
+from gloo_b200.ops import cuda as gcu  # noqa: E402
 
 rank, size, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(local)

@@ -248,13 +248,16 @@ def _make_allreduce_class(name: str, algo: str):
         __doc__ = f"{name}(ctx, tensors, streams=None, op=SUM, host_workspace=False) — run() is one fused launch."
 
         def __init__(self, ctx, tensors, streams=None, op: ReduceOp = ReduceOp.SUM, host_workspace: bool = False,
-                     literal: bool = False):
+                     literal: bool = False, variant: str = "auto"):
+            # literal=True runs the named schedule step by step; otherwise the kernel variant is
+            # picked per message size ("auto") or pinned ("one_shot" / "two_shot" / "nvls").
             tensors = list(tensors) if isinstance(tensors, (list, tuple)) else [tensors]
             self.tensors = tensors
             _, n, dt, _ = describe(tensors[0])
             st = [_stream(s) for s in streams] if streams else []
+            assert variant in ("auto", "one_shot", "two_shot", "nvls")
             self._impl = _cu.CudaAllreduce(ctx, [t.data_ptr() for t in tensors], n, int(dt), int(op), st,
-                                           ALGOS[algo] if literal else ALGOS["auto"], host_workspace)
+                                           ALGOS[algo] if literal else ALGOS[variant], host_workspace)
 
         def run(self):
             self._impl.run()
@@ -296,7 +299,7 @@ class CudaHostAllreduce:
     """
 
     def __init__(self, ctx, cuda_ctx: "CudaContext", host_inputs, host_output, chunks: int = 16,
-                 op: ReduceOp = ReduceOp.SUM):
+                 op: ReduceOp = ReduceOp.SUM, variant: str = "two_shot"):
         import torch
 
         host_inputs = list(host_inputs) if isinstance(host_inputs, (list, tuple)) else [host_inputs]
@@ -317,8 +320,12 @@ class CudaHostAllreduce:
             self.bounds = [(lo, min(n, lo + per)) for lo in range(0, n, per)] if n else []
             self.algos = []
             for lo, hi in self.bounds:
+                # Pieces are interior ranges of the symmetric buffers. The two-shot kernel is
+                # pinned: it is the variant measured on such ranges, and the reduction hides
+                # under the PCIe copies either way.
                 self.algos.append(CudaAllreduceRingChunked(ctx, [d[lo:hi] for d in self.dev],
-                                                           streams=[self.comp] * len(self.dev), op=op))
+                                                           streams=[self.comp] * len(self.dev), op=op,
+                                                           variant=variant))
             self.ev_in = [torch.cuda.Event() for _ in self.bounds]
             self.ev_red = [torch.cuda.Event() for _ in self.bounds]
             self.ev_start, self.ev_done = torch.cuda.Event(), torch.cuda.Event()

@@ -50,6 +50,8 @@ Probe probe() {
   return p;
 }
 
+std::vector<std::string> getDeviceNames() { return probe().devices; }
+
 std::shared_ptr<::glb::transport::Device> CreateDevice(const struct attr& a) {
   Probe p = probe();
   if (!p.libraryLoaded || p.devices.empty()) {

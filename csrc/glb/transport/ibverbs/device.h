@@ -38,6 +38,10 @@ struct Probe {
 // Never throws.
 Probe probe();
 
+// Names of the RDMA devices ibv_get_device_list reports (empty without libibverbs / HCA).
+// Reference: gloo/transport/ibverbs/device.h getDeviceNames().
+std::vector<std::string> getDeviceNames();
+
 // Throws InvalidOperationException naming the missing piece (library, device, or the
 // verbs data path of this build).
 std::shared_ptr<::glb::transport::Device> CreateDevice(const struct attr&);

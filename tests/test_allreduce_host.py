@@ -53,6 +53,34 @@ def test_allreduce_many_segments(algo):
     assert all(gb.spawn_threads(size, fn))
 
 
+@pytest.mark.parametrize("size", [2, 3, 5])
+@pytest.mark.parametrize("max_segment", [None, 128, 4096])
+def test_ring_streams_segments_and_leaves_the_input_alone(size, max_segment):
+    """The ring is one pipeline of segments and reads a single out-of-place input in place
+    (no up-front copy): the input must come back untouched, every length (including ones
+    that leave some chunks short or empty) must work in place and out of place, and large
+    vectors take the single-copy transport path between the rank threads."""
+    counts = [1, size - 1, size + 1, 1000, 4099, 700_001]
+
+    def fn(ctx):
+        for count in counts:
+            kw = {} if max_segment is None else {"max_segment_size": max_segment}
+            if max_segment == 128 and count > 10_000:
+                continue  # thousands of 128-byte segments add nothing
+            src = (np.arange(count, dtype=np.float64) % 997 + ctx.rank).astype(np.float64)
+            keep = src.copy()
+            out = np.full(count, -1.0)
+            gb.allreduce(ctx, out, inputs=src, **kw)
+            want = (np.arange(count, dtype=np.float64) % 997) * size + size * (size - 1) / 2
+            np.testing.assert_array_equal(src, keep)
+            np.testing.assert_array_equal(out, want)
+            gb.allreduce(ctx, src, **kw)  # in place
+            np.testing.assert_array_equal(src, want)
+        return True
+
+    assert all(gb.spawn_threads(size, fn))
+
+
 @pytest.mark.parametrize("dtype", [np.int8, np.uint8, np.int32, np.int64, np.uint64, np.float64, np.float16])
 @pytest.mark.parametrize("op", [gb.ReduceOp.SUM, gb.ReduceOp.PRODUCT, gb.ReduceOp.MIN, gb.ReduceOp.MAX])
 def test_allreduce_types_ops(dtype, op):

@@ -243,6 +243,7 @@ PYBIND11_MODULE(_C, m) {
     return transport::ibverbs::CreateDevice(a);
   }, py::arg("name") = "", py::arg("port") = 1, py::arg("index") = 0,
         "Raises InvalidOperationError naming what is missing (library, HCA, or the verbs data path of this build).");
+  m.def("ibverbs_device_names", &transport::ibverbs::getDeviceNames);
   m.def("ibverbs_probe", [] {
     auto p = transport::ibverbs::probe();
     py::dict d;

@@ -44,6 +44,8 @@ def test_uv_device_runs_new_style_collectives():
 def test_ibverbs_probe_and_error():
     p = _C.ibverbs_probe()
     assert set(p) == {"library", "devices", "peer_memory_module", "detail"} and p["detail"]
+    if hasattr(_C, "ibverbs_device_names"):
+        assert _C.ibverbs_device_names() == p["devices"]
     with pytest.raises(gb.InvalidOperationError) as e:
         _C.create_ibverbs_device()
     assert "ibverbs" in str(e.value) and ("tcp" in str(e.value))

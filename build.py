@@ -122,10 +122,12 @@ def write_ninja(verbose: bool, sanitize: str = "") -> Path:
     w("  deps = gcc")
     w("  description = NVCC $in")
     w("rule link_shared")
-    w("  command = $cxx -shared -o $out $in $ldflags $extra")
+    # link to a temporary name and rename: a reader (an importing process, a snapshot of
+    # the tree) sees either the old or the new file, never a half-written one
+    w("  command = $cxx -shared -o $out.tmp $in $ldflags $extra && mv -f $out.tmp $out")
     w("  description = LINK $out")
     w("rule link_exe")
-    w("  command = $cxx -o $out $in $ldflags $extra")
+    w("  command = $cxx -o $out.tmp $in $ldflags $extra && mv -f $out.tmp $out")
     w("  description = LINK $out")
     w("")
 

@@ -1,0 +1,37 @@
+"""torch.distributed backend "glb": every c10d collective on CPU tensors, point-to-point,
+sub-groups and DistributedDataParallel, with real processes (the consumer-facing counterpart
+of ProcessGroupGloo, which is how most users reach pytorch/gloo)."""
+import os
+import subprocess
+import sys
+import tempfile
+
+import pytest
+
+WORKER = os.path.join(os.path.dirname(os.path.abspath(__file__)), "pg_worker.py")
+
+
+@pytest.mark.parametrize("size", [1, 2, 3])
+def test_torch_distributed_backend(size):
+    init = os.path.join(tempfile.mkdtemp(prefix="glb_pg_"), "init")
+    procs = [subprocess.Popen([sys.executable, WORKER, init, str(r), str(size)], stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for r in range(size)]
+    outs = [p.communicate(timeout=240) for p in procs]
+    for r, (p, (out, err)) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"rank {r} ok" in out, (r, p.returncode, out[-500:], err[-2000:])
+
+
+@pytest.mark.gpu
+def test_torch_distributed_backend_cuda():
+    """CUDA tensors through the same backend: one process per GPU when there are several,
+    otherwise a single rank (plumbing only: a one-rank collective is the identity)."""
+    import torch
+
+    size = min(torch.cuda.device_count(), 4)
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "pg_cuda_worker.py")
+    init = os.path.join(tempfile.mkdtemp(prefix="glb_pg_cuda_"), "init")
+    procs = [subprocess.Popen([sys.executable, worker, init, str(r), str(size)], stdout=subprocess.PIPE,
+                              stderr=subprocess.PIPE, text=True) for r in range(size)]
+    outs = [p.communicate(timeout=240) for p in procs]
+    for r, (p, (out, err)) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"rank {r} ok" in out, (r, p.returncode, out[-500:], err[-2000:])

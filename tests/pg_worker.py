@@ -89,6 +89,15 @@ def main():
         [r.wait() for r in reqs]
         assert got[0] == left
 
+    # object collectives ride on byte / long tensors
+    objs = [None] * size
+    dist.all_gather_object(objs, {"rank": rank, "name": "r" * (rank + 1)})
+    assert [o["rank"] for o in objs] == list(range(size)) and objs[-1]["name"] == "r" * size
+    box = [{"cfg": 42}] if rank == 0 else [None]
+    dist.broadcast_object_list(box, src=0)
+    assert box[0] == {"cfg": 42}
+    dist.barrier()
+
     # a sub-group gets its own context through a prefixed store
     if size >= 3:
         sub = dist.new_group(ranks=[0, 2])

@@ -24,6 +24,15 @@ for NAME in "$@"; do
     wait; rm -rf $D
   done
 done
+# the self-test: same instrumentation, results checked (threads as ranks in one process)
+ST=gloo_b200/bin/glb_selftest_$SAN
+if [ -x $ST ]; then
+  TSAN_OPTIONS="suppressions=$PWD/.tsan-suppressions halt_on_error=0 log_path=$OUT/selftest.r0" \
+  ASAN_OPTIONS="detect_leaks=1 log_path=$OUT/selftest.r0" \
+  UBSAN_OPTIONS="print_stacktrace=1 log_path=$OUT/selftest.r0" \
+    $ST 2 3 4 >$OUT/selftest.stdout 2>&1 || echo "selftest failed under $SAN (see $OUT/selftest.stdout)"
+  tail -1 $OUT/selftest.stdout
+fi
 n=$(cat $OUT/*.r[0-9]*.[0-9]* 2>/dev/null | grep -c "WARNING: ThreadSanitizer\|ERROR: AddressSanitizer\|ERROR: LeakSanitizer\|runtime error")
 echo "$SAN sanitizer reports: $n (logs in $OUT)"
 [ "$n" = 0 ]

@@ -116,3 +116,14 @@ def test_mpi_bootstrap_against_thread_world_mpi():
     for p in (2, 5):
         out = subprocess.run([exe, str(p)], capture_output=True, text=True, timeout=60)
         assert out.returncode == 0 and out.stdout.startswith(f"OK {p * (p + 1) // 2}"), (out.stdout, out.stderr)
+
+
+SELFTEST = os.path.join(ROOT, "gloo_b200", "bin", "glb_selftest")
+
+
+@pytest.mark.skipif(not os.path.exists(SELFTEST), reason="selftest binary not built")
+def test_cpp_selftest():
+    """The C++ API without Python in the loop: threads as ranks, every host collective family,
+    closed-form checks (csrc/glb/benchmark/selftest_main.cc)."""
+    out = subprocess.run([SELFTEST, "1", "2", "3", "5", "8"], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and "PASS (0 failures)" in out.stdout, (out.stdout[-1500:], out.stderr[-1500:])

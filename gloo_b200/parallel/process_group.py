@@ -23,7 +23,7 @@ from __future__ import annotations
 
 import os
 from datetime import timedelta
-from typing import Dict, List, Optional
+from typing import Dict, Optional
 
 import torch
 import torch.distributed as dist
@@ -97,7 +97,6 @@ class GlbProcessGroup(dist.ProcessGroup):
         self.ctx.set_timeout(self._timeout_ms)
         self.ctx.connect_full_mesh(_C10dStore(store), device)
         self._cuda: Dict[int, object] = {}
-        self._p2p_seq: Dict[tuple, int] = {}
 
     # ---- plumbing -------------------------------------------------------------------------
     def getBackendName(self):

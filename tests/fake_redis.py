@@ -4,7 +4,6 @@ commands served). There is no redis-server in the image; this lets the RESP clie
 against real sockets and real framing. Runs as its own process (`python fake_redis.py` prints the
 port): the store's blocking calls hold the GIL, so an in-process server could never answer."""
 import socket
-import sys
 import threading
 import time
 

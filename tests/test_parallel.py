@@ -1,5 +1,4 @@
 """parallel/ strategies on the host path (CPU tensors over TCP)."""
-import numpy as np
 import torch
 
 import gloo_b200 as gb

@@ -4,7 +4,6 @@ benchmark CLI's --transport switch (reference: gloo/benchmark/options.cc:149-180
 import os
 import shutil
 import subprocess
-import sys
 import tempfile
 
 import numpy as np

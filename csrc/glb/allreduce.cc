@@ -197,7 +197,8 @@ void ring(const AllreduceOptions& opts, UnboundBuffer* out0, UnboundBuffer* src)
   for (size_t k = 0; k < agSends; k++) agOut->waitSend(timeout);
 }
 
-void bcube(const AllreduceOptions& opts, UnboundBuffer* out0) {
+// `src`: where this rank's contribution is read from in the first step (see ring()).
+void bcube(const AllreduceOptions& opts, UnboundBuffer* out0, UnboundBuffer* src) {
   const auto& context = opts.context;
   const int P = context->size;
   const int r = context->rank;
@@ -237,23 +238,27 @@ void bcube(const AllreduceOptions& opts, UnboundBuffer* out0) {
       tmp->recv(peerAt(i, d), slot + i, k * mine.len * es, mine.len * es);
       k++;
     }
+    // Step 0 reads the caller's input where it lies; from then on everything this rank
+    // still needs is inside the block it owns in the output.
+    UnboundBuffer* from = i == 0 ? src : out0;
     for (int d = 0; d < f; d++) {
       if (d == digit[i]) continue;
       const Range theirs = subRange(cur, f, d);
-      out0->send(peerAt(i, d), slot + i, theirs.off * es, theirs.len * es);
+      from->send(peerAt(i, d), slot + i, theirs.off * es, theirs.len * es);
     }
     // Reduce contributions in arrival order.
     for (int n = 0; n < f - 1; n++) {
-      int src = -1;
-      tmp->waitRecv(&src, opts.timeout);
-      int d = digit[i] + (src - r) / stride[i];
+      int srcRank = -1;
+      tmp->waitRecv(&srcRank, opts.timeout);
+      int d = digit[i] + (srcRank - r) / stride[i];
       int idx = d < digit[i] ? d : d - 1;
       if (mine.len > 0) {
         char* dst = base + mine.off * es;
-        opts.reduce(dst, dst, tmpStorage.data() + idx * mine.len * es, mine.len);
+        const char* acc = (i == 0 && n == 0) ? static_cast<const char*>(src->ptr) + mine.off * es : dst;
+        opts.reduce(dst, acc, tmpStorage.data() + idx * mine.len * es, mine.len);
       }
     }
-    for (int n = 0; n < f - 1; n++) out0->waitSend(opts.timeout);
+    for (int n = 0; n < f - 1; n++) from->waitSend(opts.timeout);
   }
 
   // Allgather: mirror image, results land directly in the output.
@@ -291,9 +296,8 @@ void allreduce(const AllreduceOptions& opts) {
   // Local phase 1: fold every input into out[0].
   UnboundBuffer* out0 = opts.out[0].get();
   UnboundBuffer* src = out0;
-  const bool isRing = opts.algorithm == AllreduceOptions::UNSPECIFIED || opts.algorithm == AllreduceOptions::RING;
-  if (isRing && context->size > 1 && opts.in.size() == 1 && opts.in[0]->ptr != out0->ptr) {
-    src = opts.in[0].get();  // the ring reads the input in place: no up-front copy
+  if (context->size > 1 && opts.in.size() == 1 && opts.in[0]->ptr != out0->ptr) {
+    src = opts.in[0].get();  // both algorithms read a single input where it lies: no up-front copy
   } else if (!opts.in.empty()) {
     if (opts.in[0]->ptr != out0->ptr) std::memcpy(out0->ptr, opts.in[0]->ptr, bytes);
     for (size_t i = 1; i < opts.in.size(); i++) {
@@ -313,7 +317,7 @@ void allreduce(const AllreduceOptions& opts) {
         ring(opts, out0, src);
         break;
       case AllreduceOptions::BCUBE:
-        bcube(opts, out0);
+        bcube(opts, out0, src);
         break;
       default:
         GLB_THROW_INVALID_OPERATION_EXCEPTION("allreduce: unknown algorithm ", opts.algorithm);

@@ -44,7 +44,6 @@ from torch.futures import Future
 from .. import _C
 from ..ops import host as H
 from ..types import ReduceOp
-from ..utils.launch import create_device
 
 BACKEND_NAME = "glb"
 _P2P_PREFIX = 0x7D  # slot prefix of send/recv issued through the process group
@@ -92,7 +91,10 @@ class GlbProcessGroup(dist.ProcessGroup):
         self._rank, self._world = rank, world_size
         self._timeout_ms = max(1000, int(timeout.total_seconds() * 1000)) if timeout else 30 * 60 * 1000
         iface = os.environ.get("GLB_SOCKET_IFNAME") or os.environ.get("GLOO_SOCKET_IFNAME") or ""
-        device = _C.create_tcp_device("", iface, False, 1) if iface else create_device()
+        # No interface named: bind this host's own name (falls back to loopback when the name
+        # does not resolve, e.g. in a container), so that ranks on other hosts can reach it -
+        # the same rule ProcessGroupGloo applies.
+        device = _C.create_tcp_device("", iface, False, 1)
         self.ctx = _C.Context(rank, world_size, 2)
         self.ctx.set_timeout(self._timeout_ms)
         self.ctx.connect_full_mesh(_C10dStore(store), device)

@@ -126,3 +126,35 @@ def test_cpp_selftest():
     closed-form checks (csrc/glb/benchmark/selftest_main.cc)."""
     out = subprocess.run([SELFTEST, "1", "2", "3", "5", "8"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and "PASS (0 failures)" in out.stdout, (out.stdout[-1500:], out.stderr[-1500:])
+
+
+def test_device_on_a_real_interface():
+    """Bind the first non-loopback interface that has an address (what a multi-node job does
+    with GLB_SOCKET_IFNAME) and run a collective through it."""
+    import threading
+
+    cands = [n for n in sorted(os.listdir("/sys/class/net")) if n != "lo"]
+    dev = None
+    for name in cands:
+        try:
+            dev = gb.create_device(hostname="", iface=name)
+            break
+        except gb.GlbError:
+            continue
+    if dev is None:
+        pytest.skip("no non-loopback interface with an address")
+    assert "127.0.0.1" not in str(dev)
+    store, out = gb.HashStore(), [None, None]
+
+    def rank(r):
+        ctx = gb.Context(r, 2)
+        ctx.connect_full_mesh(store, gb.create_device(hostname="", iface=name))
+        x = np.full(1 << 17, r + 1, np.float32)  # large enough for the single-copy path
+        gb.allreduce(ctx, x)
+        gb.barrier(ctx)
+        out[r] = float(x[-1])
+
+    ths = [threading.Thread(target=rank, args=(r,)) for r in range(2)]
+    [t.start() for t in ths]
+    [t.join(60) for t in ths]
+    assert out == [3.0, 3.0]

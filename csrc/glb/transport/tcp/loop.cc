@@ -51,6 +51,14 @@ void Loop::registerDescriptor(int fd, int events, Handler* h) {
   GLB_ENFORCE_NE(rv, -1, "epoll_ctl: ", std::strerror(errno));
 }
 
+void Loop::modifyDescriptor(int fd, int events, Handler* h) {
+  struct epoll_event ev;
+  std::memset(&ev, 0, sizeof(ev));
+  ev.events = static_cast<uint32_t>(events);
+  ev.data.ptr = h;
+  if (epoll_ctl(epfd_, EPOLL_CTL_MOD, fd, &ev) == -1 && errno == ENOENT) registerDescriptor(fd, events, h);
+}
+
 void Loop::unregisterDescriptor(int fd, Handler* h) {
   int rv = epoll_ctl(epfd_, EPOLL_CTL_DEL, fd, nullptr);
   if (rv == -1 && errno != ENOENT && errno != EBADF) {

@@ -35,6 +35,8 @@ class Loop final {
   Loop& operator=(const Loop&) = delete;
 
   void registerDescriptor(int fd, int events, Handler* h);
+  // Change the interest set of an already registered descriptor (one syscall).
+  void modifyDescriptor(int fd, int events, Handler* h);
   void unregisterDescriptor(int fd, Handler* h);
   // Non-waiting variant: stops future events but a handler call that is already
   // queued in the current batch may still happen. Pair it with barrier() before

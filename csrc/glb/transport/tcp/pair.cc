@@ -327,7 +327,7 @@ void Pair::setSync(bool sync, bool busyPoll) {
 
 void Pair::armEvents(bool wantWrite) {
   wantWrite_ = wantWrite;
-  loop_->registerDescriptor(fd_, EPOLLIN | (wantWrite ? static_cast<int>(EPOLLOUT) : 0), this);
+  loop_->modifyDescriptor(fd_, EPOLLIN | (wantWrite ? static_cast<int>(EPOLLOUT) : 0), this);
 }
 
 // ---- error handling ---------------------------------------------------------------
@@ -1001,9 +1001,13 @@ inline void cpuRelax() {
 
 void Pair::spinWait(std::unique_lock<std::mutex>& lock, const std::function<bool()>& pred) {
   const int64_t budget = spinBudgetNanos();
-  if (budget == 0 || sync_) return;
+  if (budget == 0 || sync_ || failed_ || state_ != CONNECTED || pred()) return;
   const auto deadline = std::chrono::steady_clock::now() + std::chrono::nanoseconds(budget);
   unsigned spins = 0;
+  // While this thread polls the socket the loop thread would only wake up to find the
+  // data already taken (level-triggered epoll fires on every arrival): park the
+  // descriptor for the duration of the spin.
+  PauseGuard quiet(this, /*locked=*/true);
   while (!failed_ && state_ == CONNECTED && !pred()) {
     try {
       readLoop(kReadBudget);
@@ -1023,6 +1027,44 @@ void Pair::spinWait(std::unique_lock<std::mutex>& lock, const std::function<bool
     }
     lock.lock();
     if (std::chrono::steady_clock::now() >= deadline) return;
+  }
+}
+
+// ---- epoll parking while a waiter polls --------------------------------------------------
+
+bool Pair::pauseEventsLocked() {
+  if (sync_ || wantWrite_ || state_ != CONNECTED || fd_ < 0) return false;
+  if (paused_++ == 0) loop_->modifyDescriptor(fd_, 0, this);
+  return true;
+}
+
+void Pair::resumeEventsLocked() {
+  // armEvents() is idempotent: if a queued write re-enabled the descriptor meanwhile this
+  // just registers the same interest again.
+  if (paused_ > 0 && --paused_ == 0 && !sync_ && state_ == CONNECTED && fd_ >= 0) armEvents(wantWrite_);
+}
+
+Pair::PauseGuard::PauseGuard(Pair* p, bool locked) : pair_(p), locked_(locked) {
+  static const bool enabled = [] {
+    const char* v = std::getenv("GLB_TCP_PARK_EPOLL");
+    return v == nullptr || std::atoi(v) != 0;
+  }();
+  if (!enabled) return;
+  if (locked_) {
+    took_ = pair_->pauseEventsLocked();
+  } else {
+    std::lock_guard<std::mutex> g(pair_->mu_);
+    took_ = pair_->pauseEventsLocked();
+  }
+}
+
+Pair::PauseGuard::~PauseGuard() {
+  if (!took_) return;
+  if (locked_) {
+    pair_->resumeEventsLocked();
+  } else {
+    std::lock_guard<std::mutex> g(pair_->mu_);
+    pair_->resumeEventsLocked();
   }
 }
 

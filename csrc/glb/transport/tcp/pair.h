@@ -152,6 +152,20 @@ class Pair : public ::glb::transport::Pair, private Handler {
   // mutex is free. Never throws, never blocks.
   void tryProgress();
   static int64_t spinBudgetNanos();
+  // Parks this pair's descriptor in epoll for the lifetime of the guard (GLB_TCP_PARK_EPOLL=0
+  // disables). `locked`: the caller holds mu() when the guard is created and when it dies.
+  class PauseGuard {
+   public:
+    PauseGuard(Pair* p, bool locked);
+    ~PauseGuard();
+    PauseGuard(const PauseGuard&) = delete;
+    PauseGuard& operator=(const PauseGuard&) = delete;
+
+   private:
+    Pair* pair_;
+    bool locked_;
+    bool took_ = false;
+  };
   // Process-wide counters of the single-copy path (tests and diagnostics).
   static uint64_t cmaMessages();
   static uint64_t cmaBytes();
@@ -241,6 +255,8 @@ class Pair : public ::glb::transport::Pair, private Handler {
   void finishMessage();         // requires mu_
   void signalException(const std::string& msg);  // requires mu_
   void armEvents(bool wantWrite);                // requires mu_
+  bool pauseEventsLocked();                      // requires mu_; false if parking is not possible now
+  void resumeEventsLocked();                     // requires mu_
 
   Context* const context_;
   Device* const device_;
@@ -257,6 +273,7 @@ class Pair : public ::glb::transport::Pair, private Handler {
   bool sync_ = false;
   bool busyPoll_ = false;
   bool wantWrite_ = false;
+  int paused_ = 0;  // waiters currently polling the socket themselves (descriptor parked)
   bool expecting_ = false;
   int fd_ = -1;
   Address self_;

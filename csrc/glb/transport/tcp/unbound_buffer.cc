@@ -2,6 +2,9 @@
 
 #include <sched.h>
 
+#include <memory>
+#include <vector>
+
 #include "glb/common/logging.h"
 #include "glb/transport/tcp/context.h"
 #include "glb/transport/tcp/pair.h"
@@ -58,6 +61,28 @@ void UnboundBuffer::spinUntil(std::unique_lock<std::mutex>& lock, Pred done) {
   const std::vector<int> ranks = spinRanks_;
   const auto deadline = std::chrono::steady_clock::now() + std::chrono::nanoseconds(budget);
   unsigned spins = 0;
+  // Ring-like patterns talk to one or two peers: park their descriptors so the loop thread
+  // sleeps through the arrivals this thread is about to consume (two syscalls per peer;
+  // not worth it for wide fan-in such as alltoall).
+  std::vector<std::unique_ptr<Pair::PauseGuard>> quiet;
+  if (ranks.size() <= 2 && !done()) {
+    lock.unlock();
+    for (int r : ranks) {
+      auto* p = static_cast<Pair*>(context_->peekPair(r));
+      if (p != nullptr) quiet.push_back(std::make_unique<Pair::PauseGuard>(p, /*locked=*/false));
+    }
+    lock.lock();
+  }
+  struct Unpark {  // guards take pair mutexes: release them without holding m_
+    std::unique_lock<std::mutex>& lock;
+    std::vector<std::unique_ptr<Pair::PauseGuard>>& q;
+    ~Unpark() {
+      if (q.empty()) return;
+      lock.unlock();
+      q.clear();
+      lock.lock();
+    }
+  } unpark{lock, quiet};
   while (!done()) {
     // Pair mutex before m_ is the completion path's order, so m_ is dropped here.
     lock.unlock();

@@ -54,6 +54,21 @@ def main():
             want = os.environ.get("GLB_TCP_CMA", "1") != "0"
             got = gb._C.tcp_stats()["cma_messages"] > before
             assert got == want, (got, want)
+        elif mode == "parked":
+            # rank 0 sends a large message that rank 1 has not asked for yet (it is parked at
+            # rank 1 as a descriptor of rank 0's memory); the parent then kills rank 0 and only
+            # afterwards lets rank 1 post the recv, which must fail cleanly.
+            big = np.ones(1 << 18, np.float32)
+            u = ctx.create_unbound_buffer(big.ctypes.data, big.nbytes)
+            if rank == 0:
+                u.send(1, 77)
+                time.sleep(120)
+            else:
+                while not os.path.exists(os.path.join(store_dir, "go")):
+                    time.sleep(0.02)
+                u.recv(0, 77)
+                u.wait_recv()
+                print("unexpectedly received", file=sys.stderr)
         elif mode == "sendrecv_loop":
             peer = (rank + 1) % size
             src = (rank - 1) % size

@@ -101,6 +101,22 @@ def test_healthy_run_in_sync_modes(sync):
     assert codes == [0] * 3, (codes, [p.stderr.read()[-400:] for p in procs])
 
 
+def test_sender_dies_while_its_message_is_parked():
+    """Single-copy path: a large message whose recv is not posted yet exists only as a
+    descriptor of the sender's memory. If the sender dies first, posting the recv must raise
+    IoError (the pull fails, or the pair has already noticed the EOF) - never hang or crash."""
+    d, procs = launch(2, "parked", timeout_ms=3000)
+    wait_ready(d, 2)
+    time.sleep(0.5)
+    procs[0].send_signal(signal.SIGKILL)
+    procs[0].wait()
+    time.sleep(0.2)
+    open(os.path.join(d, "go"), "w").close()
+    codes = reap(procs, 20)
+    assert codes[0] == -signal.SIGKILL
+    assert codes[1] == 10, (codes, procs[1].stderr.read()[-500:])
+
+
 @pytest.mark.parametrize("size", [2, 3])
 def test_sigstop_hits_timeout(size):
     timeout_ms = 1500

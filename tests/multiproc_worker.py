@@ -60,6 +60,8 @@ def main():
             # afterwards lets rank 1 post the recv, which must fail cleanly.
             big = np.ones(1 << 18, np.float32)
             u = ctx.create_unbound_buffer(big.ctypes.data, big.nbytes)
+            gb.barrier(ctx)
+            time.sleep(0.1)  # the capability handshake is over: large sends now go header-only
             if rank == 0:
                 u.send(1, 77)
                 time.sleep(120)

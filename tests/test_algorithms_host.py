@@ -44,6 +44,20 @@ def test_allreduce_classes(cls, size):
     assert all(gb.spawn_threads(size, fn))
 
 
+@pytest.mark.parametrize("size", [24, 32])
+def test_halving_doubling_many_ranks(size):
+    """The reference runs halving-doubling up to 24 and 32 ranks (allreduce_test.cc:143-299):
+    24 = 16-rank core + 8 folded extras, 32 = a full 5-step hypercube."""
+    def fn(ctx):
+        for count in (4, 1000):
+            bufs = _fixture(ctx.rank, size, 1, count)
+            alg.AllreduceHalvingDoubling(ctx, bufs).run()
+            np.testing.assert_allclose(bufs[0], _expected(size, 1, count), rtol=1e-5)
+        return True
+
+    assert all(gb.spawn_threads(size, fn))
+
+
 @pytest.mark.parametrize("base,size", [(2, 8), (3, 9), (3, 27), (4, 16), (4, 12), (3, 7)])
 def test_bcube_bases(base, size):
     def fn(ctx):

@@ -323,3 +323,42 @@ def test_connect_timeouts():
     with pytest.raises(gb.IoError):
         c1.connect_full_mesh(stale, gb.create_device())
     assert time.time() - t0 < 10
+
+
+# ---- property tests -------------------------------------------------------------------------------
+
+try:
+    from hypothesis import given, settings
+    from hypothesis import strategies as st
+except ImportError:  # pragma: no cover - hypothesis is optional
+    given = None
+
+if given is not None:
+
+    @settings(max_examples=500, deadline=None)
+    @given(st.floats(width=32, allow_nan=False))
+    def test_half_conversion_property(v):
+        """float -> half is numpy's round-to-nearest-even for every finite or infinite float32,
+        and half -> float is exact."""
+        bits = _C.float_to_half_bits(float(v))
+        with np.errstate(over="ignore"):
+            want = np.float32(v).astype(np.float16)
+        assert bits == int(want.view(np.uint16))
+        assert _C.half_bits_to_float(bits) == float(want) or (np.isnan(want) and np.isnan(_C.half_bits_to_float(bits)))
+
+    @settings(max_examples=300, deadline=None)
+    @given(st.floats(width=32, allow_nan=False, allow_infinity=False))
+    def test_bfloat_conversion_property(v):
+        """float -> bfloat16 rounds to nearest even on the upper 16 bits (torch agrees)."""
+        import torch
+
+        want = torch.tensor([v], dtype=torch.float32).to(torch.bfloat16).view(torch.int16).item() & 0xFFFF
+        assert _C.float_to_bfloat_bits(float(v)) == want
+
+    @settings(max_examples=200, deadline=None)
+    @given(st.integers(1, 100000))
+    def test_factorize_property(n):
+        f = _C.factorize(n)
+        assert all(p >= 2 for p in f) and f == sorted(f)
+        assert int(np.prod(f, dtype=np.int64)) == n if f else n == 1
+        assert all(all(p % q for q in range(2, int(p ** 0.5) + 1)) for p in f)  # primes

@@ -72,3 +72,26 @@ def test_step_counts_match_cost_model():
     assert len(build("ring_chunked", 0, 8, 1 << 20, 2, 4)) == 14
     assert len(build("halving_doubling", 0, 8, 1 << 20, 2, 4)) == 6
     assert len(build("halving_doubling", 0, 6, 1 << 20, 2, 4)) == 4 + 2  # fold in/out around 4 ranks
+
+
+try:
+    from hypothesis import HealthCheck, given, settings
+    from hypothesis import strategies as st
+except ImportError:  # pragma: no cover - hypothesis is optional
+    given = None
+
+if given is not None:
+
+    @settings(max_examples=120, deadline=None, suppress_health_check=[HealthCheck.too_slow])
+    @given(name=st.sampled_from(["ring", "ring_chunked", "halving_doubling", "bcube"]),
+           size=st.integers(2, 16), count=st.integers(1, 3000), pack=st.sampled_from([1, 2, 4, 8, 16]))
+    def test_any_schedule_any_shape(name, size, count, pack):
+        """Random (algorithm, rank count, length, vector width): the table is race-free and
+        computes the allreduce, including lengths below the rank count and widths that do not
+        divide the length."""
+        simulate(name, size, count, pack=pack)
+
+    @settings(max_examples=60, deadline=None)
+    @given(base=st.integers(2, 5), size=st.integers(2, 16), count=st.integers(1, 2000))
+    def test_bcube_any_base(base, size, count):
+        simulate("bcube", size, count, base=base)

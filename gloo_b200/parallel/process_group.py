@@ -119,8 +119,12 @@ class GlbProcessGroup(dist.ProcessGroup):
 
         idx = tensor.device.index if tensor.device.index is not None else torch.cuda.current_device()
         if idx not in self._cuda:
+            # torch tensors are not registered with the peer context, so they travel through
+            # its staging pool: allreduce is cut into pool-sized pieces, the data-movement
+            # collectives need the whole payload to fit (GLB_PG_STAGE_MB, default 256).
+            stage = int(os.environ.get("GLB_PG_STAGE_MB", "256")) << 20
             with torch.cuda.device(idx):
-                self._cuda[idx] = gcu.CudaContext(self.ctx, idx)
+                self._cuda[idx] = gcu.CudaContext(self.ctx, idx, stage_bytes=stage)
         return self._cuda[idx]
 
     @staticmethod

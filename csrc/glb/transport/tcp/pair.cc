@@ -7,6 +7,7 @@
 #include <netinet/tcp.h>
 #include <poll.h>
 #include <sched.h>
+#include <sys/ioctl.h>
 #include <sys/socket.h>
 #include <sys/uio.h>
 #include <unistd.h>
@@ -268,6 +269,7 @@ void Pair::attachSocket(Socket sock, bool initiator) {
     caps.hdr.slot = static_cast<uint64_t>(::getpid());
     caps.hdr.aux = reinterpret_cast<uint64_t>(probeWord());
     caps.hdr.length = *probeWord();
+    caps.bestEffort = true;
     try {
       enqueue(std::move(caps));
     } catch (const std::exception& e) {
@@ -294,6 +296,16 @@ void Pair::close() {
     if (fd_ >= 0) {
       // Abortive close: no TIME_WAIT, so test suites that churn through thousands
       // of connections do not exhaust ephemeral ports (reference: pair.cc:79-92).
+      // An abortive close throws away what the kernel has not transmitted yet, and a
+      // rank may legitimately close right after its last send completed (= was handed
+      // to the kernel): give the queue a bounded moment to drain first.
+      if (!failed_ && state_ == CONNECTED) {
+        for (int i = 0; i < 2000; i++) {
+          int pending = 0;
+          if (::ioctl(fd_, TIOCOUTQ, &pending) != 0 || pending == 0) break;
+          ::usleep(500);
+        }
+      }
       struct linger sl = {1, 0};
       ::setsockopt(fd_, SOL_SOCKET, SO_LINGER, &sl, sizeof(sl));
       loop_->removeDescriptor(fd_);
@@ -582,6 +594,13 @@ bool Pair::tryWrite(TxOp& op) {
     }
     if (errno == EINTR) continue;
     if (errno == EAGAIN || errno == EWOULDBLOCK) return false;
+    if (op.bestEffort) {
+      // The peer finished and closed before this unsolicited frame went out. Whatever it
+      // sent is still in our receive queue and must stay deliverable; if more was expected
+      // from it, the read side reports the closed connection.
+      op.sent = total;
+      return true;
+    }
     signalException(strcat_all("send: ", std::strerror(errno), " (peer ", peer_.str(), ")"));
     return false;
   }
@@ -881,6 +900,7 @@ void Pair::beginMessage() {
         canPull_ = true;
         TxOp op;
         op.hdr.opcode = OP_CAPS_OK;
+        op.bestEffort = true;
         enqueue(std::move(op));
       } else {
         GLB_DEBUG("single-copy path to rank ", peerRank_, " unavailable (different host or no ptrace permission)");

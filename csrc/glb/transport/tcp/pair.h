@@ -194,6 +194,7 @@ class Pair : public ::glb::transport::Pair, private Handler {
     size_t sent = 0;
     bool hasUbuf = false;
     bool notify = true;
+    bool bestEffort = false;  // capability chatter: a peer that is already gone is not an error
     bool cma = false;  // header-only on the wire; completion on FIN
     uint64_t cmaId = 0;
     WeakAnchor<UnboundBuffer> ubuf;

@@ -158,3 +158,24 @@ def test_device_on_a_real_interface():
     [t.start() for t in ths]
     [t.join(60) for t in ths]
     assert out == [3.0, 3.0]
+
+
+def test_cpp_example_quick_collective_then_close():
+    """examples/example_reduce.cc: connect, one tiny reduce, closeConnections(), exit - ranks
+    finish at different times, so late protocol chatter (capability frames) and the abortive
+    close of a fast rank must not turn into errors on the slower ones."""
+    lib = os.path.join(ROOT, "gloo_b200", "lib")
+    if not os.path.exists(os.path.join(lib, "libglb.so")):
+        pytest.skip("libglb.so not built")
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    exe = os.path.join(tempfile.mkdtemp(prefix="glb_ex_"), "example_reduce")
+    subprocess.check_call([cxx, "-std=c++17", "-pthread", f"-I{os.path.join(ROOT, 'csrc')}",
+                           os.path.join(ROOT, "examples", "example_reduce.cc"), f"-L{lib}", "-lglb",
+                           f"-Wl,-rpath,{lib}", "-o", exe])
+    for _ in range(8):
+        d = tempfile.mkdtemp(prefix="glb_ex_rdv_")
+        procs = [subprocess.Popen([exe, str(r), "3", d], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True)
+                 for r in range(3)]
+        outs = [p.communicate(timeout=60) for p in procs]
+        assert [p.returncode for p in procs] == [0, 0, 0], outs
+        assert "sum = 6" in outs[0][0]

@@ -266,7 +266,35 @@ void registerTyped(std::map<std::string, BenchmarkFactory>& r, bool half) {
   add("allreduce_halving_doubling",
       [](auto c, const Options& o) { return hostAllreduce<T, AllreduceHalvingDoubling<T>>(c, o); });
   add("allreduce_bcube", [](auto c, const Options& o) { return hostAllreduce<T, AllreduceBcube<T>>(c, o); });
-  add("allreduce_local", [](auto c, const Options& o) { return hostAllreduce<T, AllreduceLocal<T>>(c, o); });
+  add("allreduce_local", [](auto c, const Options& o) {
+    // Reduces this rank's own buffers only (no communication), so the expected value is
+    // the sum over the local inputs, whatever the context size.
+    auto data = std::make_shared<HostData<T>>();
+    auto algo = std::make_shared<std::unique_ptr<Algorithm>>();
+    auto count = std::make_shared<size_t>(0);
+    const int inputs = o.inputs;
+    Benchmark b;
+    b.elementSize = sizeof(T);
+    b.busFactor = 0.0;
+    b.initialize = [=](size_t n) {
+      *count = n;
+      data->fill(c->rank, c->size, inputs, n);
+      algo->reset(new AllreduceLocal<T>(c, data->ptrs, n));
+    };
+    b.run = [=] { (*algo)->run(); };
+    b.verify = [=] {
+      const double stride = static_cast<double>(c->size) * inputs;
+      for (auto* p : data->ptrs) {
+        for (size_t j = 0; j < std::min<size_t>(*count, 1 << 16); j++) {
+          const double exp = inputs * (j * stride + c->rank * inputs) + inputs * (inputs - 1) / 2.0;
+          const double got = static_cast<double>(static_cast<float>(p[j]));
+          const double tol = (sizeof(T) == 2 ? 1e-2 : 1e-5) * std::max(1.0, exp);
+          GLB_ENFORCE(std::abs(got - exp) <= tol, "Mismatch at index ", j, ": got ", got, " expected ", exp);
+        }
+      }
+    };
+    return b;
+  });
   add("new_allreduce_ring", [](auto c, const Options& o) { return newAllreduce<T>(c, o, AllreduceOptions::RING); });
   add("new_allreduce_bcube", [](auto c, const Options& o) { return newAllreduce<T>(c, o, AllreduceOptions::BCUBE); });
 

@@ -179,3 +179,20 @@ def test_cpp_example_quick_collective_then_close():
         outs = [p.communicate(timeout=60) for p in procs]
         assert [p.returncode for p in procs] == [0, 0, 0], outs
         assert "sum = 6" in outs[0][0]
+
+
+@pytest.mark.skipif(not os.path.exists(BENCH), reason="benchmark binary not built")
+def test_every_host_benchmark_name_runs_and_verifies():
+    """Each benchmark the CLI lists (the reference's names plus the new-style additions) runs on
+    two ranks with result verification on; cuda_* names need a GPU and are covered by -m gpu."""
+    res = subprocess.run([BENCH, "--help"], capture_output=True, text=True)
+    listing = res.stdout + res.stderr
+    names = [l.strip() for l in listing.split("BENCHMARK is one of:")[1].splitlines() if l.strip()]
+    host = [n for n in names if not n.startswith("cuda_")]
+    assert len(host) >= 25, names
+    bad = []
+    for n in host:
+        codes, outs = run_bench(2, "--elements", "500", "--iteration-count", "3", "--inputs", "2", n, timeout=60)
+        if codes != [0, 0]:
+            bad.append((n, codes, outs[0][-300:]))
+    assert not bad, bad

@@ -63,6 +63,7 @@ void checkAllreduce(const std::vector<T*>& ptrs, size_t n, int size, int inputs)
   for (auto* p : ptrs) {
     for (size_t j = 0; j < limit; j++) {
       const double exp = j * stride * stride + stride * (stride - 1) / 2;
+      if (sizeof(T) == 2 && exp > 60000.0) break;  // beyond the range of a 16-bit float: nothing to compare
       const double got = static_cast<double>(static_cast<float>(p[j]));
       const double tol = sizeof(T) == 2 ? 1e-2 * std::max(1.0, exp) : 1e-5 * std::max(1.0, exp);
       GLB_ENFORCE(std::abs(got - exp) <= tol, "Mismatch at index ", j, ": got ", got, " expected ", exp);

@@ -1,0 +1,91 @@
+"""Back-to-back random collectives on one context: every rank draws the same sequence
+(shared seed) of operations, sizes and roots and checks each result against numpy. Catches
+cross-talk between consecutive collectives (slot reuse, leftovers in the unexpected queue,
+messages parked for the single-copy path, acknowledgements arriving late)."""
+import numpy as np
+import pytest
+
+import gloo_b200 as gb
+
+SIZES = [0, 1, 3, 17, 1000, 4099, 70_001, 300_000]
+
+
+def _contrib(rank, n, salt):
+    return (np.arange(n, dtype=np.float64) % 251) * (salt % 7 + 1) + rank * 3 + salt
+
+
+@pytest.mark.parametrize("size,seed", [(2, 0), (3, 1), (4, 2), (5, 3), (8, 4)])
+def test_random_collective_sequences(size, seed):
+    steps = 60 if size <= 4 else 30
+
+    def fn(ctx):
+        rng = np.random.RandomState(seed)  # same stream on every rank
+        r = ctx.rank
+        for step in range(steps):
+            op = rng.choice(["allreduce", "allreduce_oop", "bcube", "broadcast", "allgather", "alltoall",
+                             "reduce_scatter", "reduce", "gather", "scatter", "barrier", "alltoallv"])
+            n = int(rng.choice(SIZES if size <= 4 else SIZES[:-1]))
+            root = int(rng.randint(size))
+            salt = int(rng.randint(1000))
+            total = sum(_contrib(q, n, salt) for q in range(size))
+            if op in ("allreduce", "bcube"):
+                x = _contrib(r, n, salt)
+                gb.allreduce(ctx, x, algorithm=gb.Algorithm.BCUBE if op == "bcube" else gb.Algorithm.RING)
+                np.testing.assert_allclose(x, total, err_msg=f"step {step} {op} n={n}")
+            elif op == "allreduce_oop":
+                x, out = _contrib(r, n, salt), np.full(n, -1.0)
+                gb.allreduce(ctx, out, inputs=x)
+                np.testing.assert_allclose(out, total, err_msg=f"step {step} {op} n={n}")
+                np.testing.assert_array_equal(x, _contrib(r, n, salt))
+            elif op == "broadcast":
+                x = _contrib(root, n, salt) if r == root else np.zeros(n)
+                gb.broadcast(ctx, x, root=root)
+                np.testing.assert_array_equal(x, _contrib(root, n, salt))
+            elif op == "allgather":
+                n = min(n, 70_001)
+                out = np.zeros(n * size)
+                gb.allgather(ctx, out, _contrib(r, n, salt))
+                np.testing.assert_array_equal(out, np.concatenate([_contrib(q, n, salt) for q in range(size)]))
+            elif op == "alltoall":
+                n = min(n, 70_001)
+                inp = np.concatenate([_contrib(r, n, salt) + 1000 * q for q in range(size)]) if n else np.zeros(0)
+                out = np.zeros(n * size)
+                gb.alltoall(ctx, out, inp)
+                want = np.concatenate([_contrib(q, n, salt) + 1000 * r for q in range(size)]) if n else np.zeros(0)
+                np.testing.assert_array_equal(out, want)
+            elif op == "alltoallv":
+                counts = [[int((a * 7 + b * 3 + salt) % 5) * (n // 50 + 1) for b in range(size)] for a in range(size)]
+                inp = np.concatenate([np.full(counts[r][q], r * 100 + q, np.float64) for q in range(size)])
+                rc = [counts[q][r] for q in range(size)]
+                out = np.zeros(sum(rc))
+                gb.alltoallv(ctx, out, rc, inp, counts[r])
+                want = np.concatenate([np.full(counts[q][r], q * 100 + r, np.float64) for q in range(size)])
+                np.testing.assert_array_equal(out, want)
+            elif op == "reduce_scatter":
+                counts = [n // size + (1 if q < n % size else 0) for q in range(size)]
+                out = np.zeros(counts[r])
+                gb.reduce_scatter(ctx, out, _contrib(r, n, salt), recv_counts=counts)
+                off = sum(counts[:r])
+                np.testing.assert_allclose(out, total[off:off + counts[r]])
+            elif op == "reduce":
+                out = np.zeros(n)
+                gb.reduce(ctx, out, _contrib(r, n, salt), root=root)
+                if r == root:
+                    np.testing.assert_allclose(out, total)
+            elif op == "gather":
+                n = min(n, 70_001)
+                out = np.zeros(n * size) if r == root else None
+                gb.gather(ctx, _contrib(r, n, salt), out, root=root)
+                if r == root:
+                    np.testing.assert_array_equal(out, np.concatenate([_contrib(q, n, salt) for q in range(size)]))
+            elif op == "scatter":
+                n = min(n, 70_001)
+                out = np.zeros(n)
+                parts = [_contrib(q, n, salt) for q in range(size)] if r == root else None
+                gb.scatter(ctx, out, parts, root=root)
+                np.testing.assert_array_equal(out, _contrib(r, n, salt))
+            else:
+                gb.barrier(ctx)
+        return True
+
+    assert all(gb.spawn_threads(size, fn, timeout_ms=60000))

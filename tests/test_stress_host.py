@@ -89,3 +89,45 @@ def test_random_collective_sequences(size, seed):
         return True
 
     assert all(gb.spawn_threads(size, fn, timeout_ms=60000))
+
+
+@pytest.mark.parametrize("size,seed", [(2, 11), (3, 12), (4, 13), (7, 14)])
+def test_interleaved_algorithm_instances(size, seed):
+    """Several old-style algorithm instances alive on one context (each owns its slots and
+    bound buffers), run in a random interleaving with fresh data every time - including the
+    reduce-scatter-only hypercube, whose flow control is per (step, peer) credit."""
+    from gloo_b200.ops import algorithms as alg
+
+    def fn(ctx):
+        rng = np.random.RandomState(seed)
+        classes = [alg.AllreduceRing, alg.AllreduceRingChunked, alg.AllreduceHalvingDoubling, alg.AllreduceBcube]
+        insts = []
+        for _ in range(6):
+            cls = classes[rng.randint(4)]
+            n = int(rng.choice([1, 5, 1000, 4099, 200000]))
+            buf = np.zeros(n)
+            insts.append((cls(ctx, [buf]), buf, n))
+        rs_n = int(rng.choice([size, 1000, 30000]))
+        counts = [rs_n // size + (1 if q < rs_n % size else 0) for q in range(size)]
+        rsbuf = np.zeros(rs_n)
+        rs = alg.ReduceScatterHalvingDoubling(ctx, [rsbuf], counts)
+        bar = alg.BarrierAllToAll(ctx)
+        for _ in range(40):
+            k = rng.randint(len(insts) + 2)
+            salt = int(rng.randint(100))
+            if k == len(insts):
+                rsbuf[:] = np.arange(rs_n) + ctx.rank + salt
+                rs.run()
+                off = sum(counts[:ctx.rank])
+                want = (np.arange(rs_n) + salt) * size + size * (size - 1) / 2
+                np.testing.assert_allclose(rsbuf[:counts[ctx.rank]], want[off:off + counts[ctx.rank]])
+            elif k == len(insts) + 1:
+                bar.run()
+            else:
+                a, buf, n = insts[k]
+                buf[:] = np.arange(n) % 97 + ctx.rank * 2 + salt
+                a.run()
+                np.testing.assert_allclose(buf, (np.arange(n) % 97 + salt) * size + size * (size - 1))
+        return True
+
+    assert all(gb.spawn_threads(size, fn, timeout_ms=60000))

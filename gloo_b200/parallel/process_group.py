@@ -72,6 +72,29 @@ def _done(result=None):
     return _create_work_from_future(fut)
 
 
+class _RecvWork(dist.Work):
+    """Completed work of a receive; carries the sender's rank for recv-from-any."""
+
+    def __init__(self, src: int):
+        super().__init__()
+        self._src = src
+
+    def wait(self, timeout=None):
+        return True
+
+    def is_completed(self):
+        return True
+
+    def is_success(self):
+        return True
+
+    def source_rank(self):
+        return self._src
+
+    def _source_rank(self):
+        return self._src
+
+
 def _op(reduce_op) -> ReduceOp:
     R = dist.ReduceOp
     for theirs, ours in ((R.SUM, ReduceOp.SUM), (R.AVG, ReduceOp.SUM), (R.PRODUCT, ReduceOp.PRODUCT),
@@ -336,7 +359,7 @@ class GlbProcessGroup(dist.ProcessGroup):
             src = buf.wait_recv()
             if h is not t:
                 t.copy_(h)
-        return _done(src)
+        return _RecvWork(src)
 
     def shutdown(self):
         try:

@@ -89,6 +89,18 @@ def main():
         [r.wait() for r in reqs]
         assert got[0] == left
 
+    if size > 1:  # recv without a source: whoever sends first
+        if rank == 0:
+            seen = set()
+            for _ in range(size - 1):
+                buf = torch.zeros(2)
+                src = dist.recv(buf, tag=9)
+                assert int(buf[0]) == src
+                seen.add(src)
+            assert seen == set(range(1, size))
+        else:
+            dist.send(torch.full((2,), float(rank)), dst=0, tag=9)
+
     # object collectives ride on byte / long tensors
     objs = [None] * size
     dist.all_gather_object(objs, {"rank": rank, "name": "r" * (rank + 1)})

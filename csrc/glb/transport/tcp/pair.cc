@@ -287,7 +287,7 @@ bool Pair::isConnected() {
 void Pair::close() {
   int fd = -1;
   {
-    std::lock_guard<std::mutex> g(mu_);
+    std::unique_lock<std::mutex> g(mu_);
     if (expecting_) {
       device_->cancelExpectation(self_.seq());
       expecting_ = false;
@@ -300,12 +300,16 @@ void Pair::close() {
       // rank may legitimately close right after its last send completed (= was handed
       // to the kernel): give the queue a bounded moment to drain first.
       if (!failed_ && state_ == CONNECTED) {
-        for (int i = 0; i < 2000; i++) {
+        for (int i = 0; i < 2000 && !failed_ && state_ == CONNECTED && fd_ >= 0; i++) {
           int pending = 0;
           if (::ioctl(fd_, TIOCOUTQ, &pending) != 0 || pending == 0) break;
+          g.unlock();  // the loop thread may still have to read from this pair meanwhile
           ::usleep(500);
+          g.lock();
         }
       }
+    }
+    if (fd_ >= 0) {
       struct linger sl = {1, 0};
       ::setsockopt(fd_, SOL_SOCKET, SO_LINGER, &sl, sizeof(sl));
       loop_->removeDescriptor(fd_);

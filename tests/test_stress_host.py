@@ -131,3 +131,27 @@ def test_interleaved_algorithm_instances(size, seed):
         return True
 
     assert all(gb.spawn_threads(size, fn, timeout_ms=60000))
+
+
+@pytest.mark.parametrize("variant", ["lazy", "shared_device", "sync", "busy_poll"])
+def test_random_sequences_on_other_device_modes(variant, monkeypatch):
+    """The same random sequences over lazily connected pairs, one device shared by all ranks,
+    and pairs in blocking / busy-polling sync mode (where unbound waits drive the sockets)."""
+    orig = gb.spawn_threads
+
+    def spawn(n, fn, **kw):
+        if variant in ("lazy", "shared_device"):
+            kw[variant] = True
+            return orig(n, fn, **kw)
+
+        def wrapped(ctx):
+            for q in range(n):
+                if q != ctx.rank:
+                    ctx.get_pair(q).set_sync(True, variant == "busy_poll")
+            return fn(ctx)
+
+        return orig(n, wrapped, **kw)
+
+    monkeypatch.setattr(gb, "spawn_threads", spawn)
+    for size, seed in ((2, 21), (3, 22), (4, 23)):
+        test_random_collective_sequences(size, seed)

@@ -71,6 +71,25 @@ def main():
                 u.recv(0, 77)
                 u.wait_recv()
                 print("unexpectedly received", file=sys.stderr)
+        elif mode == "stress_loop":
+            # endless random collectives (same sequence on every rank) until a peer dies
+            rng = np.random.RandomState(int(args[0]) if args else 0)
+            deadline = time.time() + 60
+            while time.time() < deadline:
+                op = rng.choice(["allreduce", "allgather", "alltoall", "broadcast", "reduce_scatter", "barrier"])
+                n = int(rng.choice([1, 1000, 70_000, 400_000]))
+                if op == "allreduce":
+                    gb.allreduce(ctx, np.ones(n, np.float32))
+                elif op == "allgather":
+                    gb.allgather(ctx, np.zeros(n * size, np.float32), np.ones(n, np.float32))
+                elif op == "alltoall":
+                    gb.alltoall(ctx, np.zeros(n * size, np.float32), np.ones(n * size, np.float32))
+                elif op == "broadcast":
+                    gb.broadcast(ctx, np.ones(n, np.float32), root=int(rng.randint(size)))
+                elif op == "reduce_scatter":
+                    gb.reduce_scatter(ctx, np.zeros(n, np.float32), np.ones(n * size, np.float32))
+                else:
+                    gb.barrier(ctx)
         elif mode == "sendrecv_loop":
             peer = (rank + 1) % size
             src = (rank - 1) % size

@@ -133,3 +133,24 @@ def test_sigstop_hits_timeout(size):
     assert elapsed >= timeout_ms / 1000 * 0.5
     errs = " ".join(p.stderr.read() for p in procs[1:])
     assert "Timed out" in errs or "timeout" in errs.lower() or "closed" in errs.lower()
+
+
+@pytest.mark.parametrize("seed,size,sync", [(1, 3, "0"), (2, 4, "0"), (3, 3, "1"), (4, 2, "2")])
+def test_kill_during_random_collectives(seed, size, sync):
+    """A rank dies at an arbitrary moment while all ranks run a random mix of collectives,
+    small and large (eager, single-copy, parked messages, acknowledgements in flight): every
+    survivor must come back with IoError promptly - no hang, no crash."""
+    import random
+
+    rnd = random.Random(seed)
+    d, procs = launch(size, "stress_loop", seed, timeout_ms=3000, extra_env={"GLB_TEST_SYNC": sync})
+    wait_ready(d, size)
+    time.sleep(rnd.uniform(0.05, 0.5))
+    victim = rnd.randrange(size)
+    t0 = time.time()
+    procs[victim].send_signal(signal.SIGKILL)
+    codes = reap(procs, 20)
+    assert codes[victim] == -signal.SIGKILL
+    survivors = [c for i, c in enumerate(codes) if i != victim]
+    assert all(c == 10 for c in survivors), (codes, [p.stderr.read()[-300:] for i, p in enumerate(procs) if i != victim])
+    assert time.time() - t0 < 12

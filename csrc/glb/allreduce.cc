@@ -1,6 +1,8 @@
 #include "glb/allreduce.h"
 
 #include <algorithm>
+#include <cstdlib>
+#include <cstring>
 
 #include "glb/common/utils.h"
 
@@ -280,6 +282,42 @@ void bcube(const AllreduceOptions& opts, UnboundBuffer* out0, UnboundBuffer* src
   }
 }
 
+// Latency path for small vectors (UNSPECIFIED only): every rank sends its whole contribution
+// to every other rank and reduces the P vectors locally, in rank order so that all ranks
+// produce bit-identical results. One message hop instead of the ring's 2(P-1); the same
+// idea as the CUDA one-shot kernel. Traffic is (P-1) x S per rank, hence the size limit.
+void oneShot(const AllreduceOptions& opts, UnboundBuffer* out0, UnboundBuffer* src) {
+  const auto& context = opts.context;
+  const int P = context->size;
+  const int r = context->rank;
+  const size_t bytes = opts.elements * opts.elementSize;
+  const auto slot = Slot::build(kAllreduceSlotPrefix, opts.tag);
+  // Landing zones for the peers' vectors plus a private copy of this rank's own one (the
+  // accumulator may be the very buffer it lives in).
+  std::vector<char> tmpStorage(static_cast<size_t>(P) * bytes);
+  auto tmp = context->createUnboundBuffer(tmpStorage.data(), tmpStorage.size());
+  for (int q = 0; q < P; q++) {
+    if (q != r) tmp->recv(q, slot, static_cast<size_t>(q) * bytes, bytes);
+  }
+  for (int k = 1; k < P; k++) src->send((r + k) % P, slot, 0, bytes);  // staggered fan-out
+  std::memcpy(tmpStorage.data() + static_cast<size_t>(r) * bytes, src->ptr, bytes);
+  for (int q = 1; q < P; q++) tmp->waitRecv(opts.timeout);
+  char* out = static_cast<char*>(out0->ptr);
+  opts.reduce(out, tmpStorage.data(), tmpStorage.data() + bytes, opts.elements);
+  for (int q = 2; q < P; q++) opts.reduce(out, out, tmpStorage.data() + static_cast<size_t>(q) * bytes, opts.elements);
+  for (int q = 1; q < P; q++) src->waitSend(opts.timeout);
+}
+
+size_t oneShotMaxBytes() {
+  static const size_t n = [] {
+    const char* v = std::getenv("GLB_ALLREDUCE_ONESHOT_MAX");
+    if (v == nullptr) v = std::getenv("GLOO_ALLREDUCE_ONESHOT_MAX");
+    long long b = v != nullptr ? std::atoll(v) : (16 << 10);
+    return static_cast<size_t>(b < 0 ? 0 : b);
+  }();
+  return n;
+}
+
 }  // namespace
 
 void allreduce(const AllreduceOptions& opts) {
@@ -313,6 +351,12 @@ void allreduce(const AllreduceOptions& opts) {
   if (context->size > 1) {
     switch (opts.algorithm) {
       case AllreduceOptions::UNSPECIFIED:
+        if (bytes <= oneShotMaxBytes() && context->size <= 64) {
+          oneShot(opts, out0, src);
+          break;
+        }
+        ring(opts, out0, src);
+        break;
       case AllreduceOptions::RING:
         ring(opts, out0, src);
         break;

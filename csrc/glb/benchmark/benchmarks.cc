@@ -296,6 +296,7 @@ void registerTyped(std::map<std::string, BenchmarkFactory>& r, bool half) {
     };
     return b;
   });
+  add("new_allreduce", [](auto c, const Options& o) { return newAllreduce<T>(c, o, AllreduceOptions::UNSPECIFIED); });
   add("new_allreduce_ring", [](auto c, const Options& o) { return newAllreduce<T>(c, o, AllreduceOptions::RING); });
   add("new_allreduce_bcube", [](auto c, const Options& o) { return newAllreduce<T>(c, o, AllreduceOptions::BCUBE); });
 

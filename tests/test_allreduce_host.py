@@ -53,6 +53,36 @@ def test_allreduce_many_segments(algo):
     assert all(gb.spawn_threads(size, fn))
 
 
+@pytest.mark.parametrize("size", [2, 3, 4, 7])
+def test_default_algorithm_small_vectors_one_hop(size):
+    """Without an explicit algorithm, vectors up to GLB_ALLREDUCE_ONESHOT_MAX (16 KiB) take the
+    one-hop exchange: every rank reduces all contributions in rank order, so the results are
+    bit-identical everywhere even for sums that are not associative in floating point."""
+    def fn(ctx):
+        rng = np.random.RandomState(1234 + ctx.rank)
+        got = []
+        for count in (1, 3, 257, 4096):
+            for ptrs in (1, 2):
+                bufs = [(rng.randn(count) * 10 ** rng.randint(-3, 4)).astype(np.float32) for _ in range(ptrs)]
+                mine = np.sum(np.stack(bufs).astype(np.float64), axis=0)
+                out = np.zeros(count, np.float32)
+                gb.allreduce(ctx, out, inputs=bufs if ptrs > 1 else bufs[0])
+                ref = np.zeros(count, np.float64)
+                ref[:] = mine
+                gb.allreduce(ctx, ref, algorithm=gb.Algorithm.RING)  # fp64 reference over the ring
+                np.testing.assert_allclose(out, ref, rtol=2e-4, atol=1e-2)  # float32 accumulation
+                inplace = bufs[0].copy()
+                gb.allreduce(ctx, inplace)
+                got.append(out.tobytes())
+                got.append(inplace.tobytes())
+        return got
+
+    res = gb.spawn_threads(size, fn)
+    for r in range(1, size):
+        for a, b in zip(res[0][::2], res[r][::2]):
+            assert a == b, "ranks disagree bitwise"
+
+
 @pytest.mark.parametrize("size", [2, 3, 5])
 @pytest.mark.parametrize("max_segment", [None, 128, 4096])
 def test_ring_streams_segments_and_leaves_the_input_alone(size, max_segment):

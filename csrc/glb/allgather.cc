@@ -18,6 +18,19 @@ void allgather(AllgatherOptions& opts) {
   }
   if (P == 1 || block == 0) return;
 
+  // Small blocks: one hop, everyone sends its block to everyone (P-1 tiny messages each)
+  // instead of P-1 dependent ring steps.
+  if (block <= 16384 && P <= 32) {
+    for (int k = 1; k < P; k++) {
+      const int q = (r - k + P) % P;
+      out->recv(q, slot, static_cast<size_t>(q) * block, block);
+    }
+    for (int k = 1; k < P; k++) out->send((r + k) % P, slot, static_cast<size_t>(r) * block, block);
+    for (int k = 1; k < P; k++) out->waitRecv(opts.timeout);
+    for (int k = 1; k < P; k++) out->waitSend(opts.timeout);
+    return;
+  }
+
   const int right = (r + 1) % P;
   const int left = (r - 1 + P) % P;
   // Two half-blocks per step keep the pipe full: while half A of step s is still

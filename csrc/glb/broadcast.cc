@@ -20,6 +20,19 @@ void broadcast(BroadcastOptions& opts) {
   }
   if (P == 1) return;
 
+  // Small payloads: the root sends to everyone itself. P-1 back-to-back writes cost a few
+  // microseconds; every level of the tree costs a full message hop.
+  if (out->size <= 16384 && P <= 32) {
+    if (r == opts.root) {
+      for (int k = 1; k < P; k++) out->send((r + k) % P, slot, 0, out->size);
+      for (int k = 1; k < P; k++) out->waitSend(opts.timeout);
+    } else {
+      out->recv(opts.root, slot, 0, out->size);
+      out->waitRecv(opts.timeout);
+    }
+    return;
+  }
+
   const int vrank = (r - opts.root + P) % P;
   // Parent: clear the lowest set bit of vrank. Children: vrank + 2^k for 2^k below that bit.
   int lowbit = 1;

@@ -1,5 +1,8 @@
 #include "glb/reduce.h"
 
+#include <cstring>
+#include <vector>
+
 namespace glb {
 
 void reduce(ReduceOptions& opts) {
@@ -13,12 +16,33 @@ void reduce(ReduceOptions& opts) {
   GLB_ENFORCE_EQ(out->size, bytes, "reduce: output size mismatch");
   if (opts.in) GLB_ENFORCE_EQ(opts.in->size, bytes, "reduce: input size mismatch");
   if (opts.elements == 0) return;
-  if (opts.in && opts.in->ptr != out->ptr) std::memcpy(out->ptr, opts.in->ptr, bytes);
   const int P = context->size;
   const int r = context->rank;
+  const auto slot = Slot::build(kReduceSlotPrefix, opts.tag);
+  // Small vectors: everyone sends straight to the root, which folds the contributions in
+  // rank order - one hop instead of a ring reduce-scatter plus a gather.
+  if (P > 1 && bytes <= 16384 && P <= 64) {
+    UnboundBuffer* src = opts.in ? opts.in.get() : out;
+    if (r != opts.root) {
+      src->send(opts.root, slot, 0, bytes);
+      src->waitSend(opts.timeout);
+      return;
+    }
+    std::vector<char> tmpStorage(static_cast<size_t>(P) * bytes);
+    auto tmp = context->createUnboundBuffer(tmpStorage.data(), tmpStorage.size());
+    for (int q = 0; q < P; q++) {
+      if (q != r) tmp->recv(q, slot, static_cast<size_t>(q) * bytes, bytes);
+    }
+    std::memcpy(tmpStorage.data() + static_cast<size_t>(r) * bytes, src->ptr, bytes);
+    for (int q = 1; q < P; q++) tmp->waitRecv(opts.timeout);
+    char* o = static_cast<char*>(out->ptr);
+    opts.reduce(o, tmpStorage.data(), tmpStorage.data() + bytes, opts.elements);
+    for (int q = 2; q < P; q++) opts.reduce(o, o, tmpStorage.data() + static_cast<size_t>(q) * bytes, opts.elements);
+    return;
+  }
+  if (opts.in && opts.in->ptr != out->ptr) std::memcpy(out->ptr, opts.in->ptr, bytes);
   if (P == 1) return;
 
-  const auto slot = Slot::build(kReduceSlotPrefix, opts.tag);
   detail::ringReduceScatter(context, out, opts.elements, opts.elementSize, opts.reduce, opts.maxSegmentSize,
                             slot, opts.timeout);
   // Rank i now owns the reduced chunk (i + 1) % P; ship it to the root.

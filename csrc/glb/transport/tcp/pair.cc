@@ -139,24 +139,25 @@ void Pair::connect(const std::vector<char>& bytes) {
   if (selfRank_ < peerRank_) {
     device_->expectConnection(self_.seq(), [this](Socket s) { attachSocket(std::move(s), false); });
   }
-  if (!lazy_) ensureConnected();
+  if (!lazy_) ensureConnected(/*setup=*/true);
 }
 
-void Pair::ensureConnected() {
+void Pair::ensureConnected(bool setup) {
   {
     std::unique_lock<std::mutex> lock(mu_);
     if (state_ == CONNECTED) return;
+    if (setup && everConnected_ && closedByPeer_) return;
     throwIfException();
     GLB_ENFORCE(havePeer_, "pair to rank ", peerRank_, " has no peer address (connect() not called)");
     if (selfRank_ < peerRank_) {
-      waitUntilConnected(lock);
+      waitUntilConnected(lock, setup);
       return;
     }
   }
   dial();
 }
 
-void Pair::waitUntilConnected(std::unique_lock<std::mutex>& lock) {
+void Pair::waitUntilConnected(std::unique_lock<std::mutex>& lock, bool setup) {
   auto pred = [&] { return state_ == CONNECTED || state_ == CLOSED; };
   if (timeout_ == kNoTimeout) {
     cv_.wait(lock, pred);
@@ -167,6 +168,7 @@ void Pair::waitUntilConnected(std::unique_lock<std::mutex>& lock) {
       signalException(strcat_all("Connect timeout waiting for rank ", peerRank_, " to dial ", self_.str()));
     }
   }
+  if (setup && everConnected_ && closedByPeer_) return;
   throwIfException();
 }
 
@@ -262,6 +264,7 @@ void Pair::attachSocket(Socket sock, bool initiator) {
     return;
   }
   state_ = CONNECTED;
+  everConnected_ = true;
   if (!sync_) armEvents(false);
   if (cmaEnabled() && allowCma()) {
     TxOp caps;
@@ -667,6 +670,7 @@ void Pair::readLoop(size_t budget) {
         beginMessage();
         if (state_ != CONNECTED) return;
       } else if (n == 0) {
+        closedByPeer_ = rx_.hdrRead == 0;
         signalException(strcat_all("Connection closed by peer [", peer_.str(), "]"));
         return;
       } else if (errno == EINTR) {
@@ -674,6 +678,7 @@ void Pair::readLoop(size_t budget) {
       } else if (errno == EAGAIN || errno == EWOULDBLOCK) {
         return;
       } else {
+        closedByPeer_ = errno == ECONNRESET && rx_.hdrRead == 0;
         signalException(strcat_all("recv: ", std::strerror(errno), " (peer ", peer_.str(), ")"));
         return;
       }

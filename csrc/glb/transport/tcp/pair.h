@@ -119,7 +119,9 @@ class Pair : public ::glb::transport::Pair, private Handler {
   bool isBusyPoll() const { return busyPoll_; }
 
   // Dial / wait for the inbound connection if that has not happened yet (lazy mode).
-  void ensureConnected();
+  // `setup`: called while the mesh is being built - a peer that connected and has already
+  // finished and closed again (it was quick, we were slow) is not a failure of the setup.
+  void ensureConnected(bool setup = false);
 
   // ---- used by Buffer / UnboundBuffer / Context -------------------------------
   void sendBound(Buffer* buf, size_t offset, size_t length, size_t roffset);
@@ -242,7 +244,7 @@ class Pair : public ::glb::transport::Pair, private Handler {
 
   void dial();                                     // initiator side
   void attachSocket(Socket sock, bool initiator);  // both sides
-  void waitUntilConnected(std::unique_lock<std::mutex>& lock);
+  void waitUntilConnected(std::unique_lock<std::mutex>& lock, bool setup);
 
   void enqueue(TxOp&& op);      // requires mu_
   bool tryWrite(TxOp& op);      // requires mu_; true when fully written
@@ -282,6 +284,8 @@ class Pair : public ::glb::transport::Pair, private Handler {
   bool havePeer_ = false;
   std::string exMsg_;
   bool failed_ = false;
+  bool everConnected_ = false;  // reached CONNECTED at some point
+  bool closedByPeer_ = false;   // the failure is the peer's orderly (or abortive) close
 
   std::deque<TxOp> tx_;
   std::deque<TxOp> awaitingFin_;  // CMA sends written to the wire, completed by FIN(id)

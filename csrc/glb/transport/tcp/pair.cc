@@ -97,9 +97,11 @@ Pair::Pair(Context* context, Device* device, int selfRank, int peerRank, std::ch
   self_ = device_->nextAddress();
 }
 
-Pair::~Pair() {
+void Pair::quiesce() {
   {
     std::unique_lock<std::mutex> lock(mu_);
+    if (quiesced_) return;
+    quiesced_ = true;
     if (expecting_) {
       device_->cancelExpectation(self_.seq());
       expecting_ = false;
@@ -114,6 +116,11 @@ Pair::~Pair() {
     if (fd_ >= 0) loop_->removeDescriptor(fd_);
   }
   loop_->barrier();  // the loop may still be about to call handleEvents on us
+  std::lock_guard<std::mutex> lock(mu_);  // ... or be inside it right now
+}
+
+Pair::~Pair() {
+  quiesce();
   std::lock_guard<std::mutex> lock(mu_);
   if (fd_ >= 0) {
     ioShutdown();

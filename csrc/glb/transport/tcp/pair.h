@@ -187,6 +187,10 @@ class Pair : public ::glb::transport::Pair, private Handler {
   virtual bool allowCma() const { return true; }
 
   int fd() const { return fd_; }
+  // Detach from the loop thread and wait until it can no longer be inside this pair.
+  // Subclasses that own state the I/O hooks use (the TLS session) call this first thing in
+  // their destructor - the base destructor would only get to it after they are gone.
+  void quiesce();
 
  private:
   struct TxOp {
@@ -284,6 +288,7 @@ class Pair : public ::glb::transport::Pair, private Handler {
   bool havePeer_ = false;
   std::string exMsg_;
   bool failed_ = false;
+  bool quiesced_ = false;
   bool everConnected_ = false;  // reached CONNECTED at some point
   bool closedByPeer_ = false;   // the failure is the peer's orderly (or abortive) close
 

@@ -84,7 +84,11 @@ Pair::Pair(::glb::transport::tcp::Context* context, Device* device, int selfRank
     : ::glb::transport::tcp::Pair(context, device, selfRank, peerRank, timeout, lazy), tlsDevice_(device) {}
 
 Pair::~Pair() {
+  // The loop thread may be inside SSL_read on this session right now; the base class only
+  // detaches from it in its own destructor, i.e. after this one.
+  quiesce();
   if (ssl_ != nullptr) {
+    if (fd() >= 0) openssl().SSL_shutdown(ssl_);  // close_notify, best effort (the base closes the fd)
     openssl().SSL_free(ssl_);
     ssl_ = nullptr;
   }

@@ -20,7 +20,7 @@ void allgather(AllgatherOptions& opts) {
 
   // Small blocks: one hop, everyone sends its block to everyone (P-1 tiny messages each)
   // instead of P-1 dependent ring steps.
-  if (block <= 16384 && P <= 32) {
+  if (block <= detail::oneHopMaxBytes() && P <= 32) {
     for (int k = 1; k < P; k++) {
       const int q = (r - k + P) % P;
       out->recv(q, slot, static_cast<size_t>(q) * block, block);

@@ -27,6 +27,16 @@ void AllreduceOptions::setOutputsRaw(const std::vector<void*>& ptrs, size_t n, s
 
 namespace detail {
 
+size_t oneHopMaxBytes() {
+  static const size_t n = [] {
+    const char* v = std::getenv("GLB_ONEHOP_MAX");
+    if (v == nullptr) v = std::getenv("GLB_ALLREDUCE_ONESHOT_MAX");
+    long long b = v != nullptr ? std::atoll(v) : (16 << 10);
+    return static_cast<size_t>(b < 0 ? 0 : b);
+  }();
+  return n;
+}
+
 std::vector<int> factorize(int n) {
   std::vector<int> f;
   for (int p = 2; p * p <= n; p++) {
@@ -308,16 +318,6 @@ void oneShot(const AllreduceOptions& opts, UnboundBuffer* out0, UnboundBuffer* s
   for (int q = 1; q < P; q++) src->waitSend(opts.timeout);
 }
 
-size_t oneShotMaxBytes() {
-  static const size_t n = [] {
-    const char* v = std::getenv("GLB_ALLREDUCE_ONESHOT_MAX");
-    if (v == nullptr) v = std::getenv("GLOO_ALLREDUCE_ONESHOT_MAX");
-    long long b = v != nullptr ? std::atoll(v) : (16 << 10);
-    return static_cast<size_t>(b < 0 ? 0 : b);
-  }();
-  return n;
-}
-
 }  // namespace
 
 void allreduce(const AllreduceOptions& opts) {
@@ -351,7 +351,7 @@ void allreduce(const AllreduceOptions& opts) {
   if (context->size > 1) {
     switch (opts.algorithm) {
       case AllreduceOptions::UNSPECIFIED:
-        if (bytes <= oneShotMaxBytes() && context->size <= 64) {
+        if (bytes <= detail::oneHopMaxBytes() && context->size <= 64) {
           oneShot(opts, out0, src);
           break;
         }

@@ -22,7 +22,7 @@ void broadcast(BroadcastOptions& opts) {
 
   // Small payloads: the root sends to everyone itself. P-1 back-to-back writes cost a few
   // microseconds; every level of the tree costs a full message hop.
-  if (out->size <= 16384 && P <= 32) {
+  if (out->size <= detail::oneHopMaxBytes() && P <= 32) {
     if (r == opts.root) {
       for (int k = 1; k < P; k++) out->send((r + k) % P, slot, 0, out->size);
       for (int k = 1; k < P; k++) out->waitSend(opts.timeout);

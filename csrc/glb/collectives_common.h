@@ -43,6 +43,11 @@ struct Range {
 };
 
 // i-th of `parts` near-equal pieces of r (the first r.len % parts pieces get one extra element).
+// Largest payload (bytes) for which the latency-oriented one-hop variants are used:
+// allreduce (no algorithm requested), allgather, broadcast, reduce. GLB_ONEHOP_MAX, default
+// 16 KiB; 0 disables them.
+size_t oneHopMaxBytes();
+
 inline Range subRange(Range r, size_t parts, size_t i) {
   size_t base = r.len / parts;
   size_t rem = r.len % parts;

@@ -21,7 +21,7 @@ void reduce(ReduceOptions& opts) {
   const auto slot = Slot::build(kReduceSlotPrefix, opts.tag);
   // Small vectors: everyone sends straight to the root, which folds the contributions in
   // rank order - one hop instead of a ring reduce-scatter plus a gather.
-  if (P > 1 && bytes <= 16384 && P <= 64) {
+  if (P > 1 && bytes <= detail::oneHopMaxBytes() && P <= 64) {
     UnboundBuffer* src = opts.in ? opts.in.get() : out;
     if (r != opts.root) {
       src->send(opts.root, slot, 0, bytes);

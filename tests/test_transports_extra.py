@@ -196,3 +196,28 @@ def test_every_host_benchmark_name_runs_and_verifies():
         if codes != [0, 0]:
             bad.append((n, codes, outs[0][-300:]))
     assert not bad, bad
+
+
+def test_ipv6_loopback_device():
+    """The transport is address-family agnostic: bind ::1 and run a collective over it."""
+    import threading
+
+    try:
+        dev = gb.create_device(hostname="::1")
+    except gb.GlbError:
+        pytest.skip("IPv6 loopback not available")
+    assert "[::1]" in str(dev)
+    store, out = gb.HashStore(), [None, None]
+
+    def rank(r):
+        ctx = gb.Context(r, 2)
+        ctx.connect_full_mesh(store, gb.create_device(hostname="::1"))
+        x = np.full(1 << 17, r + 1, np.float32)
+        gb.allreduce(ctx, x)
+        gb.barrier(ctx)
+        out[r] = float(x[-1])
+
+    ths = [threading.Thread(target=rank, args=(r,)) for r in range(2)]
+    [t.start() for t in ths]
+    [t.join(60) for t in ths]
+    assert out == [3.0, 3.0]

@@ -21,6 +21,7 @@ step) and the clocks seen while timing.
 from __future__ import annotations
 
 import argparse
+import glob
 import json
 import os
 import re
@@ -418,7 +419,8 @@ def run_reference(args):
                        "path": "pytorch/gloo benchmark_cuda (CudaHostWorkspace: GPU->pinned host->TCP loopback->CPU reduce)"},
             "p50_us": round(p50 / 1e3, 2), "p99_us": round(p99 / 1e3, 2), "sweep": sweep,
         }), flush=True)
-    shutil.rmtree(os.path.dirname(base) if False else base, ignore_errors=True)
+    for d in glob.glob(base + "_*"):
+        shutil.rmtree(d, ignore_errors=True)
 
 
 def main():

@@ -52,6 +52,9 @@ std::vector<int> factorize(int n) {
 void ringReduceScatter(const std::shared_ptr<Context>& context, UnboundBuffer* buf, size_t elements,
                        size_t elementSize, const AllreduceOptions::Func& reduce, size_t maxSegmentSize,
                        uint64_t slot, std::chrono::milliseconds timeout) {
+  // In-place ring reduce-scatter, streamed: a segment is forwarded as soon as it has been
+  // reduced, so consecutive steps overlap (same scheme as the first half of ring()).
+  // Afterwards rank r owns the reduced chunk (r + 1) % P.
   const int P = context->size;
   const int r = context->rank;
   if (P == 1 || elements == 0) return;
@@ -61,43 +64,47 @@ void ringReduceScatter(const std::shared_ptr<Context>& context, UnboundBuffer* b
   const Range all{0, elements};
 
   const size_t maxChunkElems = ceilDiv(elements, static_cast<size_t>(P));
-  const size_t segElems = std::max<size_t>(1, std::min(maxChunkElems, maxSegmentSize / elementSize));
+  size_t segBytes = std::min(maxSegmentSize, std::max<size_t>(256u << 10, maxChunkElems * elementSize / 4));
+  const size_t segElems = std::max<size_t>(1, std::min(maxChunkElems, segBytes / elementSize));
   const size_t nseg = ceilDiv(maxChunkElems, segElems);
-
-  // Two receive landing zones so the next segment arrives while this one is reduced.
-  std::vector<char> tmpStorage(2 * segElems * elementSize);
-  auto tmp = context->createUnboundBuffer(tmpStorage.data(), tmpStorage.size());
-
-  auto segOf = [&](const Range& chunk, size_t j) {
+  auto chunk = [&](int c) { return subRange(all, P, static_cast<size_t>(((c % P) + P) % P)); };
+  auto segOf = [&](const Range& ch, size_t j) {
     Range s;
-    s.off = chunk.off + std::min(chunk.len, j * segElems);
-    s.len = std::min(segElems, chunk.len - std::min(chunk.len, j * segElems));
+    s.off = ch.off + std::min(ch.len, j * segElems);
+    s.len = std::min(segElems, ch.len - std::min(ch.len, j * segElems));
     return s;
   };
 
-  for (int s = 0; s < P - 1; s++) {
-    const Range sendChunk = subRange(all, P, (r - s + P) % P);
-    const Range recvChunk = subRange(all, P, (r - s - 1 + 2 * P) % P);
-    size_t sendsPosted = 0;
-    auto postRecv = [&](size_t j) {
-      Range seg = segOf(recvChunk, j);
-      tmp->recv(left, slot, (j % 2) * segElems * elementSize, seg.len * elementSize);
-    };
-    postRecv(0);
-    for (size_t j = 0; j < nseg; j++) {
-      if (j + 1 < nseg) postRecv(j + 1);
-      Range sseg = segOf(sendChunk, j);
-      buf->send(right, slot, sseg.off * elementSize, sseg.len * elementSize);
-      sendsPosted++;
-      tmp->waitRecv(timeout);
-      Range rseg = segOf(recvChunk, j);
-      if (rseg.len > 0) {
-        char* dst = base + rseg.off * elementSize;
-        reduce(dst, dst, tmpStorage.data() + (j % 2) * segElems * elementSize, rseg.len);
-      }
-    }
-    for (size_t k = 0; k < sendsPosted; k++) buf->waitSend(timeout);
+  constexpr size_t kDepth = 4;
+  std::vector<char> tmpStorage(kDepth * segElems * elementSize);
+  auto tmp = context->createUnboundBuffer(tmpStorage.data(), tmpStorage.size());
+  const size_t total = static_cast<size_t>(P - 1) * nseg;
+  auto post = [&](size_t k) {
+    Range sg = segOf(chunk(r - static_cast<int>(k / nseg) - 1), k % nseg);
+    tmp->recv(left, slot, (k % kDepth) * segElems * elementSize, sg.len * elementSize);
+  };
+  for (size_t k = 0; k < std::min(kDepth, total); k++) post(k);
+  size_t sends = 0;
+  for (size_t j = 0; j < nseg; j++) {
+    Range sg = segOf(chunk(r), j);
+    buf->send(right, slot, sg.off * elementSize, sg.len * elementSize);
+    sends++;
   }
+  for (size_t k = 0; k < total; k++) {
+    const size_t s = k / nseg, j = k % nseg;
+    tmp->waitRecv(timeout);
+    Range sg = segOf(chunk(r - static_cast<int>(s) - 1), j);
+    if (sg.len > 0) {
+      char* dst = base + sg.off * elementSize;
+      reduce(dst, dst, tmpStorage.data() + (k % kDepth) * segElems * elementSize, sg.len);
+    }
+    if (k + kDepth < total) post(k + kDepth);
+    if (s + 2 < static_cast<size_t>(P)) {
+      buf->send(right, slot, sg.off * elementSize, sg.len * elementSize);
+      sends++;
+    }
+  }
+  for (size_t k = 0; k < sends; k++) buf->waitSend(timeout);
 }
 
 }  // namespace detail

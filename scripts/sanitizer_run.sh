@@ -24,6 +24,23 @@ for NAME in "$@"; do
     wait; rm -rf $D
   done
 done
+# TLS pairs (session lifetime vs. the loop thread): short runs, many connects and teardowns
+if command -v openssl >/dev/null 2>&1; then
+  C=$OUT/certs; mkdir -p $C
+  openssl req -x509 -newkey rsa:2048 -nodes -keyout $C/ca.key -out $C/ca.crt -subj /CN=san-ca -days 2 >/dev/null 2>&1
+  openssl req -newkey rsa:2048 -nodes -keyout $C/r.key -out $C/r.csr -subj /CN=rank >/dev/null 2>&1
+  openssl x509 -req -in $C/r.csr -CA $C/ca.crt -CAkey $C/ca.key -CAcreateserial -out $C/r.crt -days 2 >/dev/null 2>&1
+  i=0; while [ $i -lt 15 ]; do
+    D=$(mktemp -d /tmp/glb_san_rdv.XXXXXX)
+    for r in 1 0; do
+      TSAN_OPTIONS="suppressions=$PWD/.tsan-suppressions halt_on_error=0 log_path=$OUT/tls.$i.r$r" \
+      ASAN_OPTIONS="detect_leaks=0 log_path=$OUT/tls.$i.r$r" \
+        $BIN --size 2 --rank $r --shared-path $D --transport tls --pkey $C/r.key --cert $C/r.crt --ca-file $C/ca.crt \
+             --elements 1000 --iteration-count 10 new_allreduce_ring >$OUT/tls.$i.r$r.stdout 2>&1 &
+    done
+    wait; rm -rf $D; i=$((i+1))
+  done
+fi
 # the self-test: same instrumentation, results checked (threads as ranks in one process)
 ST=gloo_b200/bin/glb_selftest_$SAN
 if [ -x $ST ]; then

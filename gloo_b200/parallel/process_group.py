@@ -144,8 +144,9 @@ class GlbProcessGroup(dist.ProcessGroup):
         if idx not in self._cuda:
             # torch tensors are not registered with the peer context, so they travel through
             # its staging pool: allreduce is cut into pool-sized pieces, the data-movement
-            # collectives need the whole payload to fit (GLB_PG_STAGE_MB, default 256).
-            stage = int(os.environ.get("GLB_PG_STAGE_MB", "256")) << 20
+            # collectives need the whole payload to fit (GLB_PG_STAGE_MB, default 64 - the measured
+            # configuration; raise it for large all_gather / reduce_scatter payloads).
+            stage = int(os.environ.get("GLB_PG_STAGE_MB", "64")) << 20
             with torch.cuda.device(idx):
                 self._cuda[idx] = gcu.CudaContext(self.ctx, idx, stage_bytes=stage)
         return self._cuda[idx]

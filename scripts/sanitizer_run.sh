@@ -7,7 +7,7 @@ SAN=${1:-thread}; P=${2:-3}; shift; shift
 BIN=gloo_b200/bin/glb_benchmark_$SAN
 [ -x $BIN ] || python build.py --sanitize $SAN || exit 1
 [ $# -gt 0 ] || set -- allreduce_ring allreduce_ring_chunked allreduce_halving_doubling allreduce_bcube \
-  new_allreduce_ring new_allreduce_bcube reduce_scatter new_reduce_scatter allgather allgather_ring \
+  new_allreduce new_allreduce_ring new_allreduce_bcube reduce_scatter new_reduce_scatter allgather allgather_ring \
   alltoall alltoall_v gather scatter reduce broadcast broadcast_one_to_all barrier_all_to_all \
   barrier_all_to_one pairwise_exchange sendrecv_roundtrip sendrecv_stress
 OUT=$(mktemp -d /tmp/glb_san.XXXXXX)

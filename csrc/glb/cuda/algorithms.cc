@@ -23,6 +23,7 @@ AllreduceAlgo effectiveAlgo(AllreduceAlgo requested) {
     case AllreduceAlgo::RING_CHUNKED:
     case AllreduceAlgo::HALVING_DOUBLING:
     case AllreduceAlgo::BCUBE:
+    case AllreduceAlgo::HALVING_DOUBLING_PIPELINED:
       return requested;
     default:
       return requested;
@@ -93,7 +94,7 @@ struct CudaAllreduceCore::Literal {
 namespace {
 bool isLiteral(AllreduceAlgo a) {
   return a == AllreduceAlgo::RING || a == AllreduceAlgo::RING_CHUNKED || a == AllreduceAlgo::HALVING_DOUBLING ||
-         a == AllreduceAlgo::BCUBE;
+         a == AllreduceAlgo::BCUBE || a == AllreduceAlgo::HALVING_DOUBLING_PIPELINED;
 }
 }  // namespace
 
@@ -132,6 +133,10 @@ CudaAllreduceCore::CudaAllreduceCore(std::shared_ptr<Context> ctx, std::vector<v
           case AllreduceAlgo::HALVING_DOUBLING:
             lit->schedule = buildHalvingDoublingSchedule(ctx_->rank, ctx_->size, count_, pack);
             break;
+          case AllreduceAlgo::HALVING_DOUBLING_PIPELINED:
+            lit->schedule = buildHalvingDoublingPipelinedSchedule(ctx_->rank, ctx_->size, count_, pack,
+                                                                  static_cast<int>(envInt("CUDA_HD_CHUNKS", 2)));
+            break;
           default: lit->schedule = buildBcubeSchedule(ctx_->rank, ctx_->size, count_, ctx_->base, pack); break;
         }
         DeviceGuard g(dev0);
@@ -142,13 +147,80 @@ CudaAllreduceCore::CudaAllreduceCore(std::shared_ptr<Context> ctx, std::vector<v
       }
     }
   }
+  // Fold the extra local pointers inside the collective kernel when they live on the same
+  // device as the first one (and, across ranks, every pointer is 16-byte aligned so that
+  // all ranks pick the same element -> CTA mapping).
+  if (ptrs_.size() > 1 && ptrs_.size() - 1 <= static_cast<size_t>(kMaxLocal) && !envFlag("CUDA_NO_LOCAL_FUSION", false)) {
+    bool mine = true;
+    for (size_t i = 0; i < ptrs_.size(); i++) {
+      mine = mine && streams_[i].getDeviceID() == dev0 && reinterpret_cast<uintptr_t>(ptrs_[i]) % 16 == 0;
+    }
+    if (ctx_->size == 1) {
+      fuseLocal_ = mine;
+    } else if (pc_ && !literal_) {
+      fuseLocal_ = pc_->agree(mine);
+    }
+  }
   if (ctx_->size > 1 && !pc_) {
-    GLB_CUDA_CHECK(cudaMallocHost(&hostScratch_, std::max<size_t>(count_ * elementSize(dt_), 16)));
+    const size_t bytes = std::max<size_t>(count_ * elementSize(dt_), 16);
+    GLB_CUDA_CHECK(cudaMallocHost(&hostScratch_, bytes));
+    // Host workspace: cut into chunks so that D2H of chunk c+1, the host collective of chunk c
+    // and H2D of chunk c-1 overlap (cuda_allreduce_ring_chunked.cc:129-273 does the same per
+    // ring chunk).
+    const size_t minChunk = static_cast<size_t>(envInt("CUDA_HOST_CHUNK_MIN", 1 << 20));
+    hostChunks_ = static_cast<int>(std::max<size_t>(1, std::min<size_t>(static_cast<size_t>(envInt("CUDA_HOST_CHUNKS", 8)), bytes / minChunk)));
+    DeviceGuard g(dev0);
+    h2dStream_ = std::make_unique<CudaStream>(dev0);
+    chunkEvents_.resize(hostChunks_);
+    for (auto& ev : chunkEvents_) GLB_CUDA_CHECK(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
   }
 }
 
 CudaAllreduceCore::~CudaAllreduceCore() {
   if (hostScratch_ != nullptr) cudaFreeHost(hostScratch_);
+  for (auto ev : chunkEvents_) cudaEventDestroy(ev);
+}
+
+int CudaAllreduceCore::launchesPerRun() const {
+  const int cross = ctx_->size > 1 ? 1 : 0;
+  if (ptrs_.size() <= 1) return cross;
+  if (fuseLocal_) return 1;
+  return 2 + cross;
+}
+
+// D2H in chunks (all enqueued up front), then per chunk: wait for its copy, run the host
+// collective over the transport, enqueue its H2D on a second stream. PCIe down-traffic of
+// chunk c+1 and up-traffic of chunk c-1 overlap the network time of chunk c.
+void CudaAllreduceCore::runHostWorkspace(CudaStream& s0) {
+  const size_t es = elementSize(dt_);
+  const size_t per = roundUp(ceilDiv(count_, static_cast<size_t>(hostChunks_)), std::max<size_t>(1, 64 / es));
+  char* host = static_cast<char*>(hostScratch_);
+  char* dev = static_cast<char*>(ptrs_[0]);
+  int n = 0;
+  for (size_t lo = 0; lo < count_; lo += per, n++) {
+    const size_t len = std::min(per, count_ - lo);
+    GLB_CUDA_CHECK(cudaMemcpyAsync(host + lo * es, dev + lo * es, len * es, cudaMemcpyDeviceToHost, *s0));
+    GLB_CUDA_CHECK(cudaEventRecord(chunkEvents_[n], *s0));
+  }
+  ReduceFn fn = getReduceFn(dt_, op_);
+  int c = 0;
+  for (size_t lo = 0; lo < count_; lo += per, c++) {
+    const size_t len = std::min(per, count_ - lo);
+    GLB_CUDA_CHECK(cudaEventSynchronize(chunkEvents_[c]));
+    AllreduceOptions opts(ctx_);
+    opts.setOutputsRaw({host + lo * es}, len, es);
+    opts.setReduceFunction([fn](void* o, const void* a, const void* b, size_t k) { fn(o, a, b, k); });
+    opts.setTag(0x00CDA000u + static_cast<uint32_t>(c));
+    glb::allreduce(opts);
+    GLB_CUDA_CHECK(cudaMemcpyAsync(dev + lo * es, host + lo * es, len * es, cudaMemcpyHostToDevice, **h2dStream_));
+  }
+  h2dStream_->record();
+  s0.waitOn(*h2dStream_);
+  if (scale_ != 1.0) {
+    void* one[1] = {ptrs_[0]};
+    launchLocalAllreduceMany(one, 1, count_, dt_, op_, static_cast<float>(scale_), *s0);
+    noteLaunch();
+  }
 }
 
 AllreduceAlgo CudaAllreduceCore::resolvedAlgo() const {
@@ -164,57 +236,83 @@ void CudaAllreduceCore::run() {
   CudaStream& s0 = streams_[0];
   const size_t bytes = count_ * elementSize(dt_);
   DeviceGuard g(s0.getDeviceID());
+  const bool multi = ptrs_.size() > 1;
 
-  // 1. fold the local pointers into ptrs_[0]
-  if (ptrs_.size() > 1) {
+  if (multi) {
     for (size_t i = 1; i < streams_.size(); i++) {
       streams_[i].record();
       s0.waitOn(streams_[i]);
     }
-    std::vector<const void*> srcs(ptrs_.begin(), ptrs_.end());
-    launchLocalReduceMany(ptrs_[0], srcs.data(), static_cast<int>(srcs.size()), count_, dt_, op_, *s0);
-    noteLaunch();
   }
 
-  // 2. across ranks
-  if (ctx_->size > 1) {
-    if (pc_ && literal_) {
-      const size_t vecs = bytes / 16 / ctx_->size;
-      const int blocks = std::max(1, std::min<int>({pc_->maxBlocks(), tuning().maxBlocks,
-                                                    static_cast<int>(vecs / kThreads) + 1}));
-      pc_->launchGuard();
-      launchSchedule(pc_->comm(), reg_->ptrsAt(regOffset_), pc_->stagePtrs(pc_->stageBytes() / 2), literal_->deviceTable,
-                     static_cast<int>(literal_->schedule.steps.size()), dt_, op_, reg_->vectorOk && regOffset_ % 16 == 0, blocks, *s0);
+  Epilogue ep;
+  ep.scale = scale_;
+  ep.blocks = shapeBlocks_;
+  ep.unroll = shapeUnroll_;
+  ep.tile = shapeTile_;
+  if (fuseLocal_) {
+    ep.extra.n = static_cast<int>(ptrs_.size()) - 1;
+    for (int k = 0; k < ep.extra.n; k++) ep.extra.p[k] = ptrs_[k + 1];
+  }
+
+  if (fuseLocal_ && ctx_->size == 1) {
+    // The whole step in one pass: every buffer := scale * reduce(all buffers).
+    launchLocalAllreduceMany(ptrs_.data(), static_cast<int>(ptrs_.size()), count_, dt_, op_, static_cast<float>(scale_), *s0);
+    noteLaunch();
+  } else if (fuseLocal_) {
+    // One launch: fold, exchange and fan-out inside the collective kernel.
+    allreduce(*pc_, *reg_, regOffset_, count_, dt_, op_, algo_, *s0, ep);
+  } else {
+    // 1. fold the local pointers into ptrs_[0]
+    if (multi) {
+      std::vector<const void*> srcs(ptrs_.begin(), ptrs_.end());
+      launchLocalReduceMany(ptrs_[0], srcs.data(), static_cast<int>(srcs.size()), count_, dt_, op_, *s0);
       noteLaunch();
-      cudaError_t le = cudaGetLastError();
-      if (le != cudaSuccess) GLB_THROW(Exception, "schedule kernel launch failed: ", cudaGetErrorString(le));
-    } else if (pc_) {
-      allreduce(*pc_, *reg_, regOffset_, count_, dt_, op_, algo_, *s0);
-    } else {
-      // Host workspace: D2H, host collective over the transport, H2D.
-      s0.copyAsync(hostScratch_, ptrs_[0], bytes);
-      s0.wait();
-      AllreduceOptions opts(ctx_);
-      opts.setOutputsRaw({hostScratch_}, count_, elementSize(dt_));
-      ReduceFn fn = getReduceFn(dt_, op_);
-      opts.setReduceFunction([fn](void* c, const void* a, const void* b, size_t n) { fn(c, a, b, n); });
-      opts.setTag(0x00CDA000u);
-      glb::allreduce(opts);
-      s0.copyAsync(ptrs_[0], hostScratch_, bytes);
+    }
+    // 2. across ranks
+    if (ctx_->size > 1) {
+      if (pc_ && literal_) {
+        const size_t vecs = bytes / 16 / ctx_->size;
+        int cap = shapeBlocks_ > 0 ? shapeBlocks_ : tuning().maxBlocks;
+        if (const TuneEntry* e = TuningTable::get().lookup("allreduce_literal", ctx_->size, BufKind::REGISTERED, bytes)) {
+          if (e->blocks > 0 && shapeBlocks_ == 0) cap = e->blocks;
+        }
+        const int blocks = std::max(1, std::min<int>({pc_->maxBlocks(), cap, static_cast<int>(vecs / kThreads) + 1}));
+        pc_->checkHealth();
+        pc_->orderStreams(*s0);
+        pc_->launchGuard();
+        launchSchedule(pc_->comm(), reg_->ptrsAt(regOffset_), pc_->stagePtrs(pc_->stageBytes() / 2), literal_->deviceTable,
+                       static_cast<int>(literal_->schedule.steps.size()), scheduleBarriers(literal_->schedule), dt_, op_,
+                       static_cast<float>(scale_), count_, reg_->vectorOk && regOffset_ % 16 == 0, blocks, *s0);
+        noteLaunch();
+        cudaError_t le = cudaGetLastError();
+        if (le != cudaSuccess) GLB_THROW(Exception, "schedule kernel launch failed: ", cudaGetErrorString(le));
+      } else if (pc_) {
+        allreduce(*pc_, *reg_, regOffset_, count_, dt_, op_, algo_, *s0, ep);
+      } else {
+        runHostWorkspace(s0);
+      }
+    } else if (scale_ != 1.0) {
+      void* one[1] = {ptrs_[0]};
+      launchLocalAllreduceMany(one, 1, count_, dt_, op_, static_cast<float>(scale_), *s0);
+      noteLaunch();
+    }
+    // 3. replicate to the other local pointers
+    if (multi) {
+      std::vector<void*> dsts(ptrs_.begin() + 1, ptrs_.end());
+      launchLocalBroadcast(dsts.data(), static_cast<int>(dsts.size()), ptrs_[0], bytes, *s0);
+      noteLaunch();
     }
   }
 
-  // 3. replicate to the other local pointers
-  if (ptrs_.size() > 1) {
-    std::vector<void*> dsts(ptrs_.begin() + 1, ptrs_.end());
-    launchLocalBroadcast(dsts.data(), static_cast<int>(dsts.size()), ptrs_[0], bytes, *s0);
-    noteLaunch();
+  if (multi) {
     s0.record();
     for (size_t i = 1; i < streams_.size(); i++) streams_[i].waitOn(s0);
   }
   if (syncOutputs_) {
     s0.record();
     s0.wait();
+    if (pc_) pc_->checkHealth();
   }
 }
 
@@ -320,11 +418,11 @@ void CudaAllreduceLocal<T>::run() {
     streams_[i].record();
     s0.waitOn(streams_[i]);
   }
-  std::vector<const void*> srcs(ptrs_.begin(), ptrs_.end());
-  cuda::launchLocalReduceMany(ptrs_[0], srcs.data(), static_cast<int>(srcs.size()), count_, DataTypeOf<T>::value,
-                        ReduceOp::SUM, *s0);
-  std::vector<void*> dsts(ptrs_.begin() + 1, ptrs_.end());
-  cuda::launchLocalBroadcast(dsts.data(), static_cast<int>(dsts.size()), ptrs_[0], count_ * sizeof(T), *s0);
+  // One pass: every buffer := sum of all buffers (peer buffers of other local GPUs are
+  // read and written through peer access).
+  cuda::launchLocalAllreduceMany(ptrs_.data(), static_cast<int>(ptrs_.size()), count_, DataTypeOf<T>::value, ReduceOp::SUM,
+                                 1.0f, *s0);
+  cuda::noteLaunch();
   s0.record();
   for (size_t i = 1; i < streams_.size(); i++) streams_[i].waitOn(s0);
   if (syncOutputs_) s0.wait();

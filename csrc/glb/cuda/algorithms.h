@@ -61,8 +61,20 @@ class CudaAllreduceCore {
   void run();
   AllreduceAlgo resolvedAlgo() const;
   bool usesPeerMemory() const { return pc_ != nullptr; }
+  // Fused epilogue: the result is multiplied by `scale` (AVG = 1 / (ranks x local pointers))
+  // inside the collective kernel.
+  void setScale(double scale) { scale_ = scale; }
+  // Launches per run() (1 when the local fold, the exchange and the fan-out are fused).
+  int launchesPerRun() const;
+  // Pin the launch shape (sweeps / tuner): 0 = tuning table.
+  void setLaunchShape(int blocks, int unroll, int tile) {
+    shapeBlocks_ = blocks;
+    shapeUnroll_ = unroll;
+    shapeTile_ = tile;
+  }
 
  private:
+  void runHostWorkspace(CudaStream& s0);
   std::shared_ptr<Context> ctx_;
   std::vector<void*> ptrs_;
   size_t count_;
@@ -70,6 +82,12 @@ class CudaAllreduceCore {
   ReduceOp op_;
   AllreduceAlgo algo_;
   bool syncOutputs_;
+  double scale_ = 1.0;
+  bool fuseLocal_ = false;   // extra local pointers are folded inside the collective kernel
+  int shapeBlocks_ = 0, shapeUnroll_ = 0, shapeTile_ = 0;
+  int hostChunks_ = 1;
+  std::unique_ptr<CudaStream> h2dStream_;
+  std::vector<cudaEvent_t> chunkEvents_;
   std::vector<CudaStream> streams_;
   std::shared_ptr<PeerContext> pc_;
   std::shared_ptr<PeerBuffer> reg_;
@@ -170,7 +188,7 @@ const CudaReductionFunction<T>* CudaReductionFunction<T>::max = new CudaReductio
 GLB_DEFINE_CUDA_ALLREDUCE(CudaAllreduceRing, RING)
 GLB_DEFINE_CUDA_ALLREDUCE(CudaAllreduceRingChunked, RING_CHUNKED)
 GLB_DEFINE_CUDA_ALLREDUCE(CudaAllreduceHalvingDoubling, HALVING_DOUBLING)
-GLB_DEFINE_CUDA_ALLREDUCE(CudaAllreduceHalvingDoublingPipelined, HALVING_DOUBLING)
+GLB_DEFINE_CUDA_ALLREDUCE(CudaAllreduceHalvingDoublingPipelined, HALVING_DOUBLING_PIPELINED)
 GLB_DEFINE_CUDA_ALLREDUCE(CudaAllreduceBcube, BCUBE)
 #undef GLB_DEFINE_CUDA_ALLREDUCE
 

@@ -1,13 +1,16 @@
 // Fused allreduce kernels over NVLink peer memory (sm_100a).
 //
 //   barrierKernel        flag barrier only.
-//   oneShotAllreduce     latency regime. Each rank stages its input in its own
-//                        symmetric pool (double-buffered by launch parity), one
-//                        flag barrier, then every rank reads all P staged copies
-//                        straight over NVLink, reduces in registers (fp32
-//                        accumulate for 16-bit types) and writes its output. One
-//                        kernel, one barrier, no host involvement; works for any
-//                        user pointer because peers only touch the pools.
+//   llAllreduce          smallest messages. Flag-in-data ("LL") protocol: every rank stores
+//                        its contribution as 16-byte {d0,seq,d1,seq} lines straight into
+//                        every peer's pool and polls its own pool for the peers' lines: one
+//                        posted NVLink store and one poll on the critical path, no barrier
+//                        round, no MEMBAR.SYS.
+//   oneShotAllreduce     latency regime above that. Each rank stages its input in its own
+//                        symmetric pool (double-buffered by launch parity), one flag
+//                        barrier, then every rank reads all P staged copies over NVLink,
+//                        reduces in registers (fp32 accumulate for 16-bit types) and writes
+//                        its output; a push flavour stores into the peers instead.
 //   twoShotAllreduce     bandwidth regime, in place on peer-mapped user buffers.
 //                        Rank r owns chunk r: it loads that chunk from all P
 //                        buffers (reduce-scatter by direct peer reads), reduces,
@@ -18,6 +21,13 @@
 //   nvlsAllreduce        same ownership, but the reduction happens inside the
 //                        NVSwitch: multimem.ld_reduce pulls the switch-reduced
 //                        chunk, multimem.st broadcasts it; ~S(1+1/P) per direction.
+//   castAllreduce        two-shot / NVLS with an output dtype different from the input dtype
+//                        (fp32 accumulate -> bf16/fp16 store, or 16-bit in -> fp32 out).
+//
+// Every variant applies the epilogue `scale` (AVG = 1/P, loss scaling, ...) to the fp32
+// accumulator before the single final rounding, and — when a rank passes several local
+// pointers — folds them in the same launch (LocalPtrs): no separate elementwise kernel
+// runs before or after the collective.
 //
 // There is no reference counterpart: the reference stages through pinned host
 // memory + TCP (cuda_allreduce_ring_chunked.cc:129-273) and reduces on the CPU.
@@ -27,74 +37,256 @@
 namespace glb {
 namespace cuda {
 
-bool oneShotPushEnabled();
-
 __global__ void barrierKernel(CommArgs a) {
   const uint32_t e = loadEpoch(a);
   blockBarrier(a, e + 1);
   retire(a, 1, 0);
 }
 
+// ---- element groups ------------------------------------------------------------------
+// The barrier pairs CTA b of one rank with CTA b of every peer, so which CTA touches which
+// element must not depend on anything rank-local (such as the alignment of a user pointer).
+// All staged kernels therefore own 16-byte *groups* of elements by index; a group is moved
+// with one 128-bit access when the pointer allows it and element by element otherwise.
+
+template <typename T>
+__device__ __forceinline__ Pack16 loadGroup(const T* base, size_t g, size_t count, bool aligned) {
+  constexpr int K = 16 / sizeof(T);
+  const size_t i0 = g * K;
+  if (aligned && i0 + K <= count) return ld128_stream(reinterpret_cast<const char*>(base) + g * 16);
+  Pack16 p;
+  p.w[0] = p.w[1] = p.w[2] = p.w[3] = 0u;
+  T* t = reinterpret_cast<T*>(&p);
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    if (i0 + k < count) t[k] = base[i0 + k];
+  }
+  return p;
+}
+
+template <typename T>
+__device__ __forceinline__ void storeGroup(T* base, size_t g, size_t count, bool aligned, const Pack16& p) {
+  constexpr int K = 16 / sizeof(T);
+  const size_t i0 = g * K;
+  if (aligned && i0 + K <= count) {
+    st128(reinterpret_cast<char*>(base) + g * 16, p);
+    return;
+  }
+  const T* t = reinterpret_cast<const T*>(&p);
+#pragma unroll
+  for (int k = 0; k < K; k++) {
+    if (i0 + k < count) base[i0 + k] = t[k];
+  }
+}
+
+// Group g of the local contribution: the first pointer, plus the extra local pointers
+// folded in (multi-pointer classes) — the fold costs no extra pass.
+template <typename T>
+__device__ __forceinline__ Pack16 loadLocalGroup(const T* in, const LocalPtrs& extra, size_t g, size_t count,
+                                                 bool aligned, DevOp op) {
+  using PT = PackTraits<T>;
+  Pack16 p = loadGroup(in, g, count, aligned);
+  if (extra.n > 0) {
+    typename PT::AccPack acc = PT::widen(p);
+    for (int k = 0; k < extra.n; k++) PT::combine(acc, loadGroup(static_cast<const T*>(extra.p[k]), g, count, aligned), op);
+    p = PT::narrow(acc);
+  }
+  return p;
+}
+
+template <typename T>
+__device__ __forceinline__ void storeLocalGroup(T* out, const LocalPtrs& extra, size_t g, size_t count, bool aligned,
+                                                const Pack16& p) {
+  storeGroup(out, g, count, aligned, p);
+  for (int k = 0; k < extra.n; k++) storeGroup(static_cast<T*>(extra.p[k]), g, count, aligned, p);
+}
+
+// ---- LL (flag in data) -------------------------------------------------------------------
+
+template <typename T>
+struct AccType {
+  using type = T;
+};
+template <>
+struct AccType<__half> {
+  using type = float;
+};
+template <>
+struct AccType<__nv_bfloat16> {
+  using type = float;
+};
+
+template <typename T>
+__device__ __forceinline__ typename AccType<T>::type toAcc(T x) {
+  return x;
+}
+template <>
+__device__ __forceinline__ float toAcc<__half>(__half x) {
+  return __half2float(x);
+}
+template <>
+__device__ __forceinline__ float toAcc<__nv_bfloat16>(__nv_bfloat16 x) {
+  return __bfloat162float(x);
+}
+template <typename TO, typename A>
+__device__ __forceinline__ TO fromAcc(A x) {
+  return static_cast<TO>(x);
+}
+template <>
+__device__ __forceinline__ __half fromAcc<__half, float>(float x) {
+  return __float2half_rn(x);
+}
+template <>
+__device__ __forceinline__ __nv_bfloat16 fromAcc<__nv_bfloat16, float>(float x) {
+  return __float2bfloat16_rn(x);
+}
+
+// `ll.p[r]` is the LL region of rank r's pool: [parity][source rank][line]. A launch uses
+// parity = seq & 1; two halves suffice because a rank can run at most one launch ahead of
+// its slowest peer (it needs that peer's lines of launch s+1 to finish launch s+1).
+template <typename T, typename TO>
+__global__ void __launch_bounds__(kThreads)
+llAllreduceKernel(CommArgs a, const T* in, TO* out, size_t count, DevOp op, float scale, PeerPtrs ll,
+                  size_t srcStride, size_t parityStride, LocalPtrs extra) {
+  constexpr int K = 8 / sizeof(T);
+  using A = typename AccType<T>::type;
+  const uint32_t seq = ld_relaxed_sys(&a.sig[a.rank]->llSeq) + 1u;
+  const size_t base = (seq & 1u) * parityStride;
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t nunits = (count + K - 1) / K;
+  const int P = a.nranks;
+  char* myRegion = static_cast<char*>(ll.p[a.rank]) + base;
+  const bool inAligned = reinterpret_cast<uintptr_t>(in) % 8 == 0;
+  bool alive = true;
+
+  for (size_t u = tid; u < nunits && alive; u += nthreads) {
+    const size_t i0 = u * K;
+    // my 8 bytes (zero padded past the end; extra local pointers folded in)
+    uint32_t w[2] = {0u, 0u};
+    T* t = reinterpret_cast<T*>(w);
+    if (inAligned && i0 + K <= count) {
+      const uint2 v = *reinterpret_cast<const uint2*>(reinterpret_cast<const char*>(in) + u * 8);
+      w[0] = v.x;
+      w[1] = v.y;
+    } else {
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        if (i0 + k < count) t[k] = in[i0 + k];
+      }
+    }
+    for (int e = 0; e < extra.n; e++) {
+      const T* x = static_cast<const T*>(extra.p[e]);
+#pragma unroll
+      for (int k = 0; k < K; k++) {
+        if (i0 + k < count) t[k] = PackTraits<T>::combineOne(t[k], x[i0 + k], op);
+      }
+    }
+    // push to every peer (rotated so that the P senders hit P different targets)
+    for (int i = 1; i < P; i++) {
+      const int r = (a.rank + i) % P;
+      llStore(static_cast<char*>(ll.p[r]) + base + static_cast<size_t>(a.rank) * srcStride + u * 16, w[0], w[1], seq);
+    }
+    // gather in rank order: every rank sums in the same order -> bit-identical results
+    A acc[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) acc[k] = A(0);
+    for (int r = 0; r < P; r++) {
+      uint32_t d[2];
+      if (r == a.rank) {
+        d[0] = w[0];
+        d[1] = w[1];
+      } else if (!llLoad(a, myRegion + static_cast<size_t>(r) * srcStride + u * 16, seq, d[0], d[1], r)) {
+        alive = false;
+        break;
+      }
+      const T* x = reinterpret_cast<const T*>(d);
+      if (r == 0) {
+#pragma unroll
+        for (int k = 0; k < K; k++) acc[k] = toAcc<T>(x[k]);
+      } else {
+#pragma unroll
+        for (int k = 0; k < K; k++) acc[k] = applyOp<A>(acc[k], toAcc<T>(x[k]), op);
+      }
+    }
+    if (!alive) break;
+    if (scale != 1.0f) {
+      if constexpr (std::is_floating_point<A>::value) {
+#pragma unroll
+        for (int k = 0; k < K; k++) acc[k] = static_cast<A>(acc[k] * scale);
+      }
+    }
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      if (i0 + k < count) {
+        const TO o = fromAcc<TO, A>(acc[k]);
+        out[i0 + k] = o;
+        if constexpr (std::is_same<T, TO>::value) {
+          for (int e = 0; e < extra.n; e++) static_cast<TO*>(extra.p[e])[i0 + k] = o;
+        }
+      }
+    }
+  }
+  retire(a, 0, 0, 1);
+}
+
 // ---- one-shot ---------------------------------------------------------------------
 
-// Push flavour for the smallest messages: every rank STORES its contribution into slot
-// `rank` of every peer's pool (posted writes, no round trip), one barrier, then reads the P
-// slots from its own memory. Saves the remote-load round trip of the pull flavour at the
-// cost of P x the staging space, so it is used while P * bytes fits one half.
+// Push flavour: every rank STORES its contribution into slot `rank` of every peer's pool
+// (posted writes, no round trip), one barrier, then reads the P slots from its own memory.
+// Saves the remote-load round trip of the pull flavour at the cost of P x the staging
+// space, so it is used while P * bytes fits one half.
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-oneShotPushAllreduceKernel(CommArgs a, const T* in, T* out, size_t count, DevOp op, PeerPtrs stage,
-                           size_t halfBytes, size_t slotBytes, bool vectorOk) {
+oneShotPushAllreduceKernel(CommArgs a, const T* in, T* out, size_t count, DevOp op, float scale, PeerPtrs stage,
+                           size_t halfBytes, size_t slotBytes, LocalPtrs extra) {
   using PT = PackTraits<T>;
   const uint32_t e = loadEpoch(a);
   const uint32_t parity = ld_relaxed_sys(&a.sig[a.rank]->stageSeq) & 1u;
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
   const size_t base = parity * halfBytes;
-  const size_t nvec = vectorOk ? count / PT::kElems : 0;
-  const size_t tailStart = nvec * PT::kElems;
+  const size_t ngroups = (count + PT::kElems - 1) / PT::kElems;
   const size_t mySlot = base + static_cast<size_t>(a.rank) * slotBytes;
+  const bool inAligned = reinterpret_cast<uintptr_t>(in) % 16 == 0, outAligned = reinterpret_cast<uintptr_t>(out) % 16 == 0;
+  bool extraAligned = true;
+  for (int k = 0; k < extra.n; k++) extraAligned = extraAligned && reinterpret_cast<uintptr_t>(extra.p[k]) % 16 == 0;
 
-  for (size_t v = tid; v < nvec; v += nthreads) {
-    const Pack16 p = ld128_stream(reinterpret_cast<const char*>(in) + v * 16);
+  for (size_t g = tid; g < ngroups; g += nthreads) {
+    const Pack16 p = loadLocalGroup(in, extra, g, count, inAligned && extraAligned, op);
 #pragma unroll
     for (int r = 0; r < kMaxRanks; r++) {
-      if (r < a.nranks) st128_stream(static_cast<char*>(stage.p[r]) + mySlot + v * 16, p);
+      if (r < a.nranks) st128_stream(static_cast<char*>(stage.p[r]) + mySlot + g * 16, p);
     }
   }
-  for (size_t i = tailStart + tid; i < count; i += nthreads) {
-    const T x = in[i];
-    for (int r = 0; r < a.nranks; r++) reinterpret_cast<T*>(static_cast<char*>(stage.p[r]) + mySlot)[i] = x;
+
+  if (!blockBarrier(a, e + 1)) {
+    retire(a, 1, 1);
+    return;
   }
 
-  blockBarrier(a, e + 1);
-
   const char* mine = static_cast<const char*>(stage.p[a.rank]) + base;
-  for (size_t v = tid; v < nvec; v += nthreads) {
+  for (size_t g = tid; g < ngroups; g += nthreads) {
     Pack16 p[kMaxRanks];
 #pragma unroll
     for (int r = 0; r < kMaxRanks; r++) {
-      if (r < a.nranks) p[r] = ld128(mine + r * slotBytes + v * 16);
+      if (r < a.nranks) p[r] = ld128(mine + r * slotBytes + g * 16);
     }
     typename PT::AccPack acc = PT::widen(p[0]);
 #pragma unroll
     for (int r = 1; r < kMaxRanks; r++) {
       if (r < a.nranks) PT::combine(acc, p[r], op);
     }
-    st128(reinterpret_cast<char*>(out) + v * 16, PT::narrow(acc));
-  }
-  for (size_t i = tailStart + tid; i < count; i += nthreads) {
-    T acc = reinterpret_cast<const T*>(mine)[i];
-    for (int r = 1; r < a.nranks; r++) acc = PT::combineOne(acc, reinterpret_cast<const T*>(mine + r * slotBytes)[i], op);
-    out[i] = acc;
+    if (scale != 1.0f) PT::scale(acc, scale);
+    storeLocalGroup(out, extra, g, count, outAligned && extraAligned, PT::narrow(acc));
   }
   retire(a, 1, 1);
 }
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-oneShotAllreduceKernel(CommArgs a, const T* in, T* out, size_t count, DevOp op,
-                       PeerPtrs stage, size_t halfBytes, bool vectorOk) {
+oneShotAllreduceKernel(CommArgs a, const T* in, T* out, size_t count, DevOp op, float scale, PeerPtrs stage,
+                       size_t halfBytes, LocalPtrs extra) {
   using PT = PackTraits<T>;
   const uint32_t e = loadEpoch(a);
   const uint32_t parity = ld_relaxed_sys(&a.sig[a.rank]->stageSeq) & 1u;
@@ -102,41 +294,36 @@ oneShotAllreduceKernel(CommArgs a, const T* in, T* out, size_t count, DevOp op,
   const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
   const size_t stageOff = parity * halfBytes;
   char* myStage = static_cast<char*>(stage.p[a.rank]) + stageOff;
-
-  const size_t nvec = vectorOk ? count / PT::kElems : 0;
-  const size_t tailStart = nvec * PT::kElems;
+  const size_t ngroups = (count + PT::kElems - 1) / PT::kElems;
+  const bool inAligned = reinterpret_cast<uintptr_t>(in) % 16 == 0, outAligned = reinterpret_cast<uintptr_t>(out) % 16 == 0;
+  bool extraAligned = true;
+  for (int k = 0; k < extra.n; k++) extraAligned = extraAligned && reinterpret_cast<uintptr_t>(extra.p[k]) % 16 == 0;
 
   // Phase 0: publish my contribution in my pool.
-  for (size_t v = tid; v < nvec; v += nthreads) {
-    st128(myStage + v * 16, ld128_stream(reinterpret_cast<const char*>(in) + v * 16));
-  }
-  for (size_t i = tailStart + tid; i < count; i += nthreads) {
-    reinterpret_cast<T*>(myStage)[i] = in[i];
+  for (size_t g = tid; g < ngroups; g += nthreads) {
+    st128(myStage + g * 16, loadLocalGroup(in, extra, g, count, inAligned && extraAligned, op));
   }
 
-  blockBarrier(a, e + 1);
+  if (!blockBarrier(a, e + 1)) {
+    retire(a, 1, 1);
+    return;
+  }
 
   // Phase 1: reduce all P staged copies. Summation order is rank order on every
   // rank, so all ranks produce bit-identical results.
-  for (size_t v = tid; v < nvec; v += nthreads) {
+  for (size_t g = tid; g < ngroups; g += nthreads) {
     Pack16 p[kMaxRanks];
 #pragma unroll
     for (int r = 0; r < kMaxRanks; r++) {
-      if (r < a.nranks) p[r] = ld128_stream(static_cast<const char*>(stage.p[r]) + stageOff + v * 16);
+      if (r < a.nranks) p[r] = ld128_stream(static_cast<const char*>(stage.p[r]) + stageOff + g * 16);
     }
     typename PT::AccPack acc = PT::widen(p[0]);
 #pragma unroll
     for (int r = 1; r < kMaxRanks; r++) {
       if (r < a.nranks) PT::combine(acc, p[r], op);
     }
-    st128(reinterpret_cast<char*>(out) + v * 16, PT::narrow(acc));
-  }
-  for (size_t i = tailStart + tid; i < count; i += nthreads) {
-    T acc = reinterpret_cast<const T*>(static_cast<const char*>(stage.p[0]) + stageOff)[i];
-    for (int r = 1; r < a.nranks; r++) {
-      acc = PT::combineOne(acc, reinterpret_cast<const T*>(static_cast<const char*>(stage.p[r]) + stageOff)[i], op);
-    }
-    out[i] = acc;
+    if (scale != 1.0f) PT::scale(acc, scale);
+    storeLocalGroup(out, extra, g, count, outAligned && extraAligned, PT::narrow(acc));
   }
   retire(a, 1, 1);
 }
@@ -150,19 +337,79 @@ __device__ __forceinline__ void shareOf(size_t n, int parts, int r, size_t& begi
   end = begin + base + (static_cast<size_t>(r) < rem ? 1 : 0);
 }
 
+// Multi-pointer prologue: fold the extra local pointers into `mine`, share by share, with
+// the element -> (CTA, thread) mapping of the exchange phase (so the CTA that will read a
+// peer's element is the one that is barrier-paired with the CTA that folded it).
+template <typename T>
+__device__ __forceinline__ void foldLocalShares(char* mine, const LocalPtrs& extra, size_t nvec, size_t count, int P,
+                                                DevOp op, size_t tid, size_t nthreads) {
+  using PT = PackTraits<T>;
+  for (int r = 0; r < P; r++) {
+    size_t vb, ve;
+    shareOf(nvec, P, r, vb, ve);
+    for (size_t v = vb + tid; v < ve; v += nthreads) {
+      typename PT::AccPack acc = PT::widen(ld128_stream(mine + v * 16));
+      for (int k = 0; k < extra.n; k++) PT::combine(acc, ld128_stream(static_cast<const char*>(extra.p[k]) + v * 16), op);
+      st128(mine + v * 16, PT::narrow(acc));
+    }
+    const size_t tailStart = nvec * PT::kElems;
+    size_t tb, te;
+    shareOf(count - tailStart, P, r, tb, te);
+    for (size_t i = tailStart + tb + tid; i < tailStart + te; i += nthreads) {
+      T acc = reinterpret_cast<T*>(mine)[i];
+      for (int k = 0; k < extra.n; k++) acc = PT::combineOne(acc, static_cast<const T*>(extra.p[k])[i], op);
+      reinterpret_cast<T*>(mine)[i] = acc;
+    }
+  }
+}
+
+// Multi-pointer epilogue: copy the result from `mine` to the extra local pointers (same mapping).
+template <typename T>
+__device__ __forceinline__ void fanOutLocalShares(const char* mine, const LocalPtrs& extra, size_t nvec, size_t count,
+                                                  int P, size_t tid, size_t nthreads) {
+  using PT = PackTraits<T>;
+  for (int r = 0; r < P; r++) {
+    size_t vb, ve;
+    shareOf(nvec, P, r, vb, ve);
+    for (size_t v = vb + tid; v < ve; v += nthreads) {
+      const Pack16 p = ld128(mine + v * 16);
+      for (int k = 0; k < extra.n; k++) st128_stream(static_cast<char*>(extra.p[k]) + v * 16, p);
+    }
+    const size_t tailStart = nvec * PT::kElems;
+    size_t tb, te;
+    shareOf(count - tailStart, P, r, tb, te);
+    for (size_t i = tailStart + tb + tid; i < tailStart + te; i += nthreads) {
+      const T x = reinterpret_cast<const T*>(mine)[i];
+      for (int k = 0; k < extra.n; k++) static_cast<T*>(extra.p[k])[i] = x;
+    }
+  }
+}
+
 template <typename T, int NR, int UNROLL>
 __global__ void __launch_bounds__(kThreads)
-twoShotAllreduceKernel(CommArgs a, PeerPtrs bufs, size_t count, DevOp op, bool vectorOk) {
+twoShotAllreduceKernel(CommArgs a, PeerPtrs bufs, size_t count, DevOp op, float scale, bool vectorOk, LocalPtrs extra) {
   using PT = PackTraits<T>;
   const int P = NR > 0 ? NR : a.nranks;
   const uint32_t e = loadEpoch(a);
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
-
-  // Everybody's kernel has started => everybody's input is final.
-  blockBarrier<false>(a, e + 1);
-
   const size_t nvec = vectorOk ? count / PT::kElems : 0;
+  char* mine = static_cast<char*>(bufs.p[a.rank]);
+
+  // Everybody's kernel has started => everybody's input is final. With several local
+  // pointers the fold happens first and the barrier also publishes it.
+  bool ok;
+  if (extra.n > 0) {
+    foldLocalShares<T>(mine, extra, nvec, count, P, op, tid, nthreads);
+    ok = blockBarrier<true>(a, e + 1);
+  } else {
+    ok = blockBarrier<false>(a, e + 1);
+  }
+  if (!ok) {
+    retire(a, 2, 0);
+    return;
+  }
+
   size_t vb, ve;
   shareOf(nvec, P, a.rank, vb, ve);
 
@@ -195,6 +442,7 @@ twoShotAllreduceKernel(CommArgs a, PeerPtrs bufs, size_t count, DevOp op, bool v
         for (int i = 1; i < kSlots; i++) {
           if (i < P) PT::combine(acc, p[u][i], op);
         }
+        if (scale != 1.0f) PT::scale(acc, scale);
         const Pack16 res = PT::narrow(acc);
 #pragma unroll
         for (int i = 0; i < kSlots; i++) {
@@ -213,28 +461,49 @@ twoShotAllreduceKernel(CommArgs a, PeerPtrs bufs, size_t count, DevOp op, bool v
     for (size_t i = tailStart + tb + tid; i < tailStart + te; i += nthreads) {
       T acc = static_cast<const T*>(bufs.p[0])[i];
       for (int r = 1; r < P; r++) acc = PT::combineOne(acc, static_cast<const T*>(bufs.p[r])[i], op);
+      if (scale != 1.0f) acc = PT::scaleOne(acc, scale);
       for (int r = 0; r < P; r++) static_cast<T*>(bufs.p[r])[i] = acc;
     }
   }
 
   // All my stores have landed everywhere and nobody still reads my buffer.
-  blockBarrier(a, e + 2);
+  if (blockBarrier(a, e + 2) && extra.n > 0) fanOutLocalShares<T>(mine, extra, nvec, count, P, tid, nthreads);
   retire(a, 2, 0);
 }
 
 // ---- NVLS -----------------------------------------------------------------------------
 
+template <typename T>
+__device__ __forceinline__ Pack16 scalePack(const Pack16& p, float s) {
+  using PT = PackTraits<T>;
+  typename PT::AccPack acc = PT::widen(p);
+  PT::scale(acc, s);
+  return PT::narrow(acc);
+}
+
 template <typename T, int UNROLL>
 __global__ void __launch_bounds__(kThreads)
-nvlsAllreduceKernel(CommArgs a, char* mcBase, PeerPtrs bufs, size_t count) {
+nvlsAllreduceKernel(CommArgs a, char* mcBase, PeerPtrs bufs, size_t count, float scale, LocalPtrs extra) {
   using PT = PackTraits<T>;
+  const int P = a.nranks;
   const uint32_t e = loadEpoch(a);
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
-  blockBarrier<false>(a, e + 1);
   const size_t nvec = count / PT::kElems;
+  char* mine = static_cast<char*>(bufs.p[a.rank]);
+  bool ok;
+  if (extra.n > 0) {
+    foldLocalShares<T>(mine, extra, nvec, count, P, DevOp::SUM, tid, nthreads);
+    ok = blockBarrier<true>(a, e + 1);
+  } else {
+    ok = blockBarrier<false>(a, e + 1);
+  }
+  if (!ok) {
+    retire(a, 2, 0);
+    return;
+  }
   size_t vb, ve;
-  shareOf(nvec, a.nranks, a.rank, vb, ve);
+  shareOf(nvec, P, a.rank, vb, ve);
   for (size_t v0 = vb + tid; v0 < ve; v0 += nthreads * UNROLL) {
     Pack16 r[UNROLL];
 #pragma unroll
@@ -245,15 +514,85 @@ nvlsAllreduceKernel(CommArgs a, char* mcBase, PeerPtrs bufs, size_t count) {
 #pragma unroll
     for (int u = 0; u < UNROLL; u++) {
       const size_t v = v0 + static_cast<size_t>(u) * nthreads;
-      if (v < ve) multimemSt128(mcBase + v * 16, r[u]);
+      if (v < ve) multimemSt128(mcBase + v * 16, scale != 1.0f ? scalePack<T>(r[u], scale) : r[u]);
     }
   }
-  // Sub-pack tail through plain peer pointers (last rank).
-  if (a.rank == a.nranks - 1) {
-    for (size_t i = nvec * PT::kElems + tid; i < count; i += nthreads) {
+  // Sub-pack tail through plain peer pointers, split like the two-shot tail.
+  {
+    const size_t tailStart = nvec * PT::kElems;
+    size_t tb, te;
+    shareOf(count - tailStart, P, a.rank, tb, te);
+    for (size_t i = tailStart + tb + tid; i < tailStart + te; i += nthreads) {
       T acc = static_cast<const T*>(bufs.p[0])[i];
-      for (int r = 1; r < a.nranks; r++) acc = PT::combineOne(acc, static_cast<const T*>(bufs.p[r])[i], DevOp::SUM);
-      for (int r = 0; r < a.nranks; r++) static_cast<T*>(bufs.p[r])[i] = acc;
+      for (int r = 1; r < P; r++) acc = PT::combineOne(acc, static_cast<const T*>(bufs.p[r])[i], DevOp::SUM);
+      if (scale != 1.0f) acc = PT::scaleOne(acc, scale);
+      for (int r = 0; r < P; r++) static_cast<T*>(bufs.p[r])[i] = acc;
+    }
+  }
+  if (blockBarrier(a, e + 2) && extra.n > 0) fanOutLocalShares<T>(mine, extra, nvec, count, P, tid, nthreads);
+  retire(a, 2, 0);
+}
+
+// ---- cast epilogue: out-of-place, output dtype != input dtype --------------------------------
+// Rank r reduces items [share r) of every rank's input (peer loads, or multimem.ld_reduce
+// when `mcIn` is set), scales, rounds ONCE to TO and stores into every rank's output.
+// An item is 8 elements: 32 B of float, 16 B of half / bf16.
+template <typename TI, typename TO>
+__global__ void __launch_bounds__(kThreads)
+castAllreduceKernel(CommArgs a, PeerPtrs ins, char* mcIn, PeerPtrs outs, size_t count, DevOp op, float scale,
+                    bool vectorOk) {
+  using II = Item8<TI>;
+  using OI = Item8<TO>;
+  const int P = a.nranks;
+  const uint32_t e = loadEpoch(a);
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
+  if (!blockBarrier<false>(a, e + 1)) {
+    retire(a, 2, 0);
+    return;
+  }
+  const size_t nitems = vectorOk ? count / 8 : 0;
+  size_t ib, ie;
+  shareOf(nitems, P, a.rank, ib, ie);
+  for (size_t it = ib + tid; it < ie; it += nthreads) {
+    float acc[8];
+    if (mcIn != nullptr) {
+      if constexpr (std::is_same<TI, float>::value) {
+        const Pack16 x = Multimem<float>::ldReduceAdd(mcIn + it * 32), y = Multimem<float>::ldReduceAdd(mcIn + it * 32 + 16);
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+          acc[k] = __uint_as_float(x.w[k]);
+          acc[4 + k] = __uint_as_float(y.w[k]);
+        }
+      } else {
+        const auto w = PackTraits<TI>::widen(Multimem<TI>::ldReduceAdd(mcIn + it * 16));
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = w.v[k];
+      }
+    } else {
+      II::load(static_cast<const char*>(ins.p[a.rank]) + it * II::kBytes, acc);
+      for (int i = 1; i < P; i++) {
+        float x[8];
+        II::load(static_cast<const char*>(ins.p[(a.rank + i) % P]) + it * II::kBytes, x);
+#pragma unroll
+        for (int k = 0; k < 8; k++) acc[k] = applyOp<float>(acc[k], x[k], op);
+      }
+    }
+    if (scale != 1.0f) {
+#pragma unroll
+      for (int k = 0; k < 8; k++) acc[k] *= scale;
+    }
+    for (int i = 0; i < P; i++) OI::store(static_cast<char*>(outs.p[(a.rank + i) % P]) + it * OI::kBytes, acc);
+  }
+  {
+    const size_t tailStart = nitems * 8;
+    size_t tb, te;
+    shareOf(count - tailStart, P, a.rank, tb, te);
+    for (size_t i = tailStart + tb + tid; i < tailStart + te; i += nthreads) {
+      float acc = II::toFloat(static_cast<const TI*>(ins.p[0])[i]);
+      for (int r = 1; r < P; r++) acc = applyOp<float>(acc, II::toFloat(static_cast<const TI*>(ins.p[r])[i]), op);
+      acc *= scale;
+      for (int r = 0; r < P; r++) static_cast<TO*>(outs.p[r])[i] = OI::fromFloat(acc);
     }
   }
   blockBarrier(a, e + 2);
@@ -286,6 +625,44 @@ constexpr bool isHotType() {
   return std::is_same<T, float>::value || std::is_same<T, __half>::value || std::is_same<T, __nv_bfloat16>::value;
 }
 
+template <typename K>
+const void* fn(K kernel) {
+  return reinterpret_cast<const void*>(kernel);
+}
+
+// The instantiation of the two-shot kernel for (T, P, unroll); unroll 0 = default for P.
+template <typename T>
+const void* twoShotFn(int P, int unroll) {
+  if constexpr (isHotType<T>()) {
+    switch (P) {
+      case 2:
+        if (unroll == 2) return fn(twoShotAllreduceKernel<T, 2, 2>);
+        if (unroll == 8) return fn(twoShotAllreduceKernel<T, 2, 8>);
+        return fn(twoShotAllreduceKernel<T, 2, 4>);
+      case 4:
+        if (unroll == 1) return fn(twoShotAllreduceKernel<T, 4, 1>);
+        if (unroll == 4) return fn(twoShotAllreduceKernel<T, 4, 4>);
+        return fn(twoShotAllreduceKernel<T, 4, 2>);
+      case 8:
+        if (unroll == 1) return fn(twoShotAllreduceKernel<T, 8, 1>);
+        return fn(twoShotAllreduceKernel<T, 8, 2>);
+      default: break;
+    }
+  }
+  return fn(twoShotAllreduceKernel<T, 0, 1>);
+}
+
+template <typename T>
+const void* nvlsFn(int unroll) {
+  if (unroll == 2) return fn(nvlsAllreduceKernel<T, 2>);
+  if (unroll == 8) return fn(nvlsAllreduceKernel<T, 8>);
+  return fn(nvlsAllreduceKernel<T, 4>);
+}
+
+void launch(const void* kernel, int blocks, int threads, void** args, cudaStream_t stream) {
+  cudaLaunchKernel(kernel, dim3(static_cast<unsigned>(blocks)), dim3(static_cast<unsigned>(threads)), args, 0, stream);
+}
+
 }  // namespace
 
 // Force-load every kernel of this file. With CUDA's lazy module loading the first
@@ -293,30 +670,38 @@ constexpr bool isHotType() {
 // device is already spinning inside its collective kernel that launch never happens
 // (documented lazy-loading deadlock for kernels that assume concurrency).
 namespace {
-template <typename K>
-void touch(K kernel) {
+void touch(const void* kernel) {
   cudaFuncAttributes attr;
-  cudaFuncGetAttributes(&attr, reinterpret_cast<const void*>(kernel));
+  cudaFuncGetAttributes(&attr, kernel);
 }
 }  // namespace
 
 void preloadAllreduceKernels() {
-  touch(barrierKernel);
+  touch(fn(barrierKernel));
   for (DataType dt : {DataType::INT8, DataType::UINT8, DataType::INT16, DataType::INT32, DataType::UINT32, DataType::INT64,
                       DataType::UINT64, DataType::FLOAT32, DataType::FLOAT64, DataType::FLOAT16, DataType::BFLOAT16}) {
     dispatchType(dt, [&](auto tag) {
       using T = decltype(tag);
-      touch(oneShotAllreduceKernel<T>);
-      touch(oneShotPushAllreduceKernel<T>);
-      touch(twoShotAllreduceKernel<T, 0, 1>);
+      touch(fn(llAllreduceKernel<T, T>));
+      touch(fn(oneShotAllreduceKernel<T>));
+      touch(fn(oneShotPushAllreduceKernel<T>));
+      touch(twoShotFn<T>(0, 0));
       if constexpr (isHotType<T>()) {
-        touch(twoShotAllreduceKernel<T, 2, 4>);
-        touch(twoShotAllreduceKernel<T, 4, 2>);
-        touch(twoShotAllreduceKernel<T, 8, 2>);
-        touch(nvlsAllreduceKernel<T, 4>);
+        for (int P : {2, 4, 8}) {
+          for (int u : {1, 2, 4, 8}) touch(twoShotFn<T>(P, u));
+        }
+        for (int u : {2, 4, 8}) touch(nvlsFn<T>(u));
       }
     });
   }
+  touch(fn(llAllreduceKernel<float, __half>));
+  touch(fn(llAllreduceKernel<float, __nv_bfloat16>));
+  touch(fn(llAllreduceKernel<__half, float>));
+  touch(fn(llAllreduceKernel<__nv_bfloat16, float>));
+  touch(fn(castAllreduceKernel<float, __half>));
+  touch(fn(castAllreduceKernel<float, __nv_bfloat16>));
+  touch(fn(castAllreduceKernel<__half, float>));
+  touch(fn(castAllreduceKernel<__nv_bfloat16, float>));
   cudaGetLastError();
 }
 
@@ -331,56 +716,116 @@ void launchBarrier(const CommArgs& a, cudaStream_t stream) {
   barrierKernel<<<1, 32, 0, stream>>>(a);
 }
 
+bool castSupported(DataType in, DataType out) {
+  if (in == out) return true;
+  const bool in16 = in == DataType::FLOAT16 || in == DataType::BFLOAT16;
+  const bool out16 = out == DataType::FLOAT16 || out == DataType::BFLOAT16;
+  return (in == DataType::FLOAT32 && out16) || (in16 && out == DataType::FLOAT32);
+}
+
+void launchLLAllreduce(const CommArgs& a, const void* in, void* out, size_t count, DataType dt, DataType outDt,
+                       ReduceOp op, float scale, const PeerPtrs& ll, size_t srcStride, size_t parityStride,
+                       const LocalPtrs& extra, int blocks, int threads, cudaStream_t stream) {
+  const DevOp dop = static_cast<DevOp>(op);
+#define GLB_LL(TI, TO)                                                                                              \
+  llAllreduceKernel<TI, TO><<<blocks, threads, 0, stream>>>(a, static_cast<const TI*>(in), static_cast<TO*>(out), \
+                                                           count, dop, scale, ll, srcStride, parityStride, extra)
+  if (dt != outDt) {
+    if (dt == DataType::FLOAT32 && outDt == DataType::FLOAT16) GLB_LL(float, __half);
+    else if (dt == DataType::FLOAT32 && outDt == DataType::BFLOAT16) GLB_LL(float, __nv_bfloat16);
+    else if (dt == DataType::FLOAT16 && outDt == DataType::FLOAT32) GLB_LL(__half, float);
+    else if (dt == DataType::BFLOAT16 && outDt == DataType::FLOAT32) GLB_LL(__nv_bfloat16, float);
+    return;
+  }
+  dispatchType(dt, [&](auto tag) {
+    using T = decltype(tag);
+    GLB_LL(T, T);
+  });
+#undef GLB_LL
+}
+
 void launchOneShotAllreduce(const CommArgs& a, const void* in, void* out, size_t count, DataType dt, ReduceOp op,
-                            const PeerPtrs& stage, size_t halfBytes, int blocks, cudaStream_t stream) {
-  const bool vectorOk = (reinterpret_cast<uintptr_t>(in) % 16 == 0) && (reinterpret_cast<uintptr_t>(out) % 16 == 0);
+                            float scale, const PeerPtrs& stage, size_t halfBytes, const LocalPtrs& extra, int blocks,
+                            cudaStream_t stream) {
   // Push while every rank's copy fits a slot (half / P), else pull.
   const size_t slotBytes = (halfBytes / static_cast<size_t>(a.nranks)) / 16 * 16;
-  const bool push = count * elementSize(dt) <= slotBytes && oneShotPushEnabled();
+  const size_t padded = (count * elementSize(dt) + 15) / 16 * 16;
+  const bool push = padded <= slotBytes && oneShotPushEnabled();
   dispatchType(dt, [&](auto tag) {
     using T = decltype(tag);
     if (push) {
       oneShotPushAllreduceKernel<T><<<blocks, kThreads, 0, stream>>>(a, static_cast<const T*>(in), static_cast<T*>(out),
-                                                                     count, static_cast<DevOp>(op), stage, halfBytes,
-                                                                     slotBytes, vectorOk);
+                                                                     count, static_cast<DevOp>(op), scale, stage,
+                                                                     halfBytes, slotBytes, extra);
     } else {
       oneShotAllreduceKernel<T><<<blocks, kThreads, 0, stream>>>(a, static_cast<const T*>(in), static_cast<T*>(out),
-                                                                 count, static_cast<DevOp>(op), stage, halfBytes,
-                                                                 vectorOk);
+                                                                 count, static_cast<DevOp>(op), scale, stage, halfBytes,
+                                                                 extra);
     }
   });
 }
 
+const void* twoShotKernelFor(DataType dt, int nranks, int unroll) {
+  const void* k = nullptr;
+  dispatchType(dt, [&](auto tag) { k = twoShotFn<decltype(tag)>(nranks, unroll); });
+  return k;
+}
+
+const void* nvlsKernelFor(DataType dt, int unroll) {
+  switch (dt) {
+    case DataType::FLOAT32: return nvlsFn<float>(unroll);
+    case DataType::FLOAT16: return nvlsFn<__half>(unroll);
+    case DataType::BFLOAT16: return nvlsFn<__nv_bfloat16>(unroll);
+    default: return nullptr;
+  }
+}
+
 void launchTwoShotAllreduce(const CommArgs& a, const PeerPtrs& bufs, size_t count, DataType dt, ReduceOp op,
-                            bool vectorOk, int blocks, cudaStream_t stream) {
-  const DevOp dop = static_cast<DevOp>(op);
-  dispatchType(dt, [&](auto tag) {
-    using T = decltype(tag);
-    if constexpr (isHotType<T>()) {
-      switch (a.nranks) {
-        case 2: twoShotAllreduceKernel<T, 2, 4><<<blocks, kThreads, 0, stream>>>(a, bufs, count, dop, vectorOk); return;
-        case 4: twoShotAllreduceKernel<T, 4, 2><<<blocks, kThreads, 0, stream>>>(a, bufs, count, dop, vectorOk); return;
-        case 8: twoShotAllreduceKernel<T, 8, 2><<<blocks, kThreads, 0, stream>>>(a, bufs, count, dop, vectorOk); return;
-        default: break;
-      }
-    }
-    twoShotAllreduceKernel<T, 0, 1><<<blocks, kThreads, 0, stream>>>(a, bufs, count, dop, vectorOk);
-  });
+                            float scale, bool vectorOk, const LocalPtrs& extra, const LaunchCfg& cfg,
+                            cudaStream_t stream) {
+  DevOp dop = static_cast<DevOp>(op);
+  CommArgs ca = a;
+  PeerPtrs pb = bufs;
+  LocalPtrs ex = extra;
+  void* args[] = {&ca, &pb, &count, &dop, &scale, &vectorOk, &ex};
+  launch(twoShotKernelFor(dt, a.nranks, cfg.unroll), cfg.blocks, kThreads, args, stream);
 }
 
 bool nvlsSupports(DataType dt, ReduceOp op) {
   return op == ReduceOp::SUM && (dt == DataType::FLOAT32 || dt == DataType::FLOAT16 || dt == DataType::BFLOAT16);
 }
 
-void launchNvlsAllreduce(const CommArgs& a, void* mcPtr, const PeerPtrs& bufs, size_t count, DataType dt, int blocks,
-                         cudaStream_t stream) {
+void launchNvlsAllreduce(const CommArgs& a, void* mcPtr, const PeerPtrs& bufs, size_t count, DataType dt, float scale,
+                         const LocalPtrs& extra, const LaunchCfg& cfg, cudaStream_t stream) {
+  const void* k = nvlsKernelFor(dt, cfg.unroll);
+  if (k == nullptr) return;
+  CommArgs ca = a;
   char* mc = static_cast<char*>(mcPtr);
-  switch (dt) {
-    case DataType::FLOAT32: nvlsAllreduceKernel<float, 4><<<blocks, kThreads, 0, stream>>>(a, mc, bufs, count); break;
-    case DataType::FLOAT16: nvlsAllreduceKernel<__half, 4><<<blocks, kThreads, 0, stream>>>(a, mc, bufs, count); break;
-    case DataType::BFLOAT16: nvlsAllreduceKernel<__nv_bfloat16, 4><<<blocks, kThreads, 0, stream>>>(a, mc, bufs, count); break;
-    default: break;
-  }
+  PeerPtrs pb = bufs;
+  LocalPtrs ex = extra;
+  void* args[] = {&ca, &mc, &pb, &count, &scale, &ex};
+  launch(k, cfg.blocks, kThreads, args, stream);
+}
+
+const void* castKernelFor(DataType in, DataType out) {
+  if (in == DataType::FLOAT32 && out == DataType::FLOAT16) return fn(castAllreduceKernel<float, __half>);
+  if (in == DataType::FLOAT32 && out == DataType::BFLOAT16) return fn(castAllreduceKernel<float, __nv_bfloat16>);
+  if (in == DataType::FLOAT16 && out == DataType::FLOAT32) return fn(castAllreduceKernel<__half, float>);
+  if (in == DataType::BFLOAT16 && out == DataType::FLOAT32) return fn(castAllreduceKernel<__nv_bfloat16, float>);
+  return nullptr;
+}
+
+void launchCastAllreduce(const CommArgs& a, const PeerPtrs& ins, void* mcIn, const PeerPtrs& outs, size_t count,
+                         DataType dt, DataType outDt, ReduceOp op, float scale, bool vectorOk, int blocks,
+                         cudaStream_t stream) {
+  const void* k = castKernelFor(dt, outDt);
+  if (k == nullptr) return;
+  CommArgs ca = a;
+  PeerPtrs pi = ins, po = outs;
+  char* mc = static_cast<char*>(mcIn);
+  DevOp dop = static_cast<DevOp>(op);
+  void* args[] = {&ca, &pi, &mc, &po, &count, &dop, &scale, &vectorOk};
+  launch(k, blocks, kThreads, args, stream);
 }
 
 }  // namespace cuda

@@ -37,37 +37,70 @@ __device__ __forceinline__ void gridCopyWords(char* dst, const char* src, size_t
   for (size_t i = n * sizeof(W) + tid; i < bytes; i += nthreads) dst[i] = src[i];
 }
 
-// Copy `bytes` from src to dst with the whole grid, using the widest access both
-// pointers are aligned for (16 B packs when `vec`, else 8 / 4 / 2 / 1 bytes).
-__device__ __forceinline__ void gridCopy(char* dst, const char* src, size_t bytes, bool vec, size_t tid,
-                                         size_t nthreads) {
-  const uintptr_t both = reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src);
-  if (vec && both % 16 == 0) {
-    const size_t nvec = bytes / 16;
-    constexpr int U = 4;
-    for (size_t v0 = tid; v0 < nvec; v0 += nthreads * U) {
-      Pack16 p[U];
+// 16 bytes from a source that is only W-byte aligned (W = 8 or 4), as one pack.
+template <typename W>
+__device__ __forceinline__ Pack16 ldPackWords(const char* src) {
+  Pack16 p;
+  W* w = reinterpret_cast<W*>(&p);
 #pragma unroll
-      for (int u = 0; u < U; u++) {
-        const size_t v = v0 + u * nthreads;
-        if (v < nvec) p[u] = ld128_stream(src + v * 16);
-      }
+  for (int i = 0; i < static_cast<int>(16 / sizeof(W)); i++) w[i] = reinterpret_cast<const W*>(src)[i];
+  return p;
+}
+
+template <typename W>
+__device__ __forceinline__ void gridCopyBody(char* dst, const char* src, size_t nvec, size_t tid, size_t nthreads) {
+  constexpr int U = 4;
+  for (size_t v0 = tid; v0 < nvec; v0 += nthreads * U) {
+    Pack16 p[U];
 #pragma unroll
-      for (int u = 0; u < U; u++) {
-        const size_t v = v0 + u * nthreads;
-        if (v < nvec) st128_stream(dst + v * 16, p[u]);
+    for (int u = 0; u < U; u++) {
+      const size_t v = v0 + u * nthreads;
+      if (v < nvec) {
+        if constexpr (sizeof(W) == 16) {
+          p[u] = ld128_stream(src + v * 16);
+        } else {
+          p[u] = ldPackWords<W>(src + v * 16);
+        }
       }
     }
-    for (size_t i = nvec * 16 + tid; i < bytes; i += nthreads) dst[i] = src[i];
-  } else if (both % 8 == 0) {
-    gridCopyWords<unsigned long long>(dst, src, bytes, tid, nthreads);
-  } else if (both % 4 == 0) {
-    gridCopyWords<unsigned int>(dst, src, bytes, tid, nthreads);
-  } else if (both % 2 == 0) {
-    gridCopyWords<unsigned short>(dst, src, bytes, tid, nthreads);
-  } else {
-    for (size_t i = tid; i < bytes; i += nthreads) dst[i] = src[i];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t v = v0 + u * nthreads;
+      if (v < nvec) st128_stream(dst + v * 16, p[u]);
+    }
   }
+}
+
+// Copy `bytes` from src to dst with the whole grid. The DESTINATION side (usually a peer,
+// i.e. NVLink stores) always moves in 128-bit stores: a byte-wise head brings dst to a
+// 16-byte boundary, the body loads with the widest access the (local) source allows at
+// that point (16 / 8 / 4 bytes) and a byte-wise tail finishes. Only sources that are
+// not even 4-byte congruent with the destination fall back to narrow word copies.
+__device__ __forceinline__ void gridCopy(char* dst, const char* src, size_t bytes, bool /*vecHint*/, size_t tid,
+                                         size_t nthreads) {
+  const size_t mis = reinterpret_cast<uintptr_t>(dst) % 16;
+  size_t head = mis ? 16 - mis : 0;
+  if (head > bytes) head = bytes;
+  const uintptr_t srcBody = reinterpret_cast<uintptr_t>(src + head) % 16;
+  if (srcBody % 4 != 0) {
+    const uintptr_t both = reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src);
+    if (both % 2 == 0) {
+      gridCopyWords<unsigned short>(dst, src, bytes, tid, nthreads);
+    } else {
+      for (size_t i = tid; i < bytes; i += nthreads) dst[i] = src[i];
+    }
+    return;
+  }
+  for (size_t i = tid; i < head; i += nthreads) dst[i] = src[i];
+  const size_t nvec = (bytes - head) / 16;
+  if (srcBody == 0) {
+    gridCopyBody<Pack16>(dst + head, src + head, nvec, tid, nthreads);
+  } else if (srcBody % 8 == 0) {
+    gridCopyBody<unsigned long long>(dst + head, src + head, nvec, tid, nthreads);
+  } else {
+    gridCopyBody<unsigned int>(dst + head, src + head, nvec, tid, nthreads);
+  }
+  for (size_t i = head + nvec * 16 + tid; i < bytes; i += nthreads) dst[i] = src[i];
 }
 
 }  // namespace
@@ -83,8 +116,11 @@ broadcastKernel(CommArgs a, PeerPtrs bufs, char* mc, size_t bytes, int root, int
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
   const int P = a.nranks;
-  blockBarrier<false>(a, e + 1);  // every destination may now be overwritten
-  uint32_t used = 2;
+  uint32_t used = mode == 1 ? 3 : 2;
+  if (!blockBarrier<false>(a, e + 1)) {  // every destination may now be overwritten
+    retire(a, used, 0);
+    return;
+  }
   if (mode == 0) {
     if (a.rank == root) {
       const char* src = static_cast<const char*>(bufs.p[root]);
@@ -151,8 +187,10 @@ broadcastKernel(CommArgs a, PeerPtrs bufs, char* mc, size_t bytes, int root, int
         for (int r = 1; r < P; r++) static_cast<char*>(bufs.p[(root + r) % P])[i] = c;
       }
     }
-    blockBarrier(a, e + 2);
-    used = 3;
+    if (!blockBarrier(a, e + 2)) {
+      retire(a, used, 0);
+      return;
+    }
     // Every rank (the root too: nobody else holds its slice) now pushes the slice it
     // owns to all ranks that still miss it, i.e. everyone but itself and the root.
     {
@@ -201,7 +239,10 @@ gatherPushKernel(CommArgs a, const char* __restrict__ in, PeerPtrs outs, char* m
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
   const int P = a.nranks;
-  blockBarrier<false>(a, e + 1);
+  if (!blockBarrier<false>(a, e + 1)) {
+    retire(a, 2, 0);
+    return;
+  }
   const size_t off = va.off[a.rank];
   const size_t len = va.len[a.rank];
   const bool v16 = vec && off % 16 == 0;
@@ -263,7 +304,10 @@ alltoallPushKernel(CommArgs a, const char* __restrict__ in, PeerPtrs outs, VArgs
   // v-variant: publish where I expect each source's chunk; peers read it after the
   // barrier (every CTA writes the same values, so no cross-CTA ordering is needed).
   if (exchange && threadIdx.x < P) a.sig[a.rank]->xchg[threadIdx.x] = myRecv.off[threadIdx.x];
-  blockBarrier(a, e + 1);
+  if (!blockBarrier(a, e + 1)) {
+    retire(a, 2, 0);
+    return;
+  }
   if (onlySrc < 0 || onlySrc == a.rank) {
     // CTAs are dealt to destinations in proportion to the bytes each one gets (the host
     // fills blk.off = first CTA, blk.len = CTA count per destination), so every link is
@@ -335,14 +379,17 @@ struct EArgs {
 
 template <typename T, int NR, int UNROLL>
 __global__ void __launch_bounds__(kThreads)
-reducePullKernel(CommArgs a, PeerPtrs ins, char* mcIn, T* __restrict__ out, EArgs ea, DevOp op, bool vec,
-                 bool useMc) {
+reducePullKernel(CommArgs a, PeerPtrs ins, char* mcIn, T* __restrict__ out, EArgs ea, DevOp op, float scale,
+                 bool vec, bool useMc) {
   using PT = PackTraits<T>;
   const uint32_t e = loadEpoch(a);
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
   const int P = NR > 0 ? NR : a.nranks;
-  blockBarrier<false>(a, e + 1);
+  if (!blockBarrier<false>(a, e + 1)) {
+    retire(a, 2, 0);
+    return;
+  }
   const size_t off = ea.off[a.rank], len = ea.len[a.rank];
   const bool v16 = vec && (off * sizeof(T)) % 16 == 0 && reinterpret_cast<uintptr_t>(out) % 16 == 0;
   const size_t nvec = v16 ? len / PT::kElems : 0;
@@ -361,7 +408,14 @@ reducePullKernel(CommArgs a, PeerPtrs ins, char* mcIn, T* __restrict__ out, EArg
 #pragma unroll
         for (int u = 0; u < U; u++) {
           const size_t v = v0 + u * nthreads;
-          if (v < nvec) st128(reinterpret_cast<char*>(out) + v * 16, r[u]);
+          if (v < nvec) {
+            if (scale != 1.0f) {
+              typename PT::AccPack acc = PT::widen(r[u]);
+              PT::scale(acc, scale);
+              r[u] = PT::narrow(acc);
+            }
+            st128(reinterpret_cast<char*>(out) + v * 16, r[u]);
+          }
         }
       }
     }
@@ -393,6 +447,7 @@ reducePullKernel(CommArgs a, PeerPtrs ins, char* mcIn, T* __restrict__ out, EArg
           for (int i = 1; i < kSlots; i++) {
             if (i < P) PT::combine(acc, p[u][i], op);
           }
+          if (scale != 1.0f) PT::scale(acc, scale);
           st128(reinterpret_cast<char*>(out) + v * 16, PT::narrow(acc));
         }
       }
@@ -401,6 +456,7 @@ reducePullKernel(CommArgs a, PeerPtrs ins, char* mcIn, T* __restrict__ out, EArg
   for (size_t i = nvec * PT::kElems + tid; i < len; i += nthreads) {
     T acc = static_cast<const T*>(ins.p[0])[off + i];
     for (int r = 1; r < P; r++) acc = PT::combineOne(acc, static_cast<const T*>(ins.p[r])[off + i], op);
+    if (scale != 1.0f) acc = PT::scaleOne(acc, scale);
     out[i] = acc;
   }
   blockBarrier(a, e + 2);
@@ -409,24 +465,24 @@ reducePullKernel(CommArgs a, PeerPtrs ins, char* mcIn, T* __restrict__ out, EArg
 
 namespace {
 template <typename T>
-void launchReducePullT(const CommArgs& a, const PeerPtrs& ins, char* mc, void* out, const EArgs& ea, DevOp dop, bool vec,
-                       bool useMc, int blocks, cudaStream_t stream) {
+void launchReducePullT(const CommArgs& a, const PeerPtrs& ins, char* mc, void* out, const EArgs& ea, DevOp dop,
+                       float scale, bool vec, bool useMc, int blocks, cudaStream_t stream) {
   constexpr bool hot = std::is_same<T, float>::value || std::is_same<T, __half>::value ||
                        std::is_same<T, __nv_bfloat16>::value;
   if constexpr (hot) {
     switch (a.nranks) {
-      case 2: reducePullKernel<T, 2, 4><<<blocks, kThreads, 0, stream>>>(a, ins, mc, static_cast<T*>(out), ea, dop, vec, useMc); return;
-      case 4: reducePullKernel<T, 4, 2><<<blocks, kThreads, 0, stream>>>(a, ins, mc, static_cast<T*>(out), ea, dop, vec, useMc); return;
-      case 8: reducePullKernel<T, 8, 2><<<blocks, kThreads, 0, stream>>>(a, ins, mc, static_cast<T*>(out), ea, dop, vec, useMc); return;
+      case 2: reducePullKernel<T, 2, 4><<<blocks, kThreads, 0, stream>>>(a, ins, mc, static_cast<T*>(out), ea, dop, scale, vec, useMc); return;
+      case 4: reducePullKernel<T, 4, 2><<<blocks, kThreads, 0, stream>>>(a, ins, mc, static_cast<T*>(out), ea, dop, scale, vec, useMc); return;
+      case 8: reducePullKernel<T, 8, 2><<<blocks, kThreads, 0, stream>>>(a, ins, mc, static_cast<T*>(out), ea, dop, scale, vec, useMc); return;
       default: break;
     }
   }
-  reducePullKernel<T, 0, 1><<<blocks, kThreads, 0, stream>>>(a, ins, mc, static_cast<T*>(out), ea, dop, vec, useMc);
+  reducePullKernel<T, 0, 1><<<blocks, kThreads, 0, stream>>>(a, ins, mc, static_cast<T*>(out), ea, dop, scale, vec, useMc);
 }
 }  // namespace
 
 void launchReducePull(const CommArgs& a, const PeerPtrs& ins, void* mcIn, void* out, const size_t* elemOff,
-                      const size_t* elemLen, DataType dt, ReduceOp op, bool vec, bool useMc, int blocks,
+                      const size_t* elemLen, DataType dt, ReduceOp op, float scale, bool vec, bool useMc, int blocks,
                       cudaStream_t stream) {
   EArgs ea;
   for (int i = 0; i < kMaxRanks; i++) {
@@ -437,7 +493,7 @@ void launchReducePull(const CommArgs& a, const PeerPtrs& ins, void* mcIn, void* 
   char* mc = static_cast<char*>(mcIn);
 #define GLB_CASE(E, T)                                                              \
   case DataType::E:                                                                 \
-    launchReducePullT<T>(a, ins, mc, out, ea, dop, vec, useMc, blocks, stream);     \
+    launchReducePullT<T>(a, ins, mc, out, ea, dop, scale, vec, useMc, blocks, stream);     \
     break;
   switch (dt) {
     GLB_CASE(INT8, int8_t)
@@ -456,6 +512,82 @@ void launchReducePull(const CommArgs& a, const PeerPtrs& ins, void* mcIn, void* 
 }
 
 
+// ---- small allgather / alltoall without a barrier: flag-in-data lines -------------------------
+// Same protocol and pool region as llAllreduceKernel (every rank hears from every peer in a
+// launch, which is what makes two parity halves sufficient). Payload unit: 8 bytes.
+namespace {
+__device__ __forceinline__ void load8(const char* p, size_t avail, bool aligned, uint32_t& d0, uint32_t& d1) {
+  if (aligned && avail >= 8) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    d0 = v.x;
+    d1 = v.y;
+    return;
+  }
+  unsigned long long w = 0;
+  for (int k = 0; k < 8; k++) {
+    if (static_cast<size_t>(k) < avail) w |= static_cast<unsigned long long>(static_cast<unsigned char>(p[k])) << (8 * k);
+  }
+  d0 = static_cast<uint32_t>(w);
+  d1 = static_cast<uint32_t>(w >> 32);
+}
+__device__ __forceinline__ void store8(char* p, size_t avail, bool aligned, uint32_t d0, uint32_t d1) {
+  if (aligned && avail >= 8) {
+    *reinterpret_cast<uint2*>(p) = make_uint2(d0, d1);
+    return;
+  }
+  const unsigned long long w = static_cast<unsigned long long>(d0) | (static_cast<unsigned long long>(d1) << 32);
+  for (int k = 0; k < 8; k++) {
+    if (static_cast<size_t>(k) < avail) p[k] = static_cast<char>(w >> (8 * k));
+  }
+}
+}  // namespace
+
+__global__ void __launch_bounds__(kThreads)
+llExchangeKernel(CommArgs a, const char* __restrict__ in, char* __restrict__ out, size_t bytes, int mode, PeerPtrs ll,
+                 size_t srcStride, size_t parityStride) {
+  const uint32_t seq = ld_relaxed_sys(&a.sig[a.rank]->llSeq) + 1u;
+  const size_t base = (seq & 1u) * parityStride;
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const int P = a.nranks;
+  const size_t nunits = (bytes + 7) / 8;
+  const size_t items = static_cast<size_t>(P) * nunits;
+  const bool inAligned = reinterpret_cast<uintptr_t>(in) % 8 == 0 && bytes % 8 == 0;
+  const bool outAligned = reinterpret_cast<uintptr_t>(out) % 8 == 0 && bytes % 8 == 0;
+  // send: item = (peer slot i, unit u); peers rotated by rank
+  for (size_t it = tid; it < items; it += nthreads) {
+    const int i = static_cast<int>(it / nunits);
+    const size_t u = it % nunits;
+    const int dst = (a.rank + i) % P;
+    const char* src = in + (mode == 1 ? static_cast<size_t>(dst) * bytes : 0) + u * 8;
+    uint32_t d0, d1;
+    load8(src, bytes - u * 8, inAligned, d0, d1);
+    if (dst == a.rank) {
+      store8(out + static_cast<size_t>(a.rank) * bytes + u * 8, bytes - u * 8, outAligned, d0, d1);
+    } else {
+      llStore(static_cast<char*>(ll.p[dst]) + base + static_cast<size_t>(a.rank) * srcStride + u * 16, d0, d1, seq);
+    }
+  }
+  // receive
+  const char* mine = static_cast<const char*>(ll.p[a.rank]) + base;
+  for (size_t it = tid; it < items; it += nthreads) {
+    const int i = static_cast<int>(it / nunits);
+    const size_t u = it % nunits;
+    const int src = (a.rank + i) % P;
+    if (src == a.rank) continue;
+    uint32_t d0, d1;
+    if (!llLoad(a, mine + static_cast<size_t>(src) * srcStride + u * 16, seq, d0, d1, src)) break;
+    store8(out + static_cast<size_t>(src) * bytes + u * 8, bytes - u * 8, outAligned, d0, d1);
+  }
+  retire(a, 0, 0, 1);
+}
+
+void launchLLExchange(const CommArgs& a, const void* in, void* out, size_t bytes, int mode, const PeerPtrs& ll,
+                      size_t srcStride, size_t parityStride, int blocks, int threads, cudaStream_t stream) {
+  llExchangeKernel<<<blocks, threads, 0, stream>>>(a, static_cast<const char*>(in), static_cast<char*>(out), bytes, mode,
+                                                   ll, srcStride, parityStride);
+}
+
 void preloadCollectiveKernels() {
   auto touch = [](const void* k) {
     cudaFuncAttributes attr;
@@ -464,6 +596,7 @@ void preloadCollectiveKernels() {
   touch(reinterpret_cast<const void*>(broadcastKernel));
   touch(reinterpret_cast<const void*>(gatherPushKernel));
   touch(reinterpret_cast<const void*>(alltoallPushKernel));
+  touch(reinterpret_cast<const void*>(llExchangeKernel));
 #define GLB_TOUCH_RP(T) touch(reinterpret_cast<const void*>(reducePullKernel<T, 0, 1>));
   GLB_TOUCH_RP(int8_t) GLB_TOUCH_RP(uint8_t) GLB_TOUCH_RP(int16_t) GLB_TOUCH_RP(int32_t) GLB_TOUCH_RP(uint32_t)
   GLB_TOUCH_RP(long long) GLB_TOUCH_RP(unsigned long long) GLB_TOUCH_RP(float) GLB_TOUCH_RP(double)

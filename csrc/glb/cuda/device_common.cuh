@@ -15,6 +15,7 @@
 #include <cuda_runtime.h>
 
 #include <cstdint>
+#include <type_traits>
 
 #include "glb/cuda/comm_types.h"
 #include "glb/types.h"
@@ -43,15 +44,75 @@ __device__ __forceinline__ uint32_t ld_relaxed_sys(const uint32_t* p) {
   return v;
 }
 
+__device__ __forceinline__ unsigned long long globalTimerNs() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+
+// ---- failure detection ------------------------------------------------------------
+// The reference bounds every wait with the context timeout and turns a silent peer into an
+// IoException (transport/tcp/unbound_buffer.cc:52-94). The device-side equivalent: a flag
+// wait that exceeds CommArgs::timeoutNs raises the abort word in every rank's pad and in a
+// host-mapped status word, after which every barrier returns false at once and the kernels
+// run to their end without touching anything else. PeerContext::checkHealth() turns the
+// status word into the exception and poisons the context.
+// The slow paths take scalars only: handing `const CommArgs&` (a kernel parameter) to a
+// non-inlined function would force a copy of the whole struct into local memory in every
+// kernel.
+// Returns 0 when the flag arrived, kAbortTimeout when the wait timed out (the local abort
+// word is raised here), kAbortPeer when somebody else had raised it.
+static __device__ __noinline__ uint32_t waitFlagSlow(const uint32_t* flag, uint32_t want, uint32_t* abortWord,
+                                                     unsigned long long timeoutNs) {
+  const unsigned long long t0 = globalTimerNs();
+  uint32_t polls = 0;
+  while (static_cast<int32_t>(ld_acquire_sys(flag) - want) < 0) {
+    if ((++polls & 127u) == 0u) {
+      if (ld_relaxed_sys(abortWord) != 0u) return kAbortPeer;
+      if (timeoutNs != 0ull && globalTimerNs() - t0 > timeoutNs) {
+        atomicCAS(abortWord, 0u, static_cast<uint32_t>(kAbortTimeout));
+        return kAbortTimeout;
+      }
+    }
+  }
+  return 0u;
+}
+
+// After a failed wait: tell every peer (their waits end early instead of running into their
+// own time-out) and the host.
+__device__ __forceinline__ void reportAbort(const CommArgs& a, uint32_t code, int missingPeer) {
+  if (code == kAbortTimeout) {
+    a.sig[a.rank]->abortRank = static_cast<uint32_t>(missingPeer);
+    for (int r = 0; r < a.nranks; r++) {
+      if (r != a.rank) st_relaxed_sys(&a.sig[r]->abort, static_cast<uint32_t>(kAbortPeer));
+    }
+  }
+  if (a.hostStatus != nullptr && ld_relaxed_sys(a.hostStatus) == 0u) {
+    st_relaxed_sys(a.hostStatus, code | (static_cast<uint32_t>(missingPeer) << 8));
+  }
+  __threadfence_system();
+}
+
+// Spin until *flag has reached `want` (wrap-safe). Returns false when the wait was abandoned.
+__device__ __forceinline__ bool waitFlag(const CommArgs& a, const uint32_t* flag, uint32_t want, int peer) {
+  if (static_cast<int32_t>(ld_acquire_sys(flag) - want) >= 0) return true;
+  const uint32_t rc = waitFlagSlow(flag, want, &a.sig[a.rank]->abort, a.timeoutNs);
+  if (rc == 0u) return true;
+  reportAbort(a, rc, peer);
+  return false;
+}
+
 // All CTAs with the same blockIdx on every rank rendezvous. Everything the
 // callers wrote before (including stores into peer memory) is visible to every
 // peer's block after it returns (bar.sync + cumulative release/acquire at .sys).
 // kRelease=false is for the FIRST barrier of a kernel that has not written anything a
 // peer will read: "my kernel has started" needs no fence (the inputs were produced by
 // earlier kernels and are already visible system-wide), which saves a MEMBAR.SYS.
+// Returns false (on every thread of the CTA) when a peer did not show up in time.
 template <bool kRelease = true>
-__device__ __forceinline__ void blockBarrier(const CommArgs& a, uint32_t epoch) {
+__device__ __forceinline__ bool blockBarrier(const CommArgs& a, uint32_t epoch) {
   __syncthreads();
+  int ok = 1;
   if (threadIdx.x < a.nranks) {
     const int peer = threadIdx.x;
     if (kRelease) {
@@ -59,11 +120,9 @@ __device__ __forceinline__ void blockBarrier(const CommArgs& a, uint32_t epoch) 
     } else {
       st_relaxed_sys(&a.sig[peer]->flag[blockIdx.x][a.rank], epoch);
     }
-    const uint32_t* mine = &a.sig[a.rank]->flag[blockIdx.x][peer];
-    while (static_cast<int32_t>(ld_acquire_sys(mine) - epoch) < 0) {
-    }
+    ok = waitFlag(a, &a.sig[a.rank]->flag[blockIdx.x][peer], epoch, peer) ? 1 : 0;
   }
-  __syncthreads();
+  return __syncthreads_and(ok) != 0;
 }
 
 // Read the epoch at kernel entry (all CTAs see the same value: it only changes
@@ -71,7 +130,8 @@ __device__ __forceinline__ void blockBarrier(const CommArgs& a, uint32_t epoch) 
 __device__ __forceinline__ uint32_t loadEpoch(const CommArgs& a) { return ld_relaxed_sys(&a.sig[a.rank]->epoch); }
 
 // Called by every CTA at the very end; the last one publishes the new counters.
-__device__ __forceinline__ void retire(const CommArgs& a, uint32_t barriersUsed, uint32_t stagedLaunch) {
+__device__ __forceinline__ void retire(const CommArgs& a, uint32_t barriersUsed, uint32_t stagedLaunch,
+                                       uint32_t llLaunch = 0) {
   __syncthreads();
   if (threadIdx.x == 0) {
     SignalPad* me = a.sig[a.rank];
@@ -82,8 +142,45 @@ __device__ __forceinline__ void retire(const CommArgs& a, uint32_t barriersUsed,
       me->done = 0;
       me->epoch += barriersUsed;
       me->stageSeq += stagedLaunch;
+      me->llSeq += llLaunch;
     }
   }
+}
+
+// ---- flag-in-data ("LL") lines ------------------------------------------------------
+// A 16-byte line carries 8 bytes of payload and two copies of the launch's sequence
+// number: {d0, seq, d1, seq}. Each 8-byte half is written atomically, so a reader that
+// sees both flags equal to `seq` has both payload words; no barrier and no MEMBAR.SYS on
+// the critical path (one posted store + one poll).
+__device__ __forceinline__ void llStore(void* p, uint32_t d0, uint32_t d1, uint32_t seq) {
+  asm volatile("st.volatile.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(p), "r"(d0), "r"(seq), "r"(d1), "r"(seq) : "memory");
+}
+__device__ __forceinline__ bool llTryLoad(const void* p, uint32_t seq, uint32_t& d0, uint32_t& d1) {
+  uint32_t f0, f1;
+  asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(d0), "=r"(f0), "=r"(d1), "=r"(f1) : "l"(p) : "memory");
+  return f0 == seq && f1 == seq;
+}
+static __device__ __noinline__ uint32_t llLoadSlow(const void* p, uint32_t seq, uint32_t& d0, uint32_t& d1,
+                                                   uint32_t* abortWord, unsigned long long timeoutNs) {
+  const unsigned long long t0 = globalTimerNs();
+  uint32_t polls = 0;
+  while (!llTryLoad(p, seq, d0, d1)) {
+    if ((++polls & 127u) == 0u) {
+      if (ld_relaxed_sys(abortWord) != 0u) return kAbortPeer;
+      if (timeoutNs != 0ull && globalTimerNs() - t0 > timeoutNs) {
+        atomicCAS(abortWord, 0u, static_cast<uint32_t>(kAbortTimeout));
+        return kAbortTimeout;
+      }
+    }
+  }
+  return 0u;
+}
+__device__ __forceinline__ bool llLoad(const CommArgs& a, const void* p, uint32_t seq, uint32_t& d0, uint32_t& d1, int peer) {
+  if (llTryLoad(p, seq, d0, d1)) return true;
+  const uint32_t rc = llLoadSlow(p, seq, d0, d1, &a.sig[a.rank]->abort, a.timeoutNs);
+  if (rc == 0u) return true;
+  reportAbort(a, rc, peer);
+  return false;
 }
 
 // ---- 16-byte packs ----------------------------------------------------------------
@@ -158,6 +255,18 @@ struct PackTraits {
   }
   __device__ static T one(const T* p) { return *p; }
   __device__ static T combineOne(T a, T b, DevOp op) { return applyOp<T>(a, b, op); }
+  // Epilogue: multiply the reduced value (floating types only; the host rejects a scale
+  // on integer buffers).
+  __device__ static void scale(AccPack& a, float s) {
+    if constexpr (std::is_floating_point<T>::value) {
+#pragma unroll
+      for (int i = 0; i < kElems; i++) a.v[i] = static_cast<T>(a.v[i] * s);
+    }
+  }
+  __device__ static T scaleOne(T a, float s) {
+    if constexpr (std::is_floating_point<T>::value) return static_cast<T>(a * s);
+    return a;
+  }
 };
 
 template <>
@@ -196,6 +305,11 @@ struct PackTraits<__half> {
   __device__ static __half combineOne(__half a, __half b, DevOp op) {
     return __float2half_rn(applyOp<float>(__half2float(a), __half2float(b), op));
   }
+  __device__ static void scale(AccPack& a, float s) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) a.v[i] *= s;
+  }
+  __device__ static __half scaleOne(__half a, float s) { return __float2half_rn(__half2float(a) * s); }
 };
 
 template <>
@@ -231,6 +345,78 @@ struct PackTraits<__nv_bfloat16> {
   __device__ static __nv_bfloat16 combineOne(__nv_bfloat16 a, __nv_bfloat16 b, DevOp op) {
     return __float2bfloat16_rn(applyOp<float>(__bfloat162float(a), __bfloat162float(b), op));
   }
+  __device__ static void scale(AccPack& a, float s) {
+#pragma unroll
+    for (int i = 0; i < 8; i++) a.v[i] *= s;
+  }
+  __device__ static __nv_bfloat16 scaleOne(__nv_bfloat16 a, float s) {
+    return __float2bfloat16_rn(__bfloat162float(a) * s);
+  }
+};
+
+// ---- mixed-precision items (cast epilogue) --------------------------------------------
+// Eight consecutive elements of T as fp32 lanes: 2 x 16 B for float, 1 x 16 B for the
+// 16-bit types. Used by the kernels whose output dtype differs from the input dtype
+// (fp32 accumulate -> bf16/fp16 store, or 16-bit inputs -> fp32 result).
+template <typename T>
+struct Item8;
+template <>
+struct Item8<float> {
+  static constexpr int kBytes = 32;
+  __device__ static void load(const void* p, float (&v)[8]) {
+    const Pack16 a = ld128_stream(p), b = ld128_stream(static_cast<const char*>(p) + 16);
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      v[i] = __uint_as_float(a.w[i]);
+      v[4 + i] = __uint_as_float(b.w[i]);
+    }
+  }
+  __device__ static void store(void* p, const float (&v)[8]) {
+    Pack16 a, b;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+      a.w[i] = __float_as_uint(v[i]);
+      b.w[i] = __float_as_uint(v[4 + i]);
+    }
+    st128_stream(p, a);
+    st128_stream(static_cast<char*>(p) + 16, b);
+  }
+  __device__ static float toFloat(float x) { return x; }
+  __device__ static float fromFloat(float x) { return x; }
+};
+template <>
+struct Item8<__half> {
+  static constexpr int kBytes = 16;
+  __device__ static void load(const void* p, float (&v)[8]) {
+    const auto a = PackTraits<__half>::widen(ld128_stream(p));
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = a.v[i];
+  }
+  __device__ static void store(void* p, const float (&v)[8]) {
+    PackTraits<__half>::AccPack a;
+#pragma unroll
+    for (int i = 0; i < 8; i++) a.v[i] = v[i];
+    st128_stream(p, PackTraits<__half>::narrow(a));
+  }
+  __device__ static float toFloat(__half x) { return __half2float(x); }
+  __device__ static __half fromFloat(float x) { return __float2half_rn(x); }
+};
+template <>
+struct Item8<__nv_bfloat16> {
+  static constexpr int kBytes = 16;
+  __device__ static void load(const void* p, float (&v)[8]) {
+    const auto a = PackTraits<__nv_bfloat16>::widen(ld128_stream(p));
+#pragma unroll
+    for (int i = 0; i < 8; i++) v[i] = a.v[i];
+  }
+  __device__ static void store(void* p, const float (&v)[8]) {
+    PackTraits<__nv_bfloat16>::AccPack a;
+#pragma unroll
+    for (int i = 0; i < 8; i++) a.v[i] = v[i];
+    st128_stream(p, PackTraits<__nv_bfloat16>::narrow(a));
+  }
+  __device__ static float toFloat(__nv_bfloat16 x) { return __bfloat162float(x); }
+  __device__ static __nv_bfloat16 fromFloat(float x) { return __float2bfloat16_rn(x); }
 };
 
 // ---- NVLS (multimem) --------------------------------------------------------------

@@ -14,20 +14,43 @@ void preloadAllreduceKernels();
 void preloadCollectiveKernels();
 void preloadScheduleKernels();
 void preloadLocalKernels();
+void preloadPipelineKernels();
+void preloadP2pKernels();
 
-// allreduce_kernels.cu
+// allreduce_kernels.cu ---------------------------------------------------------------------
 void launchBarrier(const CommArgs& a, cudaStream_t stream);
+// Flag-in-data one-shot (no barrier). `ll.p[r]` = LL region of rank r's pool.
+void launchLLAllreduce(const CommArgs& a, const void* in, void* out, size_t count, DataType dt, DataType outDt,
+                       ReduceOp op, float scale, const PeerPtrs& ll, size_t srcStride, size_t parityStride,
+                       const LocalPtrs& extra, int blocks, int threads, cudaStream_t stream);
 void launchOneShotAllreduce(const CommArgs& a, const void* in, void* out, size_t count, DataType dt, ReduceOp op,
-                            const PeerPtrs& stage, size_t halfBytes, int blocks, cudaStream_t stream);
+                            float scale, const PeerPtrs& stage, size_t halfBytes, const LocalPtrs& extra, int blocks,
+                            cudaStream_t stream);
 void launchTwoShotAllreduce(const CommArgs& a, const PeerPtrs& bufs, size_t count, DataType dt, ReduceOp op,
-                            bool vectorOk, int blocks, cudaStream_t stream);
+                            float scale, bool vectorOk, const LocalPtrs& extra, const LaunchCfg& cfg,
+                            cudaStream_t stream);
 bool nvlsSupports(DataType dt, ReduceOp op);
 void setOneShotPush(bool on);  // tuning / A-B testing of the push flavour of one-shot
 bool oneShotPushEnabled();
-void launchNvlsAllreduce(const CommArgs& a, void* mcPtr, const PeerPtrs& bufs, size_t count, DataType dt, int blocks,
+void launchNvlsAllreduce(const CommArgs& a, void* mcPtr, const PeerPtrs& bufs, size_t count, DataType dt, float scale,
+                         const LocalPtrs& extra, const LaunchCfg& cfg, cudaStream_t stream);
+// Output dtype != input dtype (f32 <-> f16/bf16): out-of-place on registered buffers.
+bool castSupported(DataType in, DataType out);
+void launchCastAllreduce(const CommArgs& a, const PeerPtrs& ins, void* mcIn, const PeerPtrs& outs, size_t count,
+                         DataType dt, DataType outDt, ReduceOp op, float scale, bool vectorOk, int blocks,
                          cudaStream_t stream);
+// Kernel entry points (for occupancy queries: grids must stay co-resident).
+const void* twoShotKernelFor(DataType dt, int nranks, int unroll);
+const void* nvlsKernelFor(DataType dt, int unroll);
+const void* castKernelFor(DataType in, DataType out);
 
-// collective_kernels.cu
+// pipeline_kernels.cu — arbitrary pointers through the pool, 3-stage in-kernel pipeline.
+const void* pipelinedKernelFor(DataType dt, bool mc);
+void launchPipelinedAllreduce(const CommArgs& a, const void* in, void* out, size_t count, DataType dt, ReduceOp op,
+                              float scale, const PeerPtrs& stage, void* mcStage, int tileVecs, int exchangeThreads,
+                              const LocalPtrs& extra, int blocks, cudaStream_t stream);
+
+// collective_kernels.cu -----------------------------------------------------------------------
 void launchBroadcast(const CommArgs& a, const PeerPtrs& bufs, void* mc, size_t bytes, int root, int mode, bool vec,
                      int blocks, cudaStream_t stream);
 void launchGatherPush(const CommArgs& a, const void* in, const PeerPtrs& outs, void* mcOut, const size_t* offs,
@@ -36,8 +59,20 @@ void launchAlltoallPush(const CommArgs& a, const void* in, const PeerPtrs& outs,
                         const size_t* sendLen, const size_t* dstOff, const size_t* recvOffTable, int onlySrc,
                         bool vec, int blocks, cudaStream_t stream);
 void launchReducePull(const CommArgs& a, const PeerPtrs& ins, void* mcIn, void* out, const size_t* elemOff,
-                      const size_t* elemLen, DataType dt, ReduceOp op, bool vec, bool useMc, int blocks,
+                      const size_t* elemLen, DataType dt, ReduceOp op, float scale, bool vec, bool useMc, int blocks,
                       cudaStream_t stream);
+// Flag-in-data exchange for small messages (no barrier): mode 0 = allgather (my block to
+// everyone), 1 = alltoall (block j of my input to rank j). `bytes` per block, uniform.
+void launchLLExchange(const CommArgs& a, const void* in, void* out, size_t bytes, int mode, const PeerPtrs& ll,
+                      size_t srcStride, size_t parityStride, int blocks, int threads, cudaStream_t stream);
+
+// p2p_kernels.cu — point-to-point between two ranks through the receiver's mailbox ring.
+// sendBytes == 0 / recvBytes == 0 disables that role; both set = fused send+recv (one launch).
+void launchP2p(const CommArgs& a, const void* sendPtr, size_t sendBytes, int dst, void* recvPtr, size_t recvBytes,
+               int src, const PeerPtrs& mailbox, size_t boxStride, size_t slotBytes, int nslots, int lanes,
+               cudaStream_t stream);
+// One-sided copy between my memory and a peer-mapped pointer (put / get), whole grid.
+void launchPeerCopy(void* dst, const void* src, size_t bytes, int blocks, cudaStream_t stream);
 
 // reduce_kernels.cu — local element-wise ops: dst = dst (op) src, and
 // multi-source reduce / broadcast between buffers visible to one device.
@@ -45,7 +80,14 @@ void launchLocalReduce(void* dst, const void* src, size_t count, DataType dt, Re
 void launchLocalReduceMany(void* dst, const void* const* srcs, int nsrc, size_t count, DataType dt, ReduceOp op,
                            cudaStream_t stream);
 void launchLocalBroadcast(void* const* dsts, int ndst, const void* src, size_t bytes, cudaStream_t stream);
+// Every buffer := scale * reduce(all buffers) in one pass (fused reduce + broadcast).
+void launchLocalAllreduceMany(void* const* bufs, int n, size_t count, DataType dt, ReduceOp op, float scale,
+                              cudaStream_t stream);
 void launchFill(void* dst, size_t count, DataType dt, double start, double stride, cudaStream_t stream);
+// Device-side check of buf[i] == start + stride*i; deviceResult = {mismatch count, min(bad index + 1)}
+// (initialise to {0, ~0ull}).
+void launchVerify(const void* buf, size_t count, DataType dt, double start, double stride, double rtol, double atol,
+                  unsigned long long* deviceResult, cudaStream_t stream);
 void launchSpin(long long cycles, cudaStream_t stream);
 
 }  // namespace cuda

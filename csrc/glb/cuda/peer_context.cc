@@ -15,6 +15,7 @@
 #include "glb/barrier.h"
 #include "glb/common/utils.h"
 #include "glb/cuda/kernels.h"
+#include "glb/cuda/tuning.h"
 
 namespace glb {
 namespace cuda {
@@ -182,16 +183,34 @@ PeerContext::PeerContext(std::shared_ptr<Context> context, int dev, PeerOptions 
   preloadCollectiveKernels();
   preloadScheduleKernels();
   preloadLocalKernels();
+  preloadPipelineKernels();
+  preloadP2pKernels();
+  ensureTuningLoaded();
   fdChannel_ = std::make_unique<FdChannel>(rank);
   exchangeTopology();
 
-  // Symmetric pool: [SignalPad | staging]. The pad is zero-initialised (epoch 0).
-  stageOffset_ = roundUp(sizeof(SignalPad), 4096);
+  // Symmetric pool: [SignalPad | LL lines | p2p mailboxes | staging]. Zero-initialised
+  // (epoch 0, no LL line carries a valid sequence number).
+  opts_.llMaxBytes = roundUp(std::max<size_t>(opts_.llMaxBytes, 1024), 1024);
+  opts_.p2pLanes = std::max(1, std::min(opts_.p2pLanes, kP2pLanes));
+  opts_.p2pSlots = std::max(2, opts_.p2pSlots);
+  opts_.p2pSlotBytes = roundUp(std::max<size_t>(opts_.p2pSlotBytes, 16u * 1024), static_cast<size_t>(opts_.p2pLanes) * 16);
+  llOffset_ = roundUp(sizeof(SignalPad), 4096);
+  llSrcStride_ = opts_.llMaxBytes * 2;  // a 16-byte line carries 8 bytes of payload
+  mailboxOffset_ = llOffset_ + roundUp(2 * llSrcStride_ * static_cast<size_t>(size), 4096);
+  stageOffset_ = mailboxOffset_ + roundUp(mailboxStride() * static_cast<size_t>(size), 4096);
   stageBytes_ = roundUp(opts_.stageBytes, 4096);
   pool_ = allocSymmetric(stageOffset_ + stageBytes_);
   comm_.rank = rank;
   comm_.nranks = size;
   for (int i = 0; i < kMaxRanks; i++) comm_.sig[i] = static_cast<SignalPad*>(i < size ? pool_->peer[i] : nullptr);
+  // Status word the kernels raise when a device-side wait gives up.
+  GLB_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&hostStatus_), 64, cudaHostAllocMapped | cudaHostAllocPortable));
+  *hostStatus_ = 0;
+  GLB_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&hostStatusDev_), hostStatus_, 0));
+  comm_.hostStatus = hostStatusDev_;
+  setTimeout(std::chrono::duration_cast<std::chrono::milliseconds>(context->getTimeout()));
+  GLB_CUDA_CHECK(cudaEventCreateWithFlags(&orderEvent_, cudaEventDisableTiming));
   hostBarrier();
   GLB_INFO(describe());
 }
@@ -199,6 +218,8 @@ PeerContext::PeerContext(std::shared_ptr<Context> context, int dev, PeerOptions 
 PeerContext::~PeerContext() {
   DeviceGuard g(device);
   cudaDeviceSynchronize();
+  if (orderEvent_ != nullptr) cudaEventDestroy(orderEvent_);
+  if (hostStatus_ != nullptr) cudaFreeHost(hostStatus_);
   pool_.reset();
   std::lock_guard<std::mutex> lk(ipcMu_);
   for (auto& kv : ipcCache_) cudaIpcCloseMemHandle(kv.second);
@@ -298,7 +319,20 @@ void PeerContext::exchangeTopology() {
   }
   vmm_ = opts_.useVmm && allVmm && sameHost;
   nvlsPossible_ = opts_.useNvls && vmm_ && allMc && size > 1 && static_cast<int>(uuids.size()) == size;
-  maxBlocks_ = std::max(1, std::min(kMaxBlocks, me.smCount / std::max(1, ranksOnMyDevice_)));
+  // Grids must be identical on every rank (CTA b pairs with CTA b of each peer), so the
+  // co-residency cap uses the most crowded device and the smallest GPU of the job.
+  struct Shape {
+    int32_t ranksOnDevice;
+    int32_t sms;
+  } mineShape{ranksOnMyDevice_, me.smCount};
+  auto shapes = allgatherStruct(mineShape);
+  worstRanksPerDevice_ = 1;
+  minSms_ = me.smCount;
+  for (const auto& sh : shapes) {
+    worstRanksPerDevice_ = std::max(worstRanksPerDevice_, static_cast<int>(sh.ranksOnDevice));
+    minSms_ = std::min(minSms_, static_cast<int>(sh.sms));
+  }
+  maxBlocks_ = std::max(1, std::min(kMaxBlocks, minSms_ / std::max(1, worstRanksPerDevice_)));
 }
 
 std::string PeerContext::describe() const {
@@ -312,6 +346,104 @@ std::string PeerContext::describe() const {
 }
 
 PeerPtrs PeerContext::stagePtrs(size_t byteOffset) const { return pool_->ptrsAt(stageOffset_ + byteOffset); }
+
+PeerPtrs PeerContext::llPtrs() const { return pool_->ptrsAt(llOffset_); }
+
+PeerPtrs PeerContext::mailboxPtrs() const { return pool_->ptrsAt(mailboxOffset_); }
+
+void PeerContext::setTimeout(std::chrono::milliseconds t) {
+  timeout_ = t;
+  long forced = envInt("CUDA_TIMEOUT_MS", -1);
+  if (forced >= 0) timeout_ = std::chrono::milliseconds(forced);
+  comm_.timeoutNs = timeout_.count() > 0 ? static_cast<unsigned long long>(timeout_.count()) * 1000000ull : 0ull;
+}
+
+void PeerContext::checkHealth() {
+  if (!poisoned_) {
+    const uint32_t st = *static_cast<volatile uint32_t*>(hostStatus_);
+    if (st == 0) return;
+    poisoned_ = true;
+    const uint32_t code = st & 0xffu, who = st >> 8;
+    poisonReason_ = code == kAbortTimeout
+                        ? strcat_all("rank ", who, " did not reach a device-side barrier within ", timeout_.count(), " ms")
+                        : strcat_all("a peer aborted a collective (first missing rank: ", who, ")");
+    GLB_ERROR("PeerContext rank ", rank, ": ", poisonReason_, " - the context is unusable from here on");
+  }
+  GLB_THROW_IO_EXCEPTION("CUDA peer context failed: ", poisonReason_);
+}
+
+void PeerContext::synchronize(cudaStream_t stream) {
+  DeviceGuard g(device);
+  GLB_CUDA_CHECK(cudaStreamSynchronize(stream));
+  checkHealth();
+}
+
+void PeerContext::orderStreams(cudaStream_t stream) {
+  if (haveLastStream_ && stream != lastStream_) {
+    cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+    cudaStreamIsCapturing(stream, &cs);
+    if (cs == cudaStreamCaptureStatusNone) {
+      GLB_CUDA_CHECK(cudaEventRecord(orderEvent_, lastStream_));
+      GLB_CUDA_CHECK(cudaStreamWaitEvent(stream, orderEvent_, 0));
+    }
+  }
+  lastStream_ = stream;
+  haveLastStream_ = true;
+}
+
+int PeerContext::coResidentBlocks(const void* kernel, int threads) {
+  std::lock_guard<std::mutex> g(occMu_);
+  auto it = occupancy_.find(kernel);
+  int perSm = 1;
+  if (it != occupancy_.end()) {
+    perSm = it->second;
+  } else {
+    DeviceGuard dg(device);
+    int n = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&n, kernel, threads, 0) == cudaSuccess && n > 0) perSm = n;
+    cudaGetLastError();
+    occupancy_[kernel] = perSm;
+  }
+  return std::max(1, std::min(kMaxBlocks, minSms_ * perSm / std::max(1, worstRanksPerDevice_)));
+}
+
+std::shared_ptr<PeerBuffer> PeerContext::tryAllocMulticastLoopback(size_t bytes, std::string* why) {
+  std::string dummy;
+  std::string& w = why != nullptr ? *why : dummy;
+  if (size != 1) {
+    w = "needs a single-rank context";
+    return nullptr;
+  }
+  if (!vmm_ || !infos_[rank].multicastSupported) {
+    w = "no VMM / multicast support on this device";
+    return nullptr;
+  }
+  try {
+    DeviceGuard g(device);
+    auto b = allocVmm(bytes, true);
+    if (b->mc == nullptr) {
+      w = "the driver refused a one-device multicast object";
+      return nullptr;
+    }
+    return b;
+  } catch (const std::exception& e) {
+    w = e.what();
+    return nullptr;
+  }
+}
+
+CommArgs PeerContext::loopbackComm(int virtualRanks) const {
+  GLB_ENFORCE(virtualRanks >= 1 && virtualRanks <= kMaxRanks, "loopback: 1..", kMaxRanks, " virtual ranks");
+  CommArgs c = comm_;
+  c.rank = 0;
+  c.nranks = virtualRanks;
+  SignalPad* me = static_cast<SignalPad*>(pool_->local);
+  for (int i = 0; i < kMaxRanks; i++) {
+    // sig[i]->flag[b][0] aliases me->flag[b][i]
+    c.sig[i] = i < virtualRanks ? reinterpret_cast<SignalPad*>(reinterpret_cast<uint32_t*>(me) + i) : nullptr;
+  }
+  return c;
+}
 
 void* PeerContext::stageMc(size_t byteOffset) const {
   return pool_->mc ? static_cast<char*>(pool_->mc) + stageOffset_ + byteOffset : nullptr;

@@ -21,6 +21,7 @@
 
 #include <cuda_runtime.h>
 
+#include <chrono>
 #include <map>
 #include <memory>
 #include <mutex>
@@ -50,9 +51,13 @@ struct DeviceInfo {
 };
 
 struct PeerOptions {
-  size_t stageBytes = 64ull << 20;  // staging area for unregistered buffers (per rank)
-  bool useVmm = true;               // try cuMem + fd passing before cudaIpc
-  bool useNvls = true;              // bind symmetric memory to a multicast object when possible
+  size_t stageBytes = 128ull << 20;  // staging area for unregistered buffers (per rank)
+  bool useVmm = true;                // try cuMem + fd passing before cudaIpc
+  bool useNvls = true;               // bind symmetric memory to a multicast object when possible
+  size_t llMaxBytes = 64 * 1024;     // largest message of the flag-in-data (LL) kernels
+  size_t p2pSlotBytes = 512 * 1024;  // one slot of a point-to-point mailbox ring
+  int p2pSlots = 4;                  // slots per (source, destination) ring
+  int p2pLanes = 16;                 // CTAs per direction of a point-to-point transfer
 };
 
 // A buffer that every rank can address: peer[r] is rank r's copy as mapped here.
@@ -99,9 +104,29 @@ class PeerContext : public std::enable_shared_from_this<PeerContext> {
   bool usingVmm() const { return vmm_; }
   bool nvlsAvailable() const { return pool_ && pool_->mc != nullptr; }
   int ranksOnMyDevice() const { return ranksOnMyDevice_; }
-  // Largest grid a collective kernel may use so that all ranks' CTAs are co-resident.
+  // Largest grid a collective kernel may use so that all ranks' CTAs are co-resident
+  // (one CTA per SM, shared between the ranks that live on this device).
   int maxBlocks() const { return maxBlocks_; }
+  // Same, for a specific kernel: SMs x resident CTAs per SM (occupancy at `threads`).
+  int coResidentBlocks(const void* kernel, int threads = kThreads);
   std::string describe() const;
+
+  // ---- failure detection ---------------------------------------------------------------
+  // Device-side waits give up after this long (default: the context's timeout) and the
+  // context is poisoned: checkHealth() — called on entry of every collective and by
+  // synchronize() — throws IoException from then on, like a failed transport pair
+  // (gloo/transport/tcp/unbound_buffer.cc:52-94). Rebuild the context to continue.
+  void setTimeout(std::chrono::milliseconds t);
+  std::chrono::milliseconds timeout() const { return timeout_; }
+  void checkHealth();
+  bool poisoned() const { return poisoned_; }
+  // cudaStreamSynchronize + checkHealth: the place where a dead peer surfaces.
+  void synchronize(cudaStream_t stream);
+
+  // Collectives of one PeerContext share the barrier epoch in the signal pad, so they must
+  // execute one after the other on the device. Calls on the same stream are ordered
+  // already; a call on a different stream is made to wait for the previous one here.
+  void orderStreams(cudaStream_t stream);
 
   // ---- collective calls: every rank, same order ------------------------------------
   std::shared_ptr<PeerBuffer> allocSymmetric(size_t bytes);
@@ -128,6 +153,28 @@ class PeerContext : public std::enable_shared_from_this<PeerContext> {
   PeerPtrs stagePtrs(size_t byteOffset = 0) const;
   void* stageMc(size_t byteOffset = 0) const;
   size_t stageBytes() const { return stageBytes_; }
+  // Flag-in-data region: [parity][source rank][16-byte lines].
+  PeerPtrs llPtrs() const;
+  size_t llSrcStride() const { return llSrcStride_; }
+  size_t llParityStride() const { return llSrcStride_ * static_cast<size_t>(size); }
+  size_t llMaxBytes() const { return opts_.llMaxBytes; }
+  // Point-to-point mailboxes: box[source rank] = p2pSlots x p2pSlotBytes inside every pool.
+  PeerPtrs mailboxPtrs() const;
+  size_t mailboxStride() const { return opts_.p2pSlotBytes * static_cast<size_t>(opts_.p2pSlots); }
+  const PeerOptions& options() const { return opts_; }
+  const PeerBuffer& pool() const { return *pool_; }
+
+  // ---- single-process loopback (profilers, self-test) ----------------------------------
+  // Kernel arguments that make ONE launch play rank 0 of `virtualRanks` ranks: every
+  // virtual peer's pad is this rank's pad shifted by one flag column, so the barrier
+  // flags the kernel posts for its "peers" are exactly the ones it then waits for.
+  // Lets Nsight Compute (which serialises kernels and therefore cannot run two ranks
+  // that wait for each other) profile the P = 2 / 4 / 8 specialisations, and lets the
+  // self-test check them numerically, on one GPU.
+  CommArgs loopbackComm(int virtualRanks) const;
+  // Single-rank contexts only: a symmetric buffer bound to a ONE-device multicast object, so
+  // the multimem (NVLS) kernels can run in loopback. nullptr (+ reason) when unsupported.
+  std::shared_ptr<PeerBuffer> tryAllocMulticastLoopback(size_t bytes, std::string* why);
 
  private:
   uint32_t nextTag() { return 0x7C000000u + (tagSeq_++ & 0xffffffu); }
@@ -147,6 +194,8 @@ class PeerContext : public std::enable_shared_from_this<PeerContext> {
   bool vmm_ = false;
   bool nvlsPossible_ = false;
   int ranksOnMyDevice_ = 1;
+  int worstRanksPerDevice_ = 1;
+  int minSms_ = 1;
   int maxBlocks_ = 1;
   uint32_t tagSeq_ = 0;
   std::unique_ptr<FdChannel> fdChannel_;
@@ -155,7 +204,20 @@ class PeerContext : public std::enable_shared_from_this<PeerContext> {
   std::vector<std::weak_ptr<PeerBuffer>> symmetric_;  // live allocSymmetric() results
   size_t stageOffset_ = 0;
   size_t stageBytes_ = 0;
+  size_t llOffset_ = 0;
+  size_t llSrcStride_ = 0;
+  size_t mailboxOffset_ = 0;
   CommArgs comm_;
+  uint32_t* hostStatus_ = nullptr;     // pinned + mapped: written by kernels that give up
+  uint32_t* hostStatusDev_ = nullptr;  // device alias of hostStatus_
+  std::chrono::milliseconds timeout_{0};
+  bool poisoned_ = false;
+  std::string poisonReason_;
+  cudaStream_t lastStream_ = nullptr;
+  bool haveLastStream_ = false;
+  cudaEvent_t orderEvent_ = nullptr;
+  std::mutex occMu_;
+  std::map<const void*, int> occupancy_;
   // cudaIpc mappings are per (peer, allocation): cache them, opening twice is an error.
   std::mutex ipcMu_;
   std::map<std::pair<int, std::string>, void*> ipcCache_;

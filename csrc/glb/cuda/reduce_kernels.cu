@@ -4,7 +4,9 @@
 //                     for fp16/bf16, size_t counts, grid sized to the SM count.
 //   localReduceMany   dst = reduce(srcs[0..n)) in one pass (multi-pointer local reduce:
 //                     srcs may live on peer devices of the same process).
+//   localAllreduceMany every buffer := scale * reduce(all buffers), one pass (fused reduce+broadcast).
 //   localBroadcast    copy src to n destinations in one pass.
+//   verify            whole-buffer closed-form check on the device (bench / smoke).
 //   fill / spin       test helpers (pattern fill; delay kernel that surfaces
 //                     missing stream synchronisation).
 // Parity: gloo/cuda.cu:274-407 (K1-K5), cuda_private.cu:38-61 (K6),
@@ -45,6 +47,73 @@ localReduceManyKernel(T* __restrict__ dst, SrcPtrs srcs, int nsrc, size_t count,
     for (int s = 1; s < nsrc; s++) acc = PT::combineOne(acc, static_cast<const T*>(srcs.p[s])[i], op);
     dst[i] = acc;
   }
+}
+
+// Fused local allreduce: every one of the n buffers ends up holding scale * reduce(all n),
+// in ONE pass (n reads + n writes per element). This is the whole step when a job has a
+// single rank with several local pointers (CudaAllreduce* with ptrs.size() > 1, size == 1,
+// and CudaAllreduceLocal): previously a reduce pass followed by a broadcast pass.
+template <typename T>
+__global__ void __launch_bounds__(kLocalThreads)
+localAllreduceManyKernel(DstPtrs bufs, int n, size_t count, DevOp op, float scale, bool vectorOk) {
+  using PT = PackTraits<T>;
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t nvec = vectorOk ? count / PT::kElems : 0;
+  constexpr int U = 2;
+  for (size_t v0 = tid; v0 < nvec; v0 += nthreads * U) {
+    typename PT::AccPack acc[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t v = v0 + u * nthreads;
+      if (v < nvec) {
+        acc[u] = PT::widen(ld128_stream(static_cast<const char*>(bufs.p[0]) + v * 16));
+        for (int s = 1; s < n; s++) PT::combine(acc[u], ld128_stream(static_cast<const char*>(bufs.p[s]) + v * 16), op);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t v = v0 + u * nthreads;
+      if (v < nvec) {
+        if (scale != 1.0f) PT::scale(acc[u], scale);
+        const Pack16 r = PT::narrow(acc[u]);
+        for (int s = 0; s < n; s++) st128_stream(static_cast<char*>(bufs.p[s]) + v * 16, r);
+      }
+    }
+  }
+  for (size_t i = nvec * PT::kElems + tid; i < count; i += nthreads) {
+    T acc = static_cast<const T*>(bufs.p[0])[i];
+    for (int s = 1; s < n; s++) acc = PT::combineOne(acc, static_cast<const T*>(bufs.p[s])[i], op);
+    if (scale != 1.0f) acc = PT::scaleOne(acc, scale);
+    for (int s = 0; s < n; s++) static_cast<T*>(bufs.p[s])[i] = acc;
+  }
+}
+
+// Whole-buffer check against the closed form start + stride * i (evaluated in fp64, like
+// fillKernel): counts elements outside rtol/atol and remembers the first offender.
+template <typename T>
+__global__ void verifyKernel(const T* buf, size_t count, double start, double stride, double rtol, double atol,
+                             unsigned long long* result /* [0]=mismatches, [1]=first bad index + 1 */) {
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
+  unsigned long long bad = 0;
+  for (size_t i = tid; i < count; i += nthreads) {
+    const double want = start + stride * static_cast<double>(i);
+    double got;
+    if constexpr (std::is_same<T, __half>::value) {
+      got = static_cast<double>(__half2float(buf[i]));
+    } else if constexpr (std::is_same<T, __nv_bfloat16>::value) {
+      got = static_cast<double>(__bfloat162float(buf[i]));
+    } else {
+      got = static_cast<double>(buf[i]);
+    }
+    const double err = fabs(got - want);
+    if (!(err <= atol + rtol * fabs(want))) {
+      bad++;
+      atomicMin(&result[1], static_cast<unsigned long long>(i) + 1ull);
+    }
+  }
+  if (bad) atomicAdd(&result[0], bad);
 }
 
 __global__ void __launch_bounds__(kLocalThreads)
@@ -131,6 +200,32 @@ void launchLocalReduceMany(void* dst, const void* const* srcs, int nsrc, size_t 
   });
 }
 
+void launchLocalAllreduceMany(void* const* bufs, int n, size_t count, DataType dt, ReduceOp op, float scale,
+                              cudaStream_t stream) {
+  if (count == 0 || n == 0) return;
+  DstPtrs bp;
+  bool vectorOk = true;
+  for (int i = 0; i < n && i < kMaxSrcs; i++) {
+    bp.p[i] = bufs[i];
+    vectorOk = vectorOk && aligned16(bufs[i]);
+  }
+  dispatchType(dt, [&](auto tag) {
+    using T = decltype(tag);
+    const int grid = gridFor(count / PackTraits<T>::kElems / 2 + 1, kLocalThreads);
+    localAllreduceManyKernel<T><<<grid, kLocalThreads, 0, stream>>>(bp, n, count, static_cast<DevOp>(op), scale, vectorOk);
+  });
+}
+
+void launchVerify(const void* buf, size_t count, DataType dt, double start, double stride, double rtol, double atol,
+                  unsigned long long* deviceResult, cudaStream_t stream) {
+  if (count == 0) return;
+  dispatchType(dt, [&](auto tag) {
+    using T = decltype(tag);
+    verifyKernel<T><<<gridFor(count, 256), 256, 0, stream>>>(static_cast<const T*>(buf), count, start, stride, rtol,
+                                                             atol, deviceResult);
+  });
+}
+
 void launchLocalReduce(void* dst, const void* src, size_t count, DataType dt, ReduceOp op, cudaStream_t stream) {
   const void* srcs[2] = {dst, src};
   launchLocalReduceMany(dst, srcs, 2, count, dt, op, stream);
@@ -168,6 +263,8 @@ void preloadLocalKernels() {
     dispatchType(dt, [&](auto tag) {
       using T = decltype(tag);
       touch(reinterpret_cast<const void*>(localReduceManyKernel<T>));
+      touch(reinterpret_cast<const void*>(localAllreduceManyKernel<T>));
+      touch(reinterpret_cast<const void*>(verifyKernel<T>));
       touch(reinterpret_cast<const void*>(fillKernel<T>));
     });
   }

@@ -7,8 +7,8 @@ namespace cuda {
 
 template <typename T>
 __global__ void __launch_bounds__(kThreads)
-scheduleKernel(CommArgs a, PeerPtrs bufs, PeerPtrs stage, const SchedStep* __restrict__ table, int nsteps, DevOp op,
-               bool vectorOk) {
+scheduleKernel(CommArgs a, PeerPtrs bufs, PeerPtrs stage, const SchedStep* __restrict__ table, int nsteps,
+               int nbarriers, DevOp op, float scale, size_t count, bool vectorOk) {
   using PT = PackTraits<T>;
   const uint32_t e = loadEpoch(a);
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -23,10 +23,18 @@ scheduleKernel(CommArgs a, PeerPtrs bufs, PeerPtrs stage, const SchedStep* __res
   // ownership that holds no matter how the ranges of consecutive steps differ.
   auto firstOwned = [&](size_t begin) { return begin + (tid + nthreads - begin % nthreads) % nthreads; };
 
+  uint32_t used = 0;
+  bool alive = true;
   for (int s = 0; s < nsteps; s++) {
-    // Step s may read what peers produced in step s-1 (and, for s == 0, their inputs).
-    blockBarrier(a, e + 1 + s);
     const SchedStep st = table[s];
+    // A phase may read what peers produced in the previous phase (and, first, their inputs).
+    if (st.sync) {
+      used++;
+      if (!blockBarrier(a, e + used)) {
+        alive = false;
+        break;
+      }
+    }
     const size_t off = st.off, len = st.len;
     if (len == 0) continue;
     // Vector part: whole 16-byte packs inside [off, off+len) (ranges are pack aligned
@@ -64,12 +72,33 @@ scheduleKernel(CommArgs a, PeerPtrs bufs, PeerPtrs stage, const SchedStep* __res
         local[i] = static_cast<const T*>(srcs.p[st.peers[0]])[i];
       }
     } else {
-      for (size_t pv = firstOwned(pvBegin); pv < pvEnd; pv += nthreads) {
-        typename PT::AccPack acc = PT::widen(ld128(lbase + pv * 16));
-        for (int p = 0; p < st.npeers; p++) {
-          PT::combine(acc, ld128_stream(static_cast<const char*>(srcs.p[st.peers[p]]) + pv * 16), op);
+      constexpr int U = 4;  // independent packs in flight per thread (each: 1 local + npeers remote loads)
+      for (size_t pv0 = firstOwned(pvBegin); pv0 < pvEnd; pv0 += nthreads * U) {
+        typename PT::AccPack acc[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const size_t pv = pv0 + u * nthreads;
+          if (pv < pvEnd) acc[u] = PT::widen(ld128(lbase + pv * 16));
         }
-        st128(lbase + pv * 16, PT::narrow(acc));
+        for (int p = 0; p < st.npeers; p++) {
+          const char* src = static_cast<const char*>(srcs.p[st.peers[p]]);
+          Pack16 x[U];
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const size_t pv = pv0 + u * nthreads;
+            if (pv < pvEnd) x[u] = ld128_stream(src + pv * 16);
+          }
+#pragma unroll
+          for (int u = 0; u < U; u++) {
+            const size_t pv = pv0 + u * nthreads;
+            if (pv < pvEnd) PT::combine(acc[u], x[u], op);
+          }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+          const size_t pv = pv0 + u * nthreads;
+          if (pv < pvEnd) st128(lbase + pv * 16, PT::narrow(acc[u]));
+        }
       }
       for (size_t i = firstOwned(tailBegin); i < tailEnd; i += nthreads) {
         T acc = local[i];
@@ -78,16 +107,30 @@ scheduleKernel(CommArgs a, PeerPtrs bufs, PeerPtrs stage, const SchedStep* __res
       }
     }
   }
-  blockBarrier(a, e + 1 + nsteps);
-  retire(a, nsteps + 1, 0);
+  if (alive) {
+    used++;
+    if (blockBarrier(a, e + used) && scale != 1.0f) {
+      // Fused epilogue: nobody reads my buffer any more; scale my copy in place.
+      const size_t nvec = vectorOk ? count / PT::kElems : 0;
+      char* lbase = reinterpret_cast<char*>(local);
+      for (size_t v = tid; v < nvec; v += nthreads) {
+        typename PT::AccPack acc = PT::widen(ld128(lbase + v * 16));
+        PT::scale(acc, scale);
+        st128(lbase + v * 16, PT::narrow(acc));
+      }
+      for (size_t i = nvec * PT::kElems + tid; i < count; i += nthreads) local[i] = PT::scaleOne(local[i], scale);
+    }
+  }
+  retire(a, static_cast<uint32_t>(nbarriers), 0);
 }
 
 void launchSchedule(const CommArgs& a, const PeerPtrs& bufs, const PeerPtrs& stage, const SchedStep* table,
-                    int nsteps, DataType dt, ReduceOp op, bool vectorOk, int blocks, cudaStream_t stream) {
+                    int nsteps, int nbarriers, DataType dt, ReduceOp op, float scale, size_t count, bool vectorOk,
+                    int blocks, cudaStream_t stream) {
   const DevOp dop = static_cast<DevOp>(op);
 #define GLB_CASE(E, T)                                                                                          \
   case DataType::E:                                                                                             \
-    scheduleKernel<T><<<blocks, kThreads, 0, stream>>>(a, bufs, stage, table, nsteps, dop, vectorOk);           \
+    scheduleKernel<T><<<blocks, kThreads, 0, stream>>>(a, bufs, stage, table, nsteps, nbarriers, dop, scale, count, vectorOk); \
     break;
   switch (dt) {
     GLB_CASE(INT8, int8_t)

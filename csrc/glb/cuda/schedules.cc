@@ -20,6 +20,7 @@ SchedStep makeStep(int mode, Range r, std::initializer_list<int> peers, int from
   s.off = r.off;
   s.len = r.len;
   s.fromStage = fromStage;
+  s.sync = 1;
   for (int p : peers) s.peers[s.npeers++] = p;
   return s;
 }
@@ -133,6 +134,40 @@ Schedule buildHalvingDoublingSchedule(int rank, int size, size_t count, size_t p
     }
   }
   return s;
+}
+
+Schedule buildHalvingDoublingPipelinedSchedule(int rank, int size, size_t count, size_t packElems, int chunks) {
+  Schedule s;
+  s.name = "halving_doubling_pipelined";
+  chunks = std::max(1, chunks);
+  // Too small to cut: every chunk must keep at least one pack per rank.
+  while (chunks > 1 && count / static_cast<size_t>(chunks) < packElems * static_cast<size_t>(size)) chunks--;
+  std::vector<Schedule> per(chunks);
+  size_t depth = 0;
+  for (int c = 0; c < chunks; c++) {
+    const Range r = alignedPart(Range{0, count}, chunks, c, packElems);
+    per[c] = buildHalvingDoublingSchedule(rank, size, r.len, packElems);
+    for (auto& st : per[c].steps) st.off += r.off;
+    depth = std::max(depth, per[c].steps.size());
+  }
+  // Phase t runs step t - c of chunk c for every chunk that has one.
+  for (size_t t = 0; t < depth + chunks - 1; t++) {
+    bool first = true;
+    for (int c = 0; c < chunks; c++) {
+      if (t < static_cast<size_t>(c) || t - c >= per[c].steps.size()) continue;
+      SchedStep st = per[c].steps[t - c];
+      st.sync = first ? 1 : 0;
+      first = false;
+      s.steps.push_back(st);
+    }
+  }
+  return s;
+}
+
+int scheduleBarriers(const Schedule& s) {
+  int n = 1;
+  for (const auto& st : s.steps) n += st.sync ? 1 : 0;
+  return n;
 }
 
 Schedule buildBcubeSchedule(int rank, int size, size_t count, int base, size_t packElems) {

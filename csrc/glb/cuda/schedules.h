@@ -30,6 +30,9 @@ struct SchedStep {
   int npeers;
   int peers[kSchedMaxPeers];
   int fromStage;            // 1: read the peers' pool copy instead of their user buffer
+  int sync;                 // 1: a device barrier separates this step from the previous one;
+                            // 0: it belongs to the same phase (pipelined schedules run the
+                            // steps of several chunks between two barriers)
   unsigned long long off;   // element offset
   unsigned long long len;   // element count
 };
@@ -46,10 +49,18 @@ Schedule buildRingSchedule(int rank, int size, size_t count, size_t packElems);
 Schedule buildRingChunkedSchedule(int rank, int size, size_t count, size_t packElems);
 Schedule buildHalvingDoublingSchedule(int rank, int size, size_t count, size_t packElems);
 Schedule buildBcubeSchedule(int rank, int size, size_t count, int base, size_t packElems);
+// Halving-doubling over `chunks` sub-vectors, skewed by one step each: while chunk c runs
+// step s, chunk c+1 runs step s-1 in the same barrier phase (the reference's
+// CudaAllreduceHalvingDoublingPipelined, cuda_allreduce_halving_doubling.cc:412-455,
+// overlaps the local reduction of one chunk with the transfer of the next the same way).
+Schedule buildHalvingDoublingPipelinedSchedule(int rank, int size, size_t count, size_t packElems, int chunks = 2);
+// Number of device barriers a schedule needs (steps with sync = 1, plus the closing one).
+int scheduleBarriers(const Schedule& s);
 
 // kernels.h-style launcher (defined in schedule_kernels.cu). `table` is device memory.
 void launchSchedule(const CommArgs& a, const PeerPtrs& bufs, const PeerPtrs& stage, const SchedStep* table,
-                    int nsteps, DataType dt, ReduceOp op, bool vectorOk, int blocks, cudaStream_t stream);
+                    int nsteps, int nbarriers, DataType dt, ReduceOp op, float scale, size_t count, bool vectorOk,
+                    int blocks, cudaStream_t stream);
 
 }  // namespace cuda
 }  // namespace glb

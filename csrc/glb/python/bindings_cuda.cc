@@ -7,6 +7,8 @@
 #include "glb/cuda/cuda_util.h"
 #include "glb/cuda/kernels.h"
 #include "glb/cuda/peer_context.h"
+#include "glb/cuda/selftest.h"
+#include "glb/cuda/tuning.h"
 #include "glb/cuda/stream.h"
 
 namespace py = pybind11;
@@ -20,6 +22,22 @@ void registerCudaAlgorithms(py::module_& m);  // bindings_cuda_algorithms.cc
 namespace {
 inline void* P(uintptr_t p) { return reinterpret_cast<void*>(p); }
 inline cudaStream_t S(uintptr_t s) { return reinterpret_cast<cudaStream_t>(s); }
+
+Epilogue makeEpilogue(double scale, int outDtype, const std::vector<uintptr_t>& extra, int blocks, int unroll, int tile) {
+  Epilogue ep;
+  ep.scale = scale;
+  if (outDtype >= 0) {
+    ep.castOutput = true;
+    ep.outDtype = static_cast<DataType>(outDtype);
+  }
+  GLB_ENFORCE_LE(extra.size(), static_cast<size_t>(kMaxLocal), "at most ", kMaxLocal, " extra local pointers");
+  ep.extra.n = static_cast<int>(extra.size());
+  for (size_t i = 0; i < extra.size(); i++) ep.extra.p[i] = P(extra[i]);
+  ep.blocks = blocks;
+  ep.unroll = unroll;
+  ep.tile = tile;
+  return ep;
+}
 }  // namespace
 
 void registerCuda(py::module_& root) {
@@ -85,7 +103,47 @@ void registerCuda(py::module_& root) {
       .def("host_barrier", [](PeerContext& pc) {
         py::gil_scoped_release nogil;
         pc.hostBarrier();
-      });
+      })
+      .def("set_timeout", [](PeerContext& pc, long ms) { pc.setTimeout(std::chrono::milliseconds(ms)); },
+           "Device-side waits give up after this many milliseconds (0 = never).")
+      .def("timeout_ms", [](PeerContext& pc) { return static_cast<long>(pc.timeout().count()); })
+      .def("check_health", &PeerContext::checkHealth, "Raises IoException if a device-side wait has timed out.")
+      .def("poisoned", &PeerContext::poisoned)
+      .def("synchronize", [](PeerContext& pc, uintptr_t stream) {
+        py::gil_scoped_release nogil;
+        pc.synchronize(S(stream));
+      }, py::arg("stream") = 0, "cudaStreamSynchronize + check_health")
+      .def("ll_max_bytes", &PeerContext::llMaxBytes)
+      .def("co_resident_blocks_two_shot", [](PeerContext& pc, int dtype, int unroll) {
+        return pc.coResidentBlocks(twoShotKernelFor(static_cast<DataType>(dtype), pc.size, unroll));
+      })
+      .def("loopback_selftest", [](PeerContext& pc, uintptr_t stream, size_t count) {
+        std::vector<SelfTestResult> res;
+        {
+          py::gil_scoped_release nogil;
+          res = loopbackSelfTest(pc, S(stream), count);
+        }
+        py::list out;
+        for (const auto& r : res) {
+          py::dict d;
+          d["name"] = r.name;
+          d["ok"] = r.ok;
+          d["skipped"] = r.skipped;
+          d["detail"] = r.detail;
+          out.append(d);
+        }
+        return out;
+      }, py::arg("stream") = 0, py::arg("count") = size_t(1) << 18,
+         "Run every hot kernel with 2/4/8 virtual ranks on this GPU (profiler safe) and check the results.")
+      .def("loopback_timeout_test", [](PeerContext& pc, uintptr_t stream, int timeoutMs) {
+        double ms = 0;
+        bool raised;
+        {
+          py::gil_scoped_release nogil;
+          raised = loopbackTimeoutTest(pc, S(stream), timeoutMs, &ms);
+        }
+        return py::make_tuple(raised, ms);
+      }, py::arg("stream") = 0, py::arg("timeout_ms") = 200);
 
   m.def("barrier", [](PeerContext& pc, uintptr_t stream) {
     py::gil_scoped_release nogil;
@@ -93,22 +151,107 @@ void registerCuda(py::module_& root) {
   }, py::arg("pc"), py::arg("stream") = 0);
 
   m.def("allreduce_registered", [](PeerContext& pc, const PeerBuffer& buf, size_t byteOffset, size_t count, int dtype,
-                                   int op, int algo, uintptr_t stream) {
+                                   int op, int algo, uintptr_t stream, double scale, std::vector<uintptr_t> extra,
+                                   int blocks, int unroll, int tile) {
+    const Epilogue ep = makeEpilogue(scale, -1, extra, blocks, unroll, tile);
     py::gil_scoped_release nogil;
     allreduce(pc, buf, byteOffset, count, static_cast<DataType>(dtype), static_cast<ReduceOp>(op),
-              static_cast<AllreduceAlgo>(algo), S(stream));
+              static_cast<AllreduceAlgo>(algo), S(stream), ep);
   }, py::arg("pc"), py::arg("buf"), py::arg("byte_offset"), py::arg("count"), py::arg("dtype"), py::arg("op") = 1,
-     py::arg("algo") = 0, py::arg("stream") = 0);
+     py::arg("algo") = 0, py::arg("stream") = 0, py::arg("scale") = 1.0, py::arg("extra") = std::vector<uintptr_t>(),
+     py::arg("blocks") = 0, py::arg("unroll") = 0, py::arg("tile") = 0);
 
   m.def("allreduce", [](PeerContext& pc, uintptr_t in, uintptr_t out, size_t count, int dtype, int op, int algo,
-                        uintptr_t stream) {
+                        uintptr_t stream, double scale, int outDtype, std::vector<uintptr_t> extra, int blocks,
+                        int tile) {
+    const Epilogue ep = makeEpilogue(scale, outDtype, extra, blocks, 0, tile);
     py::gil_scoped_release nogil;
     allreduce(pc, P(in), P(out), count, static_cast<DataType>(dtype), static_cast<ReduceOp>(op),
-              static_cast<AllreduceAlgo>(algo), S(stream));
+              static_cast<AllreduceAlgo>(algo), S(stream), ep);
   }, py::arg("pc"), py::arg("input"), py::arg("output"), py::arg("count"), py::arg("dtype"), py::arg("op") = 1,
-     py::arg("algo") = 0, py::arg("stream") = 0);
+     py::arg("algo") = 0, py::arg("stream") = 0, py::arg("scale") = 1.0, py::arg("out_dtype") = -1,
+     py::arg("extra") = std::vector<uintptr_t>(), py::arg("blocks") = 0, py::arg("tile") = 0);
 
-  m.def("choose_allreduce", [](const PeerContext& pc, size_t bytes, int dtype, int op, bool registered, bool mc) {
+  m.def("allreduce_cast", [](PeerContext& pc, const PeerBuffer& in, size_t inOff, const PeerBuffer& out, size_t outOff,
+                             size_t count, int dtype, int outDtype, int op, uintptr_t stream, double scale, int blocks) {
+    Epilogue ep;
+    ep.scale = scale;
+    ep.blocks = blocks;
+    py::gil_scoped_release nogil;
+    allreduceCast(pc, in, inOff, out, outOff, count, static_cast<DataType>(dtype), static_cast<DataType>(outDtype),
+                  static_cast<ReduceOp>(op), S(stream), ep);
+  }, py::arg("pc"), py::arg("input"), py::arg("in_offset"), py::arg("output"), py::arg("out_offset"), py::arg("count"),
+     py::arg("dtype"), py::arg("out_dtype"), py::arg("op") = 1, py::arg("stream") = 0, py::arg("scale") = 1.0,
+     py::arg("blocks") = 0);
+
+  m.def("plan_allreduce", [](PeerContext& pc, size_t bytes, int dtype, int op, int kind) {
+    AllreducePlan p = planAllreduce(pc, bytes, static_cast<DataType>(dtype), static_cast<ReduceOp>(op),
+                                    static_cast<BufKind>(kind));
+    py::dict d;
+    d["algo"] = std::string(allreduceAlgoName(p.algo));
+    d["blocks"] = p.cfg.blocks;
+    d["unroll"] = p.cfg.unroll;
+    d["tile"] = p.tile;
+    d["from_table"] = p.fromTable;
+    return d;
+  }, py::arg("pc"), py::arg("bytes"), py::arg("dtype"), py::arg("op") = 1, py::arg("kind") = 0,
+     "What AUTO resolves to (kind: 0 symmetric+multicast, 1 registered, 2 plain pointer).");
+
+  // ---- point to point / one-sided ------------------------------------------------------
+  m.def("send", [](PeerContext& pc, uintptr_t p, size_t bytes, int dst, uintptr_t st) {
+    py::gil_scoped_release nogil;
+    send(pc, P(p), bytes, dst, S(st));
+  }, py::arg("pc"), py::arg("ptr"), py::arg("bytes"), py::arg("dst"), py::arg("stream") = 0);
+  m.def("recv", [](PeerContext& pc, uintptr_t p, size_t bytes, int src, uintptr_t st) {
+    py::gil_scoped_release nogil;
+    recv(pc, P(p), bytes, src, S(st));
+  }, py::arg("pc"), py::arg("ptr"), py::arg("bytes"), py::arg("src"), py::arg("stream") = 0);
+  m.def("sendrecv", [](PeerContext& pc, uintptr_t sp, size_t sbytes, int dst, uintptr_t rp, size_t rbytes, int src,
+                       uintptr_t st) {
+    py::gil_scoped_release nogil;
+    sendrecv(pc, P(sp), sbytes, dst, P(rp), rbytes, src, S(st));
+  }, py::arg("pc"), py::arg("send_ptr"), py::arg("send_bytes"), py::arg("dst"), py::arg("recv_ptr"),
+     py::arg("recv_bytes"), py::arg("src"), py::arg("stream") = 0);
+  m.def("put", [](PeerContext& pc, uintptr_t local, const PeerBuffer& remote, size_t off, size_t bytes, int peer,
+                  uintptr_t st) {
+    py::gil_scoped_release nogil;
+    put(pc, P(local), remote, off, bytes, peer, S(st));
+  }, py::arg("pc"), py::arg("local"), py::arg("remote"), py::arg("remote_offset"), py::arg("bytes"), py::arg("peer"),
+     py::arg("stream") = 0);
+  m.def("get", [](PeerContext& pc, uintptr_t local, const PeerBuffer& remote, size_t off, size_t bytes, int peer,
+                  uintptr_t st) {
+    py::gil_scoped_release nogil;
+    get(pc, P(local), remote, off, bytes, peer, S(st));
+  }, py::arg("pc"), py::arg("local"), py::arg("remote"), py::arg("remote_offset"), py::arg("bytes"), py::arg("peer"),
+     py::arg("stream") = 0);
+
+  // ---- tuning table ---------------------------------------------------------------------
+  m.def("tuning_load_file", [](const std::string& path) {
+    std::string err;
+    int n = TuningTable::get().loadFile(path, &err);
+    if (n < 0) GLB_THROW_INVALID_OPERATION_EXCEPTION("tuning table: ", err);
+    return n;
+  });
+  m.def("tuning_load_string", [](const std::string& text) {
+    std::string err;
+    return TuningTable::get().loadString(text, &err);
+  });
+  m.def("tuning_clear", [] { TuningTable::get().clear(); });
+  m.def("tuning_dump", [] { return TuningTable::get().dump(); });
+  m.def("tuning_source", [] { return TuningTable::get().source(); });
+  m.def("tuning_lookup", [](const std::string& coll, int P, int kind, size_t bytes) -> py::object {
+    const TuneEntry* e = TuningTable::get().lookup(coll, P, static_cast<BufKind>(kind), bytes);
+    if (e == nullptr) return py::none();
+    py::dict d;
+    d["algo"] = e->algo;
+    d["blocks"] = e->blocks;
+    d["unroll"] = e->unroll;
+    d["tile"] = e->tile;
+    d["maxbytes"] = e->maxBytes;
+    return d;
+  });
+
+  m.def("choose_allreduce", [](PeerContext& pc, size_t bytes, int dtype, int op, bool registered, bool mc) {
     return static_cast<int>(chooseAllreduce(pc, bytes, static_cast<DataType>(dtype), static_cast<ReduceOp>(op),
                                             registered, mc));
   });
@@ -134,6 +277,10 @@ void registerCuda(py::module_& root) {
     d["nvls_min_bytes"] = t.nvlsMinBytes;
     d["max_blocks"] = t.maxBlocks;
     d["one_shot_blocks"] = t.oneShotBlocks;
+    d["ll_max_bytes"] = t.llMaxBytes;
+    d["copy_blocks"] = t.copyBlocks;
+    d["pipe_tile"] = t.pipeTile;
+    d["pipe_exchange_threads"] = t.pipeExchangeThreads;
     return d;
   });
   m.def("set_tuning", [](py::dict d) {
@@ -145,6 +292,10 @@ void registerCuda(py::module_& root) {
     if (d.contains("nvls_reduce_scatter")) t.nvlsReduceScatter = d["nvls_reduce_scatter"].cast<bool>();
     if (d.contains("copy_blocks")) t.copyBlocks = d["copy_blocks"].cast<int>();
     if (d.contains("one_shot_push")) setOneShotPush(d["one_shot_push"].cast<bool>());
+    if (d.contains("ll_max_bytes")) t.llMaxBytes = d["ll_max_bytes"].cast<size_t>();
+    if (d.contains("pipe_tile")) t.pipeTile = d["pipe_tile"].cast<int>();
+    if (d.contains("pipe_exchange_threads")) t.pipeExchangeThreads = d["pipe_exchange_threads"].cast<int>();
+    if (d.contains("alltoallv_blocks")) t.alltoallvBlocks = d["alltoallv_blocks"].cast<int>();
   });
 
   // ---- local ops / helpers ------------------------------------------------------------
@@ -166,6 +317,33 @@ void registerCuda(py::module_& root) {
     launchLocalBroadcast(ps.data(), static_cast<int>(ps.size()), P(src), bytes, S(stream));
     GLB_CUDA_CHECK(cudaGetLastError());
   }, py::arg("dsts"), py::arg("src"), py::arg("bytes"), py::arg("stream") = 0);
+  m.def("local_allreduce_many", [](std::vector<uintptr_t> bufs, size_t count, int dtype, int op, double scale,
+                                   uintptr_t stream) {
+    std::vector<void*> ps;
+    for (auto b : bufs) ps.push_back(P(b));
+    launchLocalAllreduceMany(ps.data(), static_cast<int>(ps.size()), count, static_cast<DataType>(dtype),
+                             static_cast<ReduceOp>(op), static_cast<float>(scale), S(stream));
+    noteLaunch();
+    GLB_CUDA_CHECK(cudaGetLastError());
+  }, py::arg("bufs"), py::arg("count"), py::arg("dtype"), py::arg("op") = 1, py::arg("scale") = 1.0, py::arg("stream") = 0,
+     "Every buffer := scale * reduce(all buffers), one kernel, one pass.");
+  // Whole-buffer closed-form check on the device: returns (mismatches, first bad index or -1).
+  m.def("verify", [](uintptr_t buf, size_t count, int dtype, double start, double stride, double rtol, double atol,
+                     uintptr_t stream) {
+    unsigned long long* dres = nullptr;
+    unsigned long long h[2] = {0ull, ~0ull};
+    GLB_CUDA_CHECK(cudaMalloc(reinterpret_cast<void**>(&dres), 16));
+    GLB_CUDA_CHECK(cudaMemcpyAsync(dres, h, 16, cudaMemcpyHostToDevice, S(stream)));
+    launchVerify(P(buf), count, static_cast<DataType>(dtype), start, stride, rtol, atol, dres, S(stream));
+    noteLaunch();
+    cudaError_t e1 = cudaMemcpyAsync(h, dres, 16, cudaMemcpyDeviceToHost, S(stream));
+    cudaError_t e2 = cudaStreamSynchronize(S(stream));
+    cudaFree(dres);
+    GLB_CUDA_CHECK(e1);
+    GLB_CUDA_CHECK(e2);
+    return py::make_tuple(static_cast<size_t>(h[0]), h[1] == ~0ull ? static_cast<long long>(-1) : static_cast<long long>(h[1] - 1));
+  }, py::arg("buf"), py::arg("count"), py::arg("dtype"), py::arg("start") = 0.0, py::arg("stride") = 1.0,
+     py::arg("rtol") = 1e-5, py::arg("atol") = 0.0, py::arg("stream") = 0);
   m.def("fill", [](uintptr_t dst, size_t count, int dtype, double start, double stride, uintptr_t stream) {
     launchFill(P(dst), count, static_cast<DataType>(dtype), start, stride, S(stream));
     GLB_CUDA_CHECK(cudaGetLastError());

@@ -41,7 +41,11 @@ void registerCudaAlgorithms(py::module_& m) {
           py::arg("streams") = std::vector<uintptr_t>(), py::arg("algo") = 0, py::arg("host_workspace") = false)
       .def("run", [](CudaAllreduceCore& c) { py::gil_scoped_release nogil; c.run(); })
       .def("resolved_algo", [](CudaAllreduceCore& c) { return std::string(allreduceAlgoName(c.resolvedAlgo())); })
-      .def("uses_peer_memory", &CudaAllreduceCore::usesPeerMemory);
+      .def("uses_peer_memory", &CudaAllreduceCore::usesPeerMemory)
+      .def("set_scale", &CudaAllreduceCore::setScale, "Fused epilogue: result *= scale inside the collective kernel.")
+      .def("set_launch_shape", &CudaAllreduceCore::setLaunchShape, py::arg("blocks") = 0, py::arg("unroll") = 0,
+           py::arg("tile") = 0)
+      .def("launches_per_run", &CudaAllreduceCore::launchesPerRun);
 
   py::class_<CudaBroadcastCore>(m, "CudaBroadcast")
       .def(py::init([](std::shared_ptr<Context> ctx, std::vector<uintptr_t> p, size_t count, int dtype, int root,
@@ -93,6 +97,7 @@ void registerCudaAlgorithms(py::module_& m) {
     if (name == "ring") sc = buildRingSchedule(rank, size, count, pack);
     else if (name == "ring_chunked") sc = buildRingChunkedSchedule(rank, size, count, pack);
     else if (name == "halving_doubling") sc = buildHalvingDoublingSchedule(rank, size, count, pack);
+    else if (name == "halving_doubling_pipelined") sc = buildHalvingDoublingPipelinedSchedule(rank, size, count, pack, base);
     else if (name == "bcube") sc = buildBcubeSchedule(rank, size, count, base, pack);
     else GLB_THROW_INVALID_OPERATION_EXCEPTION("unknown schedule ", name);
     py::list out;
@@ -102,6 +107,7 @@ void registerCudaAlgorithms(py::module_& m) {
       d["from_stage"] = st.fromStage;
       d["off"] = st.off;
       d["len"] = st.len;
+      d["sync"] = st.sync;
       py::list peers;
       for (int i = 0; i < st.npeers; i++) peers.append(st.peers[i]);
       d["peers"] = peers;
@@ -159,6 +165,14 @@ void registerCudaAlgorithms(py::module_& m) {
     py::gil_scoped_release nogil;
     alltoallv(pc, P(in), sendBytes, P(out), recvBytes, S(st));
   });
+  m.def("alltoall_reg", [](PeerContext& pc, uintptr_t in, const PeerBuffer& out, size_t off, size_t bytes, uintptr_t st) {
+    py::gil_scoped_release nogil;
+    alltoall(pc, P(in), out, off, bytes, S(st));
+  });
+  m.def("alltoall", [](PeerContext& pc, uintptr_t in, uintptr_t out, size_t bytes, uintptr_t st) {
+    py::gil_scoped_release nogil;
+    alltoall(pc, P(in), P(out), bytes, S(st));
+  });
   m.def("scatter_reg", [](PeerContext& pc, uintptr_t in, const PeerBuffer& out, size_t off, size_t bytes, int root,
                           uintptr_t st) {
     py::gil_scoped_release nogil;
@@ -169,15 +183,17 @@ void registerCudaAlgorithms(py::module_& m) {
     scatter(pc, P(in), P(out), bytes, root, S(st));
   });
   m.def("reduce_scatter_reg", [](PeerContext& pc, const PeerBuffer& in, size_t off, uintptr_t out,
-                                 std::vector<size_t> counts, int dtype, int op, uintptr_t st) {
+                                 std::vector<size_t> counts, int dtype, int op, uintptr_t st, double scale) {
     py::gil_scoped_release nogil;
-    reduce_scatter(pc, in, off, P(out), counts, static_cast<DataType>(dtype), static_cast<ReduceOp>(op), S(st));
-  });
+    reduce_scatter(pc, in, off, P(out), counts, static_cast<DataType>(dtype), static_cast<ReduceOp>(op), S(st), scale);
+  }, py::arg("pc"), py::arg("input"), py::arg("offset"), py::arg("output"), py::arg("counts"), py::arg("dtype"),
+     py::arg("op") = 1, py::arg("stream") = 0, py::arg("scale") = 1.0);
   m.def("reduce_scatter", [](PeerContext& pc, uintptr_t in, uintptr_t out, std::vector<size_t> counts, int dtype,
-                             int op, uintptr_t st) {
+                             int op, uintptr_t st, double scale) {
     py::gil_scoped_release nogil;
-    reduce_scatter(pc, P(in), P(out), counts, static_cast<DataType>(dtype), static_cast<ReduceOp>(op), S(st));
-  });
+    reduce_scatter(pc, P(in), P(out), counts, static_cast<DataType>(dtype), static_cast<ReduceOp>(op), S(st), scale);
+  }, py::arg("pc"), py::arg("input"), py::arg("output"), py::arg("counts"), py::arg("dtype"), py::arg("op") = 1,
+     py::arg("stream") = 0, py::arg("scale") = 1.0);
   m.def("reduce_reg", [](PeerContext& pc, const PeerBuffer& in, size_t inOff, const PeerBuffer& out, size_t outOff,
                          size_t count, int dtype, int op, int root, uintptr_t st) {
     py::gil_scoped_release nogil;

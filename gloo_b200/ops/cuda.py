@@ -20,8 +20,15 @@ from ..types import DataType, ReduceOp, describe, element_size
 
 _cu = _C.cuda
 
-ALGOS = {"auto": 0, "one_shot": 1, "two_shot": 2, "nvls": 3, "ring": 10, "ring_chunked": 11,
-         "halving_doubling": 12, "bcube": 13}
+ALGOS = {"auto": 0, "one_shot": 1, "two_shot": 2, "nvls": 3, "ll": 4, "pipelined": 5, "ring": 10, "ring_chunked": 11,
+         "halving_doubling": 12, "bcube": 13, "halving_doubling_pipelined": 14}
+
+
+def _torch_dtype_to_glb(dtype) -> DataType:
+    import torch
+
+    return {torch.float32: DataType.FLOAT32, torch.float16: DataType.FLOAT16, torch.bfloat16: DataType.BFLOAT16,
+            torch.float64: DataType.FLOAT64}[dtype]
 
 
 def _stream(stream) -> int:
@@ -139,19 +146,90 @@ class CudaContext:
     def barrier(self, stream=None):
         _cu.barrier(self.pc, _stream(stream))
 
-    def allreduce(self, tensor, op: ReduceOp = ReduceOp.SUM, algo="auto", out=None, stream=None):
-        """In place on ``tensor`` (or tensor -> out)."""
+    def allreduce(self, tensor, op: ReduceOp = ReduceOp.SUM, algo="auto", out=None, stream=None, scale: float = 1.0,
+                  average: bool = False, extra: Sequence = (), blocks: int = 0, unroll: int = 0, tile: int = 0):
+        """In place on ``tensor`` (or tensor -> out), ONE kernel launch.
+
+        ``scale`` / ``average`` (= 1/size) are applied to the fp32 accumulator inside the
+        collective kernel, before the single rounding to the output dtype. ``out`` may have a
+        different dtype (float32 <-> float16 / bfloat16): registered tensors of any size, plain
+        tensors up to the LL limit. ``extra``: more local tensors of the same shape that are
+        folded into the reduction and overwritten with the result (multi-pointer semantics).
+        ``blocks`` / ``unroll`` / ``tile`` pin the launch shape (tuner)."""
         ptr, n, dt, _ = describe(tensor)
         s = _stream(stream)
-        if out is None:
+        if average:
+            scale = scale / self.size
+        ex = [t.data_ptr() for t in extra]
+        if out is None or out.data_ptr() == ptr:
             buf, off = self.lookup(tensor)
             if buf is not None:
-                _cu.allreduce_registered(self.pc, buf, off, n, int(dt), int(op), _algo(algo), s)
+                _cu.allreduce_registered(self.pc, buf, off, n, int(dt), int(op), _algo(algo), s, scale, ex, blocks,
+                                         unroll, tile)
                 return tensor
-            _cu.allreduce(self.pc, ptr, ptr, n, int(dt), int(op), _algo(algo), s)
+            _cu.allreduce(self.pc, ptr, ptr, n, int(dt), int(op), _algo(algo), s, scale, -1, ex, blocks, tile)
             return tensor
-        _cu.allreduce(self.pc, ptr, out.data_ptr(), n, int(dt), int(op), _algo(algo), s)
+        _, _, odt, _ = describe(out)
+        if odt != dt:
+            ibuf, ioff = self.lookup(tensor)
+            obuf, ooff = self.lookup(out)
+            if ibuf is not None and obuf is not None and not ex:
+                _cu.allreduce_cast(self.pc, ibuf, ioff, obuf, ooff, n, int(dt), int(odt), int(op), s, scale, blocks)
+                return out
+            _cu.allreduce(self.pc, ptr, out.data_ptr(), n, int(dt), int(op), _algo(algo), s, scale, int(odt), ex, blocks,
+                          tile)
+            return out
+        _cu.allreduce(self.pc, ptr, out.data_ptr(), n, int(dt), int(op), _algo(algo), s, scale, -1, ex, blocks, tile)
         return out
+
+    def plan(self, tensor, op: ReduceOp = ReduceOp.SUM) -> dict:
+        """What ``algo="auto"`` resolves to for this tensor (variant + launch shape)."""
+        _, n, dt, _ = describe(tensor)
+        buf, off = self.lookup(tensor)
+        kind = 2 if buf is None else (0 if (buf.has_multicast and off % 16 == 0) else 1)
+        return _cu.plan_allreduce(self.pc, n * element_size(dt), int(dt), int(op), kind)
+
+    # ---- health ---------------------------------------------------------------------------
+    def set_timeout(self, ms: int):
+        """Device-side waits give up after ``ms`` milliseconds (then the context is poisoned)."""
+        self.pc.set_timeout(int(ms))
+
+    def check_health(self):
+        self.pc.check_health()
+
+    def synchronize(self, stream=None):
+        """Wait for the stream and raise ``IoException`` if a peer went missing meanwhile."""
+        self.pc.synchronize(_stream(stream))
+
+    # ---- point to point ---------------------------------------------------------------------
+    def send(self, tensor, dst: int, stream=None):
+        """Stream ``tensor`` to rank ``dst`` over NVLink (matched with its recv in posting order)."""
+        _cu.send(self.pc, tensor.data_ptr(), tensor.numel() * tensor.element_size(), dst, _stream(stream))
+
+    def recv(self, tensor, src: int, stream=None):
+        _cu.recv(self.pc, tensor.data_ptr(), tensor.numel() * tensor.element_size(), src, _stream(stream))
+        return tensor
+
+    def sendrecv(self, send_tensor, dst: int, recv_tensor, src: int, stream=None):
+        """Both directions in one kernel: the call for ring / pipeline exchanges."""
+        _cu.sendrecv(self.pc, send_tensor.data_ptr(), send_tensor.numel() * send_tensor.element_size(), dst,
+                     recv_tensor.data_ptr(), recv_tensor.numel() * recv_tensor.element_size(), src, _stream(stream))
+        return recv_tensor
+
+    def put(self, local, remote, peer: int, remote_offset: int = 0, stream=None):
+        """One-sided: copy ``local`` into rank ``peer``'s copy of the registered tensor ``remote``."""
+        buf, off = self.lookup(remote)
+        assert buf is not None, "put() needs a registered / symmetric remote tensor"
+        _cu.put(self.pc, local.data_ptr(), buf, off + remote_offset * remote.element_size(),
+                local.numel() * local.element_size(), peer, _stream(stream))
+
+    def get(self, local, remote, peer: int, remote_offset: int = 0, stream=None):
+        """One-sided: read rank ``peer``'s copy of the registered tensor ``remote`` into ``local``."""
+        buf, off = self.lookup(remote)
+        assert buf is not None, "get() needs a registered / symmetric remote tensor"
+        _cu.get(self.pc, local.data_ptr(), buf, off + remote_offset * remote.element_size(),
+                local.numel() * local.element_size(), peer, _stream(stream))
+        return local
 
     def broadcast(self, tensor, root: int = 0, stream=None):
         ptr, n, dt, _ = describe(tensor)
@@ -192,8 +270,14 @@ class CudaContext:
         return output
 
     def alltoall(self, output, input, stream=None):
-        per = input.numel() // self.size
-        return self.alltoallv(output, [per] * self.size, input, [per] * self.size, stream)
+        """Fixed-size exchange: chunk j of ``input`` goes to rank j (one size for all ranks)."""
+        per = input.numel() // self.size * input.element_size()
+        buf, off = self.lookup(output)
+        if buf is not None:
+            _cu.alltoall_reg(self.pc, input.data_ptr(), buf, off, per, _stream(stream))
+        else:
+            _cu.alltoall(self.pc, input.data_ptr(), output.data_ptr(), per, _stream(stream))
+        return output
 
     def alltoallv(self, output, out_counts: Sequence[int], input, in_counts: Sequence[int], stream=None):
         es = input.element_size()
@@ -217,16 +301,16 @@ class CudaContext:
         return output
 
     def reduce_scatter(self, output, input, counts: Optional[Sequence[int]] = None, op: ReduceOp = ReduceOp.SUM,
-                       stream=None):
+                       stream=None, scale: float = 1.0):
         ptr, n, dt, _ = describe(input)
         if counts is None:
             base, rem = divmod(n, self.size)
             counts = [base + (1 if r < rem else 0) for r in range(self.size)]
         buf, off = self.lookup(input)
         if buf is not None:
-            _cu.reduce_scatter_reg(self.pc, buf, off, output.data_ptr(), list(counts), int(dt), int(op), _stream(stream))
+            _cu.reduce_scatter_reg(self.pc, buf, off, output.data_ptr(), list(counts), int(dt), int(op), _stream(stream), scale)
         else:
-            _cu.reduce_scatter(self.pc, ptr, output.data_ptr(), list(counts), int(dt), int(op), _stream(stream))
+            _cu.reduce_scatter(self.pc, ptr, output.data_ptr(), list(counts), int(dt), int(op), _stream(stream), scale)
         return output
 
     def reduce(self, output, input, root: int = 0, op: ReduceOp = ReduceOp.SUM, stream=None):
@@ -255,12 +339,22 @@ def _make_allreduce_class(name: str, algo: str):
             self.tensors = tensors
             _, n, dt, _ = describe(tensors[0])
             st = [_stream(s) for s in streams] if streams else []
-            assert variant in ("auto", "one_shot", "two_shot", "nvls")
+            assert variant in ("auto", "one_shot", "two_shot", "nvls", "ll", "pipelined")
             self._impl = _cu.CudaAllreduce(ctx, [t.data_ptr() for t in tensors], n, int(dt), int(op), st,
                                            ALGOS[algo] if literal else ALGOS[variant], host_workspace)
 
         def run(self):
             self._impl.run()
+
+        def set_scale(self, scale: float):
+            """Fused epilogue: the result is multiplied by ``scale`` inside the collective kernel."""
+            self._impl.set_scale(float(scale))
+
+        def set_launch_shape(self, blocks: int = 0, unroll: int = 0, tile: int = 0):
+            self._impl.set_launch_shape(blocks, unroll, tile)
+
+        def launches_per_run(self) -> int:
+            return self._impl.launches_per_run()
 
         def resolved_algo(self) -> str:
             return self._impl.resolved_algo()
@@ -275,7 +369,8 @@ def _make_allreduce_class(name: str, algo: str):
 CudaAllreduceRing = _make_allreduce_class("CudaAllreduceRing", "ring")
 CudaAllreduceRingChunked = _make_allreduce_class("CudaAllreduceRingChunked", "ring_chunked")
 CudaAllreduceHalvingDoubling = _make_allreduce_class("CudaAllreduceHalvingDoubling", "halving_doubling")
-CudaAllreduceHalvingDoublingPipelined = _make_allreduce_class("CudaAllreduceHalvingDoublingPipelined", "halving_doubling")
+CudaAllreduceHalvingDoublingPipelined = _make_allreduce_class("CudaAllreduceHalvingDoublingPipelined",
+                                                              "halving_doubling_pipelined")
 CudaAllreduceBcube = _make_allreduce_class("CudaAllreduceBcube", "bcube")
 
 

@@ -12,9 +12,12 @@ the same door for this library::
 Rendezvous goes through the c10d store handed to the backend (wrapped as a ``gb.Store``), so
 ``env://``, ``tcp://`` and ``file://`` all work. CPU tensors use the host collectives;
 CUDA tensors use ``gloo_b200.ops.cuda.CudaContext`` of their device (created on first use,
-collectively) and are asynchronous on the current stream, like NCCL work. Point-to-point
-``send``/``recv`` on CUDA tensors are staged through host memory (ring exchanges over NVLink
-are ``parallel.RingExchange``).
+collectively) and are asynchronous on the current stream, like NCCL work; ``ReduceOp.AVG``
+is applied inside the collective kernel (fused scale epilogue), not as a second pass.
+Point-to-point ``send``/``recv`` return asynchronous work objects: host tensors go through the
+transport (``wait()`` completes them), CUDA tensors travel over NVLink on dedicated send /
+receive streams (``wait()`` orders the caller's stream after the transfer, as with NCCL), so
+the usual "every rank posts isend, then irecv" pattern cannot deadlock.
 
 Every method mirrors the signature c10d calls on a Python ``ProcessGroup``
 (torch/testing/_internal/distributed/multi_threaded_pg.py is the reference for that).
@@ -72,6 +75,77 @@ def _done(result=None):
     return _create_work_from_future(fut)
 
 
+class _HostP2pWork(dist.Work):
+    """A posted host send / receive: completes in wait() (the transport progresses it in the
+    background), keeps the buffer and the tensors alive until then."""
+
+    def __init__(self, buf, is_send: bool, keep, on_done=None, src: int = -1):
+        super().__init__()
+        self._buf, self._is_send, self._keep, self._on_done, self._src = buf, is_send, keep, on_done, src
+        self._done = False
+
+    def wait(self, timeout=None):
+        if not self._done:
+            if self._is_send:
+                self._buf.wait_send()
+            else:
+                got = self._buf.wait_recv()
+                if got is not None and isinstance(got, int):
+                    self._src = got
+            if self._on_done is not None:
+                self._on_done()
+            self._done = True
+            self._keep = None
+        return True
+
+    def is_completed(self):
+        return self._done
+
+    def is_success(self):
+        return True
+
+    def source_rank(self):
+        self.wait()
+        return self._src
+
+    def _source_rank(self):
+        return self.source_rank()
+
+    def __del__(self):
+        # A posted operation must not outlive its buffer: finish it if the caller dropped the work.
+        try:
+            self.wait()
+        except Exception:  # noqa: BLE001
+            pass
+
+
+class _StreamWork(dist.Work):
+    """A CUDA transfer enqueued on a side stream: wait() makes the caller's stream wait for it."""
+
+    def __init__(self, event, keep, src: int = -1):
+        super().__init__()
+        self._event, self._keep, self._src = event, keep, src
+
+    def wait(self, timeout=None):
+        torch.cuda.current_stream().wait_event(self._event)
+        return True
+
+    def is_completed(self):
+        return self._event.query()
+
+    def is_success(self):
+        return True
+
+    def synchronize(self):
+        self._event.synchronize()
+
+    def source_rank(self):
+        return self._src
+
+    def _source_rank(self):
+        return self._src
+
+
 class _RecvWork(dist.Work):
     """Completed work of a receive; carries the sender's rank for recv-from-any."""
 
@@ -122,6 +196,7 @@ class GlbProcessGroup(dist.ProcessGroup):
         self.ctx.set_timeout(self._timeout_ms)
         self.ctx.connect_full_mesh(_C10dStore(store), device)
         self._cuda: Dict[int, object] = {}
+        self._p2p_streams: Dict[int, tuple] = {}
 
     # ---- plumbing -------------------------------------------------------------------------
     def getBackendName(self):
@@ -146,7 +221,7 @@ class GlbProcessGroup(dist.ProcessGroup):
             # its staging pool: allreduce is cut into pool-sized pieces, the data-movement
             # collectives need the whole payload to fit (GLB_PG_STAGE_MB, default 64 - the measured
             # configuration; raise it for large all_gather / reduce_scatter payloads).
-            stage = int(os.environ.get("GLB_PG_STAGE_MB", "64")) << 20
+            stage = int(os.environ.get("GLB_PG_STAGE_MB", "128")) << 20
             with torch.cuda.device(idx):
                 self._cuda[idx] = gcu.CudaContext(self.ctx, idx, stage_bytes=stage)
         return self._cuda[idx]
@@ -162,11 +237,15 @@ class GlbProcessGroup(dist.ProcessGroup):
         for t in tensors:
             w = self._contig(t)
             if w.is_cuda:
-                self._cc(w).allreduce(w, op=op)
+                # AVG is the kernel's scale epilogue: one launch, no second pass over the data.
+                fused = _is_avg(opts.reduceOp) and w.is_floating_point()
+                self._cc(w).allreduce(w, op=op, average=fused)
+                if _is_avg(opts.reduceOp) and not fused:
+                    w.div_(self._world)
             else:
                 H.allreduce(self.ctx, w, op=op)
-            if _is_avg(opts.reduceOp):
-                w.div_(self._world)
+                if _is_avg(opts.reduceOp):
+                    w.div_(self._world)
             if w is not t:
                 t.copy_(w)
         return _done(tensors)
@@ -214,11 +293,14 @@ class GlbProcessGroup(dist.ProcessGroup):
         out, inp = self._contig(output_tensor), self._contig(input_tensor)
         op = _op(opts.reduceOp)
         if out.is_cuda:
-            self._cc(out).reduce_scatter(out.view(-1), inp.view(-1), op=op)
+            fused = _is_avg(opts.reduceOp) and out.is_floating_point()
+            self._cc(out).reduce_scatter(out.view(-1), inp.view(-1), op=op, scale=1.0 / self._world if fused else 1.0)
+            if _is_avg(opts.reduceOp) and not fused:
+                out.div_(self._world)
         else:
             H.reduce_scatter(self.ctx, out.view(-1), inp.view(-1), op=op)
-        if _is_avg(opts.reduceOp):
-            out.div_(self._world)
+            if _is_avg(opts.reduceOp):
+                out.div_(self._world)
         if out is not output_tensor:
             output_tensor.copy_(out)
         return _done(output_tensor)
@@ -331,36 +413,71 @@ class GlbProcessGroup(dist.ProcessGroup):
         # One ordered stream of messages per (src, dst, tag); the transport matches FIFO per slot.
         return _C.slot_build(_P2P_PREFIX, int(tag) & 0xFFFFFFFF, 0)
 
+    def _side_streams(self, idx: int):
+        """(send stream, recv stream) of a device: p2p kernels wait for their peer on the device,
+        so they must not queue behind each other or behind the caller's compute."""
+        if idx not in self._p2p_streams:
+            from ..ops import cuda as gcu
+
+            self._p2p_streams[idx] = (gcu.new_stream(idx), gcu.new_stream(idx))
+        return self._p2p_streams[idx]
+
+    def _cuda_p2p(self, t, peer: int, is_send: bool):
+        cc = self._cc(t)
+        idx = cc.device
+        side = self._side_streams(idx)[0 if is_send else 1]
+        cur = torch.cuda.current_stream(idx)
+        w = self._contig(t) if is_send else (t if t.is_contiguous() else torch.empty_like(t, memory_format=torch.contiguous_format))
+        side.wait_stream(cur)
+        if is_send:
+            cc.send(w, peer, stream=side)
+        else:
+            cc.recv(w, peer, stream=side)
+            if w is not t:
+                with torch.cuda.stream(side):
+                    t.copy_(w)
+        w.record_stream(side)
+        t.record_stream(side)
+        ev = torch.cuda.Event()
+        ev.record(side)
+        return _StreamWork(ev, (w, t), src=peer if not is_send else -1)
+
     def send(self, tensors, dstRank, tag=0):
+        work = None
         for t in tensors:
+            if t.is_cuda:
+                work = self._cuda_p2p(t.detach(), dstRank, True)
+                continue
             h = self._contig(t).detach()
-            if h.is_cuda:
-                h = h.cpu()
             buf = self.ctx.create_unbound_buffer(h.data_ptr(), h.numel() * h.element_size())
             buf.send(dstRank, self._slot(self._rank, dstRank, tag))
-            buf.wait_send()
-        return _done(None)
+            work = _HostP2pWork(buf, True, (h, t))
+        return work if work is not None else _done(None)
 
     def recv(self, tensors, srcRank, tag=0):
+        work = None
         for t in tensors:
-            h = torch.empty(t.shape, dtype=t.dtype) if (t.is_cuda or not t.is_contiguous()) else t
+            if t.is_cuda:
+                work = self._cuda_p2p(t, srcRank, False)
+                continue
+            h = t if t.is_contiguous() else torch.empty(t.shape, dtype=t.dtype)
             buf = self.ctx.create_unbound_buffer(h.data_ptr(), h.numel() * h.element_size())
             buf.recv(srcRank, self._slot(srcRank, self._rank, tag))
-            buf.wait_recv()
-            if h is not t:
-                t.copy_(h)
-        return _done(None)
+            work = _HostP2pWork(buf, False, (h, t), on_done=(lambda h=h, t=t: t.copy_(h)) if h is not t else None,
+                                src=srcRank)
+        return work if work is not None else _done(None)
 
     def recv_anysource(self, tensors, tag=0):
-        src = -1
+        work = None
         for t in tensors:
-            h = torch.empty(t.shape, dtype=t.dtype) if (t.is_cuda or not t.is_contiguous()) else t
+            if t.is_cuda:
+                raise NotImplementedError("glb backend: recv from any source is a host-transport feature; CUDA tensors "
+                                          "travel over NVLink and match in posting order per peer (as with NCCL)")
+            h = t if t.is_contiguous() else torch.empty(t.shape, dtype=t.dtype)
             buf = self.ctx.create_unbound_buffer(h.data_ptr(), h.numel() * h.element_size())
             buf.recv([r for r in range(self._world) if r != self._rank], self._slot(-1, self._rank, tag))
-            src = buf.wait_recv()
-            if h is not t:
-                t.copy_(h)
-        return _RecvWork(src)
+            work = _HostP2pWork(buf, False, (h, t), on_done=(lambda h=h, t=t: t.copy_(h)) if h is not t else None)
+        return work if work is not None else _RecvWork(-1)
 
     def shutdown(self):
         try:

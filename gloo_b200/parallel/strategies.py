@@ -18,11 +18,18 @@ class _Base:
         self.cc = cuda_ctx
         self.rank, self.size = ctx.rank, ctx.size
 
-    def _allreduce(self, t, op=ReduceOp.SUM):
+    def _allreduce(self, t, op=ReduceOp.SUM, average: bool = False):
+        """Allreduce, optionally averaged. On CUDA the 1/P is the kernel's fused scale epilogue
+        (one launch); on the host it is a second pass."""
         if _is_cuda(t):
-            self.cc.allreduce(t, op=op)
+            fused = average and t.is_floating_point()
+            self.cc.allreduce(t, op=op, average=fused)
+            if average and not fused:
+                t.div_(self.size)
         else:
             H.allreduce(self.ctx, t, op=op)
+            if average:
+                t.div_(self.size) if hasattr(t, "div_") else t.__itruediv__(self.size)
         return t
 
 
@@ -82,9 +89,7 @@ class DataParallel(_Base):
             for g in group:
                 flat[off:off + g.numel()].copy_(g.reshape(-1))
                 off += g.numel()
-            self._allreduce(flat)
-            if average:
-                flat.div_(self.size)
+            self._allreduce(flat, average=average)
             off = 0
             for g in group:
                 g.copy_(flat[off:off + g.numel()].view_as(g))
@@ -103,11 +108,14 @@ class ZeroShard(_Base):
     def reduce_scatter_gradients(self, flat_grad, out_shard, average: bool = True):
         _, _, counts = self.shard_range(flat_grad.numel())
         if _is_cuda(flat_grad):
-            self.cc.reduce_scatter(out_shard, flat_grad, counts)
+            fused = average and flat_grad.is_floating_point()
+            self.cc.reduce_scatter(out_shard, flat_grad, counts, scale=1.0 / self.size if fused else 1.0)
+            if average and not fused:
+                out_shard.div_(self.size)
         else:
             H.reduce_scatter(self.ctx, out_shard, flat_grad, counts)
-        if average:
-            out_shard.div_(self.size) if hasattr(out_shard, "div_") else None
+            if average:
+                out_shard.div_(self.size) if hasattr(out_shard, "div_") else None
         return out_shard
 
     def allgather_parameters(self, flat_param, shard):
@@ -194,9 +202,9 @@ class UlyssesAttention(_Base):
 class RingExchange(_Base):
     """Neighbour exchange for ring attention (KV rotation) and pipeline parallelism.
 
-    CPU tensors go through UnboundBuffer send/recv. CUDA tensors use the alltoallv
-    kernel with a single non-zero destination (a direct NVLink write to the right
-    neighbour), which keeps the rotation a single launch.
+    CPU tensors go through UnboundBuffer send/recv. CUDA tensors use the fused NVLink
+    send+recv kernel (``CudaContext.sendrecv``): one launch streams ``send`` into the right
+    neighbour's mailbox ring while draining what the left neighbour streams into ours.
     """
 
     def rotate(self, send, recv, step: int = 1):
@@ -205,10 +213,7 @@ class RingExchange(_Base):
             recv.copy_(send)
             return recv
         if _is_cuda(send):
-            n = send.numel()
-            sc = [n if j == right else 0 for j in range(self.size)]
-            rc = [n if j == left else 0 for j in range(self.size)]
-            self.cc.alltoallv(recv, rc, send, sc)
+            self.cc.sendrecv(send, right, recv, left)
             return recv
         from ..types import describe
 

@@ -16,3 +16,10 @@ cmake /tmp/refsrc -G Ninja -DCMAKE_BUILD_TYPE=Release -DUSE_CUDA=ON -DGLOO_USE_C
 ninja -j"$(nproc)"
 cp gloo/benchmark/benchmark gloo/benchmark/benchmark_cuda "$HERE/_ref/bin/"
 echo "installed: $HERE/_ref/bin"
+# End-to-end driver (pinned host -> GPU -> stock CudaAllreduceRingChunked::run() -> pinned host)
+# linked against the reference's own, unmodified static libraries.
+g++ -O2 -std=c++17 "$HERE/ref_e2e.cc" -I/tmp/refsrc -I/tmp/refbuild -I/usr/local/cuda/include \
+  /tmp/refbuild/gloo/libgloo_cuda.a /tmp/refbuild/gloo/libgloo.a \
+  -L/usr/local/cuda/lib64 -Wl,-rpath,/usr/local/cuda/lib64 -lcudart -lnccl -lpthread -ldl \
+  -o "$HERE/_ref/bin/ref_e2e"
+echo "installed: $HERE/_ref/bin/ref_e2e"

@@ -1,12 +1,15 @@
 // AllreduceHalvingDoubling<T> (old-style): recursive vector halving with distance
 // doubling (reduce-scatter, lg P steps) followed by the mirrored allgather; 2·lg P
-// steps, 2·S bytes. Non-power-of-two P: the P - 2^k surplus ranks first fold their
-// vector onto a partner and receive the final result back afterwards (the
-// reference uses binary blocks instead, allreduce_halving_doubling.h:39-64; the
-// fold costs one extra step on each side but keeps every rank's schedule regular).
+// steps, 2·S bytes. Non-power-of-two P: binary blocks (binary_blocks.h; the reference's
+// scheme, allreduce_halving_doubling.h:39-64): blocks of decreasing power-of-two size run
+// the halving phase concurrently and are chained for the cross-block reduction, so no rank
+// idles. GLB_HD_FOLD=1 selects the simpler alternative instead: the P - 2^k surplus ranks
+// fold their vector onto a partner first and get the result back afterwards (one extra
+// full-vector hop on each side).
 // Parity: gloo/allreduce_halving_doubling.h:38-415.
 #pragma once
 
+#include "glb/binary_blocks.h"
 #include "glb/mixed_radix.h"
 
 namespace glb {
@@ -20,6 +23,10 @@ class AllreduceHalvingDoubling : public Algorithm {
     GLB_ENFORCE(!ptrs_.empty());
     if (contextSize_ == 1) return;
     const int core = detail::largestPow2AtMost(contextSize_);
+    if (core != contextSize_ && !envFlag("HD_FOLD", false)) {
+      blocks_.reset(new detail::BinaryBlocksAllreduce<T>(context_, ptrs_[0], count_, fn_));
+      return;
+    }
     std::vector<int> factors(log2ceil(static_cast<uint32_t>(core)), 2);
     engine_.reset(new detail::MixedRadix<T>(this, context_, ptrs_[0], count_, fn_, factors, core, true));
   }
@@ -27,7 +34,9 @@ class AllreduceHalvingDoubling : public Algorithm {
   void run() override {
     if (count_ == 0) return;
     for (size_t i = 1; i < ptrs_.size(); i++) fn_->call(ptrs_[0], ptrs_[i], count_);
-    if (engine_) {
+    if (blocks_) {
+      blocks_->run();
+    } else if (engine_) {
       engine_->foldIn();
       engine_->reduceScatter();
       engine_->allgather();
@@ -42,6 +51,7 @@ class AllreduceHalvingDoubling : public Algorithm {
   const size_t bytes_;
   const ReductionFunction<T>* fn_;
   std::unique_ptr<detail::MixedRadix<T>> engine_;
+  std::unique_ptr<detail::BinaryBlocksAllreduce<T>> blocks_;
 };
 
 }  // namespace glb

@@ -22,7 +22,7 @@ class Device;
 class UnboundBuffer;
 }  // namespace transport
 
-class Context {
+class Context : public std::enable_shared_from_this<Context> {
  public:
   Context(int rank, int size, int base = 2);
   virtual ~Context();

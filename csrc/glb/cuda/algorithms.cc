@@ -287,6 +287,7 @@ void CudaAllreduceCore::run() {
         noteLaunch();
         cudaError_t le = cudaGetLastError();
         if (le != cudaSuccess) GLB_THROW(Exception, "schedule kernel launch failed: ", cudaGetErrorString(le));
+        pc_->markLaunched(*s0);
       } else if (pc_) {
         allreduce(*pc_, *reg_, regOffset_, count_, dt_, op_, algo_, *s0, ep);
       } else {

@@ -110,7 +110,7 @@ __device__ __forceinline__ void gridCopy(char* dst, const char* src, size_t byte
 // mode 1: scatter + allgather: root pushes slice i to rank i, then every rank
 //         pushes its slice to the others; per-GPU egress ~S instead of (P-1)·S.
 // mode 2: NVLS: root issues multimem.st, the switch replicates.
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 broadcastKernel(CommArgs a, PeerPtrs bufs, char* mc, size_t bytes, int root, int mode, bool vec) {
   const uint32_t e = loadEpoch(a);
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
@@ -232,7 +232,7 @@ struct VArgs {
   size_t len[kMaxRanks];
 };
 
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
 gatherPushKernel(CommArgs a, const char* __restrict__ in, PeerPtrs outs, char* mcOut, VArgs va, int onlyDst,
                  bool vec) {
   const uint32_t e = loadEpoch(a);
@@ -586,6 +586,38 @@ void launchLLExchange(const CommArgs& a, const void* in, void* out, size_t bytes
                       size_t srcStride, size_t parityStride, int blocks, int threads, cudaStream_t stream) {
   llExchangeKernel<<<blocks, threads, 0, stream>>>(a, static_cast<const char*>(in), static_cast<char*>(out), bytes, mode,
                                                    ll, srcStride, parityStride);
+}
+
+const void* broadcastKernelPtr() { return reinterpret_cast<const void*>(broadcastKernel); }
+const void* gatherPushKernelPtr() { return reinterpret_cast<const void*>(gatherPushKernel); }
+const void* alltoallPushKernelPtr() { return reinterpret_cast<const void*>(alltoallPushKernel); }
+const void* reducePullKernelPtr(DataType dt, int nranks) {
+#define GLB_RP(E, T)                                                                                   \
+  case DataType::E: {                                                                                  \
+    constexpr bool hot = std::is_same<T, float>::value || std::is_same<T, __half>::value ||            \
+                         std::is_same<T, __nv_bfloat16>::value;                                        \
+    if constexpr (hot) {                                                                               \
+      if (nranks == 2) return reinterpret_cast<const void*>(reducePullKernel<T, 2, 4>);                \
+      if (nranks == 4) return reinterpret_cast<const void*>(reducePullKernel<T, 4, 2>);                \
+      if (nranks == 8) return reinterpret_cast<const void*>(reducePullKernel<T, 8, 2>);                \
+    }                                                                                                  \
+    return reinterpret_cast<const void*>(reducePullKernel<T, 0, 1>);                                   \
+  }
+  switch (dt) {
+    GLB_RP(INT8, int8_t)
+    GLB_RP(UINT8, uint8_t)
+    GLB_RP(INT16, int16_t)
+    GLB_RP(INT32, int32_t)
+    GLB_RP(UINT32, uint32_t)
+    GLB_RP(INT64, long long)
+    GLB_RP(UINT64, unsigned long long)
+    GLB_RP(FLOAT32, float)
+    GLB_RP(FLOAT64, double)
+    GLB_RP(FLOAT16, __half)
+    GLB_RP(BFLOAT16, __nv_bfloat16)
+  }
+#undef GLB_RP
+  return nullptr;
 }
 
 void preloadCollectiveKernels() {

@@ -96,6 +96,12 @@ void prologue(PeerContext& pc, cudaStream_t stream) {
   pc.launchGuard();
 }
 
+// ... and after it has launched.
+void finish(PeerContext& pc, cudaStream_t stream, const char* what) {
+  checkLaunch(what);
+  pc.markLaunched(stream);
+}
+
 float scaleOf(const Epilogue& ep, DataType dt) {
   if (ep.scale == 1.0) return 1.0f;
   GLB_ENFORCE(dt == DataType::FLOAT32 || dt == DataType::FLOAT64 || dt == DataType::FLOAT16 || dt == DataType::BFLOAT16,
@@ -177,7 +183,7 @@ void barrier(PeerContext& pc, cudaStream_t stream) {
   DeviceGuard g(pc.device);
   prologue(pc, stream);
   launchBarrier(pc.comm(), stream);
-  checkLaunch("barrier");
+  finish(pc, stream, "barrier");
 }
 
 namespace {
@@ -232,6 +238,7 @@ void runPipelined(PeerContext& pc, const void* in, void* out, size_t count, Data
 void allreduce(PeerContext& pc, const PeerBuffer& buf, size_t byteOffset, size_t count, DataType dt, ReduceOp op,
                AllreduceAlgo algo, cudaStream_t stream, const Epilogue& ep) {
   GLB_TRACE_RANGE("glb::cuda::allreduce");
+  pc.checkHealth();
   if (count == 0) return;
   const size_t es = elementSize(dt);
   const size_t bytes = count * es;
@@ -298,12 +305,13 @@ void allreduce(PeerContext& pc, const PeerBuffer& buf, size_t byteOffset, size_t
       GLB_THROW_INVALID_OPERATION_EXCEPTION("allreduce: algorithm ", allreduceAlgoName(algo),
                                             " is not available on this entry point");
   }
-  checkLaunch("allreduce");
+  finish(pc, stream, "allreduce");
 }
 
 void allreduce(PeerContext& pc, const void* in, void* out, size_t count, DataType dt, ReduceOp op,
                AllreduceAlgo algo, cudaStream_t stream, const Epilogue& ep) {
   GLB_TRACE_RANGE("glb::cuda::allreduce(user pointers)");
+  pc.checkHealth();
   if (count == 0) return;
   GLB_ENFORCE(op != ReduceOp::CUSTOM, "custom reductions run on the host path only");
   DeviceGuard g(pc.device);
@@ -357,7 +365,7 @@ void allreduce(PeerContext& pc, const void* in, void* out, size_t count, DataTyp
     default:
       GLB_THROW_INVALID_OPERATION_EXCEPTION("allreduce: algorithm ", allreduceAlgoName(algo), " needs registered buffers");
   }
-  checkLaunch("allreduce(user pointers)");
+  finish(pc, stream, "allreduce(user pointers)");
 }
 
 void allreduceCast(PeerContext& pc, const PeerBuffer& in, size_t inOffset, const PeerBuffer& out, size_t outOffset,
@@ -393,7 +401,7 @@ void allreduceCast(PeerContext& pc, const PeerBuffer& in, size_t inOffset, const
   prologue(pc, stream);
   launchCastAllreduce(pc.comm(), in.ptrsAt(inOffset), useMc ? static_cast<char*>(in.mc) + inOffset : nullptr,
                       out.ptrsAt(outOffset), count, dt, outDt, op, scale, vec, blocks, stream);
-  checkLaunch("allreduceCast");
+  finish(pc, stream, "allreduceCast");
 }
 
 
@@ -428,11 +436,16 @@ StagedOut stagedBulk(const PeerContext& pc, size_t needBytes, const char* what) 
 
 // Store-only kernels (broadcast / gather / alltoall pushes) are light on registers, so two
 // CTAs per SM stay co-resident: their cap is 2x the reduce kernels'.
-int bwBlocks(const PeerContext& pc, const char* coll, size_t bytes) {
-  size_t want = ceilDiv(std::max<size_t>(bytes / 16, 1), static_cast<size_t>(kThreads) * 4);
-  int cap = std::min({tuning().copyBlocks, 2 * pc.maxBlocks(), kMaxBlocks});
-  if (const TuneEntry* e = TuningTable::get().lookup(coll, pc.size, BufKind::REGISTERED, bytes)) {
-    if (e->blocks > 0) cap = std::min(e->blocks, std::min(2 * pc.maxBlocks(), kMaxBlocks));
+// Grid of a store-only kernel: enough CTAs for `workBytes`, at most what the tuning table (keyed
+// by `keyBytes`) or the copyBlocks knob allows, and never more than can be co-resident for THIS
+// kernel (occupancy query: every CTA waits for its twin on the peers, so all must be running).
+int bwBlocks(PeerContext& pc, const char* coll, const void* kernel, size_t workBytes, size_t keyBytes = ~size_t(0)) {
+  if (keyBytes == ~size_t(0)) keyBytes = workBytes;
+  size_t want = ceilDiv(std::max<size_t>(workBytes / 16, 1), static_cast<size_t>(kThreads) * 4);
+  const int resident = kernel != nullptr ? pc.coResidentBlocks(kernel) : pc.maxBlocks();
+  int cap = std::min({tuning().copyBlocks, resident, kMaxBlocks});
+  if (const TuneEntry* e = TuningTable::get().lookup(coll, pc.size, BufKind::REGISTERED, keyBytes)) {
+    if (e->blocks > 0) cap = std::min({e->blocks, resident, kMaxBlocks});
   }
   return std::max(1, static_cast<int>(std::min<size_t>(want, static_cast<size_t>(cap))));
 }
@@ -458,11 +471,11 @@ void broadcast(PeerContext& pc, const PeerBuffer& buf, size_t byteOffset, size_t
     long forced = envInt("CUDA_BCAST_MODE", -1);
     if (forced >= 0 && forced <= 2 && (forced != 2 || (buf.mc != nullptr && vec))) mode = static_cast<int>(forced);
   }
-  const int blocks = bwBlocks(pc, "broadcast", mode == 1 ? bytes / pc.size * 2 : bytes);
+  const int blocks = bwBlocks(pc, "broadcast", broadcastKernelPtr(), mode == 1 ? bytes / pc.size * 2 : bytes, bytes);
   prologue(pc, stream);
   launchBroadcast(pc.comm(), buf.ptrsAt(byteOffset), buf.mc ? static_cast<char*>(buf.mc) + byteOffset : nullptr,
                   bytes, root, mode, vec, blocks, stream);
-  checkLaunch("broadcast");
+  finish(pc, stream, "broadcast");
 }
 
 void broadcast(PeerContext& pc, void* ptr, size_t bytes, int root, cudaStream_t stream) {
@@ -485,8 +498,8 @@ void broadcast(PeerContext& pc, void* ptr, size_t bytes, int root, cudaStream_t 
     }
     prologue(pc, stream);
     launchBroadcast(pc.comm(), stage, pc.stageMc(l.bulkOff), n, root, mode, true,
-                    bwBlocks(pc, "broadcast", mode == 1 ? n / pc.size * 2 : n), stream);
-    checkLaunch("broadcast(staged)");
+                    bwBlocks(pc, "broadcast", broadcastKernelPtr(), mode == 1 ? n / pc.size * 2 : n, n), stream);
+    finish(pc, stream, "broadcast(staged)");
     if (pc.rank != root) GLB_CUDA_CHECK(cudaMemcpyAsync(p, mine, n, cudaMemcpyDeviceToDevice, stream));
   }
 }
@@ -503,8 +516,8 @@ void gatherCommon(PeerContext& pc, const void* in, const PeerPtrs& outs, void* m
   const size_t largest = *std::max_element(bytesPerRank.begin(), bytesPerRank.end());
   prologue(pc, stream);
   launchGatherPush(pc.comm(), in, outs, mcOut, off.data(), bytesPerRank.data(), onlyDst, vec,
-                   bwBlocks(pc, "allgather", largest), stream);
-  checkLaunch("allgather/gather");
+                   bwBlocks(pc, "allgather", gatherPushKernelPtr(), largest), stream);
+  finish(pc, stream, "allgather/gather");
 }
 
 bool allEqual(const std::vector<size_t>& v) {
@@ -531,7 +544,7 @@ bool tryLLExchange(PeerContext& pc, const void* in, void* outLocal, size_t bytes
   prologue(pc, stream);
   launchLLExchange(pc.comm(), in, outLocal, bytesPerBlock, mode, pc.llPtrs(), pc.llSrcStride(), pc.llParityStride(), blocks,
                    threads, stream);
-  checkLaunch("ll exchange");
+  finish(pc, stream, "ll exchange");
   return true;
 }
 }  // namespace
@@ -618,14 +631,14 @@ void alltoallCommon(PeerContext& pc, const void* in, const std::vector<size_t>& 
   const bool vec = vecOut && reinterpret_cast<uintptr_t>(in) % 16 == 0;
   int blocks;
   if (uniform) {
-    blocks = bwBlocks(pc, "alltoall", soff.back());
+    blocks = bwBlocks(pc, "alltoall", alltoallPushKernelPtr(), soff.back(), sendBytes[0]);
   } else {
-    blocks = std::max(1, std::min({tuning().alltoallvBlocks, 2 * pc.maxBlocks(), kMaxBlocks}));
+    blocks = std::max(1, std::min({tuning().alltoallvBlocks, pc.coResidentBlocks(alltoallPushKernelPtr()), kMaxBlocks}));
   }
   prologue(pc, stream);
   launchAlltoallPush(pc.comm(), in, outs, soff.data(), sendBytes.data(), dstOff.data(), uniform ? nullptr : roff.data(),
                      -1, vec, blocks, stream);
-  checkLaunch("alltoall");
+  finish(pc, stream, "alltoall");
 }
 }  // namespace
 
@@ -698,8 +711,8 @@ void scatter(PeerContext& pc, const void* in, const PeerBuffer& out, size_t outO
   const bool vec = out.vectorOk && outOffset % 16 == 0 && (pc.rank != root || reinterpret_cast<uintptr_t>(in) % 16 == 0);
   prologue(pc, stream);
   launchAlltoallPush(pc.comm(), in, out.ptrsAt(outOffset), soff.data(), slen.data(), doff.data(), nullptr, root, vec,
-                     bwBlocks(pc, "alltoall", bytes * pc.size), stream);
-  checkLaunch("scatter");
+                     bwBlocks(pc, "alltoall", alltoallPushKernelPtr(), bytes * pc.size, bytes), stream);
+  finish(pc, stream, "scatter");
 }
 
 void scatter(PeerContext& pc, const void* in, void* out, size_t bytes, int root, cudaStream_t stream) {
@@ -714,8 +727,8 @@ void scatter(PeerContext& pc, const void* in, void* out, size_t bytes, int root,
   prologue(pc, stream);
   launchAlltoallPush(pc.comm(), in, st.ptrs, soff.data(), slen.data(), doff.data(), nullptr, root,
                      pc.rank != root || reinterpret_cast<uintptr_t>(in) % 16 == 0,
-                     bwBlocks(pc, "alltoall", bytes * pc.size), stream);
-  checkLaunch("scatter(staged)");
+                     bwBlocks(pc, "alltoall", alltoallPushKernelPtr(), bytes * pc.size, bytes), stream);
+  finish(pc, stream, "scatter(staged)");
   if (bytes > 0) GLB_CUDA_CHECK(cudaMemcpyAsync(out, st.mine, bytes, cudaMemcpyDeviceToDevice, stream));
 }
 
@@ -743,8 +756,9 @@ void reducePullCommon(PeerContext& pc, const PeerPtrs& ins, void* mcIn, bool vec
   const float scale = scaleOf(ep, dt);
   prologue(pc, stream);
   launchReducePull(pc.comm(), ins, mcIn, out, off.data(), counts.data(), dt, op, scale, vecIn, useMc,
-                   blocksFor(pc, largest * es / 16, 1, cap), stream);
-  checkLaunch("reduce_scatter");
+                   std::min(blocksFor(pc, largest * es / 16, 1, cap), pc.coResidentBlocks(reducePullKernelPtr(dt, pc.size))),
+                   stream);
+  finish(pc, stream, "reduce_scatter");
 }
 }  // namespace
 
@@ -839,8 +853,11 @@ void p2pCommon(PeerContext& pc, const void* sendPtr, size_t sendBytes, int dst, 
   // No orderStreams / launchGuard: p2p kernels do not use the barrier epoch, and a host
   // rendezvous of ALL ranks would deadlock a pairwise operation.
   const auto& o = pc.options();
+  // Both ends must cut a slot into the same stripes: the lane count comes from job-wide
+  // values only. Sender and receiver CTAs wait for each other, so they must be co-resident.
+  const int lanes = std::max(1, std::min(o.p2pLanes, pc.maxBlocks() / 2));
   launchP2p(pc.comm(), sendPtr, sendBytes, sendBytes ? dst : 0, recvPtr, recvBytes, recvBytes ? src : 0, pc.mailboxPtrs(),
-            pc.mailboxStride(), o.p2pSlotBytes, o.p2pSlots, o.p2pLanes, stream);
+            pc.mailboxStride(), o.p2pSlotBytes, o.p2pSlots, lanes, stream);
   checkLaunch("p2p");
 }
 }  // namespace
@@ -865,7 +882,7 @@ void put(PeerContext& pc, const void* local, const PeerBuffer& remote, size_t re
   if (bytes == 0) return;
   DeviceGuard g(pc.device);
   pc.checkHealth();
-  launchPeerCopy(static_cast<char*>(remote.peer[peer]) + remoteOffset, local, bytes, bwBlocks(pc, "put", bytes), stream);
+  launchPeerCopy(static_cast<char*>(remote.peer[peer]) + remoteOffset, local, bytes, bwBlocks(pc, "put", nullptr, bytes), stream);
   checkLaunch("put");
 }
 
@@ -876,7 +893,7 @@ void get(PeerContext& pc, void* local, const PeerBuffer& remote, size_t remoteOf
   if (bytes == 0) return;
   DeviceGuard g(pc.device);
   pc.checkHealth();
-  launchPeerCopy(local, static_cast<const char*>(remote.peer[peer]) + remoteOffset, bytes, bwBlocks(pc, "get", bytes), stream);
+  launchPeerCopy(local, static_cast<const char*>(remote.peer[peer]) + remoteOffset, bytes, bwBlocks(pc, "get", nullptr, bytes), stream);
   checkLaunch("get");
 }
 

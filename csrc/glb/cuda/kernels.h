@@ -61,6 +61,11 @@ void launchAlltoallPush(const CommArgs& a, const void* in, const PeerPtrs& outs,
 void launchReducePull(const CommArgs& a, const PeerPtrs& ins, void* mcIn, void* out, const size_t* elemOff,
                       const size_t* elemLen, DataType dt, ReduceOp op, float scale, bool vec, bool useMc, int blocks,
                       cudaStream_t stream);
+// Entry points, for occupancy queries (every CTA of a collective kernel must be resident).
+const void* broadcastKernelPtr();
+const void* gatherPushKernelPtr();
+const void* alltoallPushKernelPtr();
+const void* reducePullKernelPtr(DataType dt, int nranks);
 // Flag-in-data exchange for small messages (no barrier): mode 0 = allgather (my block to
 // everyone), 1 = alltoall (block j of my input to rank j). `bytes` per block, uniform.
 void launchLLExchange(const CommArgs& a, const void* in, void* out, size_t bytes, int mode, const PeerPtrs& ll,

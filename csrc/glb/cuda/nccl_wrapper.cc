@@ -40,6 +40,13 @@ struct Api {
   int (*ncclRecv)(void*, size_t, int, int, ncclComm_t, cudaStream_t);
   int (*ncclGroupStart)();
   int (*ncclGroupEnd)();
+  // Optional (NCCL >= 2.19): NCCL-allocated, registered user buffers — what lets NCCL run
+  // NVLS / zero-copy on the caller's buffer. The comparator uses them so that "ours on
+  // symmetric memory vs NCCL" compares like with like.
+  int (*ncclMemAlloc)(void**, size_t);
+  int (*ncclMemFree)(void*);
+  int (*ncclCommRegister)(ncclComm_t, void*, size_t, void**);
+  int (*ncclCommDeregister)(ncclComm_t, void*);
 };
 
 Api gApi;
@@ -80,6 +87,10 @@ void load() {
   GLB_NCCL(ncclGroupStart)
   GLB_NCCL(ncclGroupEnd)
 #undef GLB_NCCL
+  gApi.ncclMemAlloc = reinterpret_cast<decltype(gApi.ncclMemAlloc)>(dlsym(lib, "ncclMemAlloc"));
+  gApi.ncclMemFree = reinterpret_cast<decltype(gApi.ncclMemFree)>(dlsym(lib, "ncclMemFree"));
+  gApi.ncclCommRegister = reinterpret_cast<decltype(gApi.ncclCommRegister)>(dlsym(lib, "ncclCommRegister"));
+  gApi.ncclCommDeregister = reinterpret_cast<decltype(gApi.ncclCommDeregister)>(dlsym(lib, "ncclCommDeregister"));
   gLoaded = ok;
 }
 
@@ -186,6 +197,37 @@ NcclComm::~NcclComm() {
     DeviceGuard g(device_);
     gApi.ncclCommDestroy(static_cast<ncclComm_t>(comm_));
   }
+}
+
+void* NcclComm::memAlloc(size_t bytes) {
+  const Api& a = api();
+  if (a.ncclMemAlloc == nullptr) GLB_THROW_INVALID_OPERATION_EXCEPTION("this NCCL has no ncclMemAlloc");
+  DeviceGuard g(device_);
+  void* p = nullptr;
+  check(a.ncclMemAlloc(&p, bytes), "ncclMemAlloc");
+  return p;
+}
+
+void NcclComm::memFree(void* p) {
+  const Api& a = api();
+  if (a.ncclMemFree != nullptr && p != nullptr) {
+    DeviceGuard g(device_);
+    a.ncclMemFree(p);
+  }
+}
+
+void* NcclComm::registerBuffer(void* p, size_t bytes) {
+  const Api& a = api();
+  if (a.ncclCommRegister == nullptr) GLB_THROW_INVALID_OPERATION_EXCEPTION("this NCCL has no ncclCommRegister");
+  DeviceGuard g(device_);
+  void* handle = nullptr;
+  check(a.ncclCommRegister(static_cast<ncclComm_t>(comm_), p, bytes, &handle), "ncclCommRegister");
+  return handle;
+}
+
+void NcclComm::deregisterBuffer(void* handle) {
+  const Api& a = api();
+  if (a.ncclCommDeregister != nullptr && handle != nullptr) a.ncclCommDeregister(static_cast<ncclComm_t>(comm_), handle);
 }
 
 void NcclComm::groupStart() { check(api().ncclGroupStart(), "ncclGroupStart"); }

@@ -41,6 +41,12 @@ class NcclComm {
   // alltoall through grouped send/recv (what NCCL users write by hand).
   void alltoall(const void* src, void* dst, size_t countPerRank, DataType dt, cudaStream_t stream);
 
+  // NCCL-owned, communicator-registered buffers (ncclMemAlloc + ncclCommRegister).
+  void* memAlloc(size_t bytes);
+  void memFree(void* p);
+  void* registerBuffer(void* p, size_t bytes);  // returns the registration handle
+  void deregisterBuffer(void* handle);
+
   static void groupStart();
   static void groupEnd();
 

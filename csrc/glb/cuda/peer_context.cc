@@ -379,14 +379,21 @@ void PeerContext::synchronize(cudaStream_t stream) {
 }
 
 void PeerContext::orderStreams(cudaStream_t stream) {
+  // The previous collective recorded `orderEvent_` right after its launch. The stream handle
+  // of that launch is only ever COMPARED here, never used: it may belong to a stream that
+  // has been destroyed since.
   if (haveLastStream_ && stream != lastStream_) {
     cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
     cudaStreamIsCapturing(stream, &cs);
-    if (cs == cudaStreamCaptureStatusNone) {
-      GLB_CUDA_CHECK(cudaEventRecord(orderEvent_, lastStream_));
-      GLB_CUDA_CHECK(cudaStreamWaitEvent(stream, orderEvent_, 0));
-    }
+    if (cs == cudaStreamCaptureStatusNone) GLB_CUDA_CHECK(cudaStreamWaitEvent(stream, orderEvent_, 0));
   }
+}
+
+void PeerContext::markLaunched(cudaStream_t stream) {
+  cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
+  cudaStreamIsCapturing(stream, &cs);
+  if (cs != cudaStreamCaptureStatusNone) return;  // inside a graph the capture order is the order
+  GLB_CUDA_CHECK(cudaEventRecord(orderEvent_, stream));
   lastStream_ = stream;
   haveLastStream_ = true;
 }

@@ -127,6 +127,8 @@ class PeerContext : public std::enable_shared_from_this<PeerContext> {
   // execute one after the other on the device. Calls on the same stream are ordered
   // already; a call on a different stream is made to wait for the previous one here.
   void orderStreams(cudaStream_t stream);
+  // Called right after a collective kernel has been launched on `stream`.
+  void markLaunched(cudaStream_t stream);
 
   // ---- collective calls: every rank, same order ------------------------------------
   std::shared_ptr<PeerBuffer> allocSymmetric(size_t bytes);

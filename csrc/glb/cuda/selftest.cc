@@ -16,6 +16,7 @@
 
 #include "glb/common/utils.h"
 #include "glb/cuda/kernels.h"
+#include "glb/cuda/local_ops.h"
 #include "glb/cuda/schedules.h"
 
 namespace glb {
@@ -451,6 +452,98 @@ bool loopbackTimeoutTest(PeerContext& pc, cudaStream_t stream, int timeoutMs, do
     return true;
   }
   return false;
+}
+
+// LocalOp classes (cuda/local_ops.h) on one device: memcpy, native / host reduce and
+// broadcast, and the dispatchers. The NCCL flavours need one GPU per pointer and are
+// exercised when `devices` names several.
+std::vector<SelfTestResult> localOpsSelfTest(const std::vector<int>& devices, size_t count) {
+  std::vector<SelfTestResult> out;
+  auto run = [&](const std::string& name, auto&& body) {
+    SelfTestResult r;
+    r.name = name;
+    try {
+      r.detail = body();
+      r.ok = r.detail.empty();
+    } catch (const std::exception& e) {
+      r.detail = e.what();
+    }
+    out.push_back(r);
+  };
+  const int n = static_cast<int>(devices.size());
+  GLB_ENFORCE_GE(n, 1);
+  std::vector<CudaDevicePointer<float>> ptrs;
+  std::vector<CudaStream> streams;
+  const int nptr = std::max(n, 3);
+  for (int i = 0; i < nptr; i++) {
+    const int dev = devices[i % n];
+    DeviceGuard g(dev);
+    ptrs.push_back(CudaDevicePointer<float>::alloc(count));
+    streams.emplace_back(dev);
+  }
+  auto fill = [&] {
+    for (int i = 0; i < nptr; i++) {
+      DeviceGuard g(ptrs[i].getDeviceID());
+      launchFill(*ptrs[i], count, DataType::FLOAT32, i, nptr, *streams[i]);
+    }
+  };
+  const double tri = nptr * (nptr - 1) / 2.0;
+  auto check = [&](const float* host, double start, double stride) -> std::string {
+    for (size_t i = 0; i < count; i++) {
+      if (!close(host[i], start + stride * static_cast<double>(i))) return strcat_all("element ", i, ": got ", host[i]);
+    }
+    return "";
+  };
+  auto host = CudaHostPointer<float>::alloc(count);
+
+  run("CudaLocalMemcpy (device -> host)", [&]() -> std::string {
+    fill();
+    CudaLocalMemcpy<float, CudaDevicePointer<float>, CudaHostPointer<float>> cp(streams[0], ptrs[0], host, 0, count);
+    cp.run();
+    return check(*host, 0, nptr);
+  });
+  run("cudaDeviceReduce + cudaDeviceBroadcast", [&]() -> std::string {
+    fill();
+    auto red = cudaDeviceReduce<float>(streams, ptrs, ptrs[0], CudaReductionFunction<float>::sum, 0, count);
+    red->run();
+    auto bc = cudaDeviceBroadcast<float>(streams, ptrs, ptrs[0], 0, count);
+    bc->run();
+    CudaLocalMemcpy<float, CudaDevicePointer<float>, CudaHostPointer<float>> cp(streams[nptr - 1], ptrs[nptr - 1], host, 0, count);
+    cp.run();
+    return check(*host, tri, static_cast<double>(nptr) * nptr);
+  });
+  run("cudaHostReduce (device fold) + cudaHostBroadcast", [&]() -> std::string {
+    fill();
+    auto red = cudaHostReduce<float>(streams, ptrs, host, CudaReductionFunction<float>::sum, 0, count);
+    red->run();
+    std::string why = check(*host, tri, static_cast<double>(nptr) * nptr);
+    if (!why.empty()) return why;
+    auto bc = cudaHostBroadcast<float>(streams, ptrs, host, 0, count);
+    bc->run();
+    auto back = CudaHostPointer<float>::alloc(count);
+    CudaLocalMemcpy<float, CudaDevicePointer<float>, CudaHostPointer<float>> cp(streams[1], ptrs[1], back, 0, count);
+    cp.run();
+    return check(*back, tri, static_cast<double>(nptr) * nptr);
+  });
+  run("CudaLocalHostReduce (CPU fold)", [&]() -> std::string {
+    fill();
+    CudaLocalHostReduce<float> red(streams, ptrs, host, CudaReductionFunction<float>::sum, 0, count);
+    red.run();
+    return check(*host, tri, static_cast<double>(nptr) * nptr);
+  });
+  if (n >= 2 && n == nptr && ncclAvailable()) {
+    run("CudaLocalNCCLReduce + CudaLocalNCCLBroadcast", [&]() -> std::string {
+      fill();
+      CudaLocalNCCLReduce<float> red(streams, ptrs, ptrs[0], CudaReductionFunction<float>::sum, 0, count);
+      red.run();
+      CudaLocalNCCLBroadcast<float> bc(streams, ptrs, ptrs[0], 0, count);
+      bc.run();
+      CudaLocalMemcpy<float, CudaDevicePointer<float>, CudaHostPointer<float>> cp(streams[n - 1], ptrs[n - 1], host, 0, count);
+      cp.run();
+      return check(*host, tri, static_cast<double>(nptr) * nptr);
+    });
+  }
+  return out;
 }
 
 }  // namespace cuda

@@ -28,5 +28,9 @@ std::vector<SelfTestResult> loopbackSelfTest(PeerContext& pc, cudaStream_t strea
 // Poisons `pc` (use a throw-away context).
 bool loopbackTimeoutTest(PeerContext& pc, cudaStream_t stream, int timeoutMs, double* elapsedMs = nullptr);
 
+// The LocalOp classes (memcpy, native / host / NCCL reduce and broadcast, dispatchers) over
+// buffers on the given devices (one entry = everything on that device).
+std::vector<SelfTestResult> localOpsSelfTest(const std::vector<int>& devices, size_t count = 100003);
+
 }  // namespace cuda
 }  // namespace glb

@@ -29,6 +29,7 @@
 #include "glb/rendezvous/redis_store.h"
 #include "glb/transport/ibverbs/device.h"
 #include "glb/transport/uv/device.h"
+#include "glb/transport/nvl/device.h"
 #include "glb/scatter.h"
 #include "glb/transport/tcp/device.h"
 #include "glb/transport/tcp/tls/device.h"
@@ -235,6 +236,14 @@ PYBIND11_MODULE(_C, m) {
     return transport::uv::CreateDevice(a);
   }, py::arg("hostname") = "", py::arg("iface") = "",
         "Reference-compatible name for the portable TCP transport; backed by the epoll transport here.");
+  m.def("create_nvl_device", [](std::shared_ptr<transport::Device> control, int cudaDevice) {
+    transport::nvl::attr a;
+    a.control = std::move(control);
+    a.cudaDevice = cudaDevice;
+    return transport::nvl::CreateDevice(a);
+  }, py::arg("control"), py::arg("cuda_device") = -1,
+     "NVLink peer-memory transport: device pointers as unbound buffers (send / recv / put / get over NVLink), "
+     "host pointers through `control`.");
   m.def("create_ibverbs_device", [](const std::string& name, int port, int index) {
     transport::ibverbs::attr a;
     a.name = name;

@@ -225,6 +225,24 @@ void registerCuda(py::module_& root) {
   }, py::arg("pc"), py::arg("local"), py::arg("remote"), py::arg("remote_offset"), py::arg("bytes"), py::arg("peer"),
      py::arg("stream") = 0);
 
+  m.def("local_ops_selftest", [](std::vector<int> devices, size_t count) {
+    std::vector<SelfTestResult> res;
+    {
+      py::gil_scoped_release nogil;
+      res = localOpsSelfTest(devices, count);
+    }
+    py::list out;
+    for (const auto& r : res) {
+      py::dict d;
+      d["name"] = r.name;
+      d["ok"] = r.ok;
+      d["detail"] = r.detail;
+      out.append(d);
+    }
+    return out;
+  }, py::arg("devices"), py::arg("count") = 100003,
+     "Exercise the LocalOp classes (CudaLocalMemcpy / Native / Host / NCCL reduce + broadcast, dispatchers).");
+
   // ---- tuning table ---------------------------------------------------------------------
   m.def("tuning_load_file", [](const std::string& path) {
     std::string err;

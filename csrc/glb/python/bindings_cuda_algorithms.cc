@@ -89,7 +89,14 @@ void registerCudaAlgorithms(py::module_& m) {
       })
       .def("alltoall", [](NcclComm& c, uintptr_t src, uintptr_t dst, size_t n, int dt, uintptr_t st) {
         c.alltoall(P(src), P(dst), n, static_cast<DataType>(dt), S(st));
-      });
+      })
+      .def("mem_alloc", [](NcclComm& c, size_t bytes) { return reinterpret_cast<uintptr_t>(c.memAlloc(bytes)); },
+           "ncclMemAlloc: a buffer NCCL can register for NVLS / zero-copy.")
+      .def("mem_free", [](NcclComm& c, uintptr_t p) { c.memFree(P(p)); })
+      .def("register_buffer", [](NcclComm& c, uintptr_t p, size_t bytes) {
+        return reinterpret_cast<uintptr_t>(c.registerBuffer(P(p), bytes));
+      })
+      .def("deregister_buffer", [](NcclComm& c, uintptr_t h) { c.deregisterBuffer(P(h)); });
 
   // Step tables of the literal schedules (pure host code: testable without a GPU).
   m.def("build_schedule", [](const std::string& name, int rank, int size, size_t count, int base, size_t pack) {

@@ -21,6 +21,7 @@ void Context::connectFullMesh(std::shared_ptr<Store> store, std::shared_ptr<tran
   transportContext->createAndConnectAllPairs(std::move(store));
   device_ = dev;
   transportContext_ = std::move(transportContext);
+  transportContext_->onAttached(weak_from_this());
 }
 
 ContextFactory::ContextFactory(std::shared_ptr<::glb::Context> backingContext)
@@ -84,6 +85,7 @@ std::shared_ptr<::glb::Context> ContextFactory::makeContext(std::shared_ptr<tran
   }
   context->device_ = dev;
   context->transportContext_ = std::move(tctx);
+  context->transportContext_->onAttached(std::weak_ptr<::glb::Context>(context));
   return context;
 }
 

@@ -16,6 +16,7 @@
 #include "glb/transport/unbound_buffer.h"
 
 namespace glb {
+class Context;  // the communicator that owns a transport context
 namespace transport {
 
 class Context {
@@ -29,7 +30,10 @@ class Context {
   virtual std::unique_ptr<Pair>& getPair(int rank) { return pairs_.at(rank); }
   virtual std::unique_ptr<Pair>& createPair(int rank) = 0;
   // The pair object as is (no lazy connect); may be null.
-  Pair* peekPair(int rank) { return pairs_.at(rank).get(); }
+  virtual Pair* peekPair(int rank) { return pairs_.at(rank).get(); }
+  // Called once the owning glb::Context holds this transport context (end of
+  // connectFullMesh / ContextFactory::makeContext, i.e. collectively on every rank).
+  virtual void onAttached(const std::weak_ptr<::glb::Context>& /*owner*/) {}
 
   // Generic rendezvous: every rank publishes the addresses of all its pairs under
   // its rank key, then connects to each peer (O(P^2) store traffic). Transports
@@ -42,7 +46,7 @@ class Context {
     GLB_THROW_INVALID_OPERATION_EXCEPTION("this transport has no one-sided support");
   }
 
-  void setTimeout(std::chrono::milliseconds timeout) { timeout_ = timeout; }
+  virtual void setTimeout(std::chrono::milliseconds timeout) { timeout_ = timeout; }
   std::chrono::milliseconds getTimeout() const { return timeout_; }
 
   // Address blob used by ContextFactory to wire up a derived context without a store.

@@ -1,0 +1,281 @@
+#!/usr/bin/env python
+"""Measure the tuning table of the CUDA collectives on this box.
+
+One rank per GPU (torchrun, or the driver's launcher)::
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 \
+        --master-port 29533 -m gloo_b200.tune --out gpurun_out/tune_P8
+
+For every message size of a geometric sweep and every kind of buffer (``sym``: library
+symmetric memory with an NVSwitch multicast alias, ``reg``: peer-registered cudaMalloc
+memory, ``user``: plain pointer through the pool) every applicable kernel variant is timed
+with every launch shape of a small grid (CTAs x unroll, tile for the pipelined kernel):
+device-timed with CUDA events, max over ranks, median of the iterations, L2 flushed between
+iterations. The fastest candidate per size becomes a table entry; adjacent sizes with the
+same choice are merged. ``<out>.tune`` is the table (`GLB_TUNE_FILE`, or copy it to
+``gloo_b200/tuning/b200.tune``), ``<out>.json`` keeps every measurement, including the NCCL
+comparator at the same sizes, so the table can be audited: AUTO must never be more than a
+few percent off the best pinned variant.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+
+import numpy as np
+
+
+def geometric_sizes(lo: int, hi: int, per_octave: int = 1):
+    out, x = [], float(lo)
+    while x <= hi * 1.0001:
+        out.append(int(round(x / 16)) * 16 if x >= 64 else int(x))
+        x *= 2 ** (1.0 / per_octave)
+    return sorted(set(max(4, s) for s in out))
+
+
+def main(argv=None):
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--out", default="gpurun_out/tune")
+    ap.add_argument("--dtype", default="float32")
+    ap.add_argument("--min-bytes", type=int, default=1024)
+    ap.add_argument("--max-bytes", type=int, default=512 << 20)
+    ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--quick", action="store_true", help="coarser grid (half the shapes, every other size)")
+    ap.add_argument("--collectives", default="allreduce,allgather,alltoall,reduce_scatter,broadcast")
+    ap.add_argument("--kinds", default="sym,reg,user")
+    ap.add_argument("--no-nccl", action="store_true")
+    ap.add_argument("--stage-mb", type=int, default=256)
+    args = ap.parse_args(argv)
+
+    import torch
+
+    import gloo_b200 as gb
+    from gloo_b200.ops import cuda as gcu
+
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dtype = getattr(torch, args.dtype)
+    es = torch.empty((), dtype=dtype).element_size()
+    path = f"/tmp/glb_tune_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}"
+    ctx = gb.init_context(rank, world, path=path, timeout_ms=180000)
+    cu = gb._C.cuda
+    cu.tuning_clear()  # measure with explicit shapes only
+    cc = gcu.CudaContext(ctx, local, stage_bytes=args.stage_mb << 20)
+    say = (lambda *a: print(*a, flush=True)) if rank == 0 else (lambda *a: None)
+    say(cc.describe())
+    nccl = None
+    if not args.no_nccl and world > 1:
+        try:
+            nccl = cu.NcclComm.init_rank(ctx, local)
+        except Exception as e:  # noqa: BLE001
+            say("NCCL comparator unavailable:", e)
+    stream = torch.cuda.Stream()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    dt_code = int({torch.float32: gb.DataType.FLOAT32, torch.float16: gb.DataType.FLOAT16,
+                   torch.bfloat16: gb.DataType.BFLOAT16}[dtype])
+
+    def timed(fn, nbytes):
+        iters = args.iters if nbytes <= (32 << 20) else max(6, args.iters // 3)
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
+        with torch.cuda.stream(stream):
+            for _ in range(2):
+                fn()
+            for a, b in evs:
+                if nbytes < (128 << 20):
+                    flush.fill_(0)
+                a.record(stream)
+                fn()
+                b.record(stream)
+        stream.synchronize()
+        per = np.asarray([a.elapsed_time(b) * 1e3 for a, b in evs], dtype=np.float64)
+        if world > 1:
+            gb.allreduce(ctx, per, op=gb.ReduceOp.MAX)
+        per.sort()
+        return float(per[len(per) // 2])
+
+    sizes = geometric_sizes(args.min_bytes, args.max_bytes, 1)
+    if args.quick:
+        sizes = sizes[::2] + ([sizes[-1]] if (len(sizes) - 1) % 2 else [])
+    cores = 148
+    blocks_bw = [32, 64, 96, 128, 148] if not args.quick else [64, 128, 148]
+    blocks_light = [64, 148, 222, 296] if not args.quick else [148, 296]
+    collectives = [c for c in args.collectives.split(",") if c]
+    kinds = [k for k in args.kinds.split(",") if k]
+    results = []   # every measurement
+    table = []     # (coll, kind, bytes, best dict)
+    ll_max = cc.pc.ll_max_bytes()
+    P = world
+
+    def record(coll, kind, nbytes, cands):
+        """cands: list of dicts with 'us'. Stores all, returns the best."""
+        ok = [c for c in cands if c.get("us")]
+        for c in cands:
+            results.append(dict(c, coll=coll, kind=kind, bytes=nbytes))
+        if not ok:
+            return None
+        best = min(ok, key=lambda c: c["us"])
+        table.append((coll, kind, nbytes, best))
+        return best
+
+    def attempt(label, fn, nbytes, **shape):
+        try:
+            us = timed(fn, nbytes)
+            return dict(algo=label, us=round(us, 2), **shape)
+        except Exception as e:  # noqa: BLE001
+            say(f"  {label} {shape} @ {nbytes}: {type(e).__name__}: {str(e)[:160]}")
+            return dict(algo=label, us=None, **shape)
+
+    # ---- allreduce ----------------------------------------------------------------------------
+    if "allreduce" in collectives and world > 1:
+        for nbytes in sizes:
+            n = max(1, nbytes // es)
+            nb = n * es
+            sym = cc.empty(n, dtype)
+            sym.fill_(1)
+            reg = torch.ones(n, dtype=dtype, device="cuda")
+            cc.register(reg)
+            plain = torch.ones(n, dtype=dtype, device="cuda")
+            torch.cuda.synchronize()
+            ref = None
+            if nccl is not None:
+                ref = attempt("nccl", lambda: nccl.allreduce(plain.data_ptr(), plain.data_ptr(), n, dt_code, 1, stream.cuda_stream), nb)
+            for kind in kinds:
+                t = {"sym": sym, "reg": reg, "user": plain}[kind]
+                cands = []
+                if nb <= ll_max:
+                    for b in (1, 4, 16):
+                        cands.append(attempt("ll", lambda: cc.allreduce(t, algo="ll", stream=stream, blocks=b), nb, blocks=b))
+                if nb * P <= (256 << 10) * 2 and nb <= (128 << 10):
+                    for b in (2, 8, 16):
+                        cands.append(attempt("one_shot", lambda: cc.allreduce(t, algo="one_shot", stream=stream, blocks=b), nb, blocks=b))
+                if kind in ("sym", "reg") and nb >= 4096:
+                    unrolls = {2: (2, 4, 8), 4: (1, 2, 4), 8: (1, 2)}.get(P, (0,))
+                    for b in blocks_bw:
+                        for u in unrolls:
+                            cands.append(attempt("two_shot", lambda: cc.allreduce(t, algo="two_shot", stream=stream, blocks=b, unroll=u), nb,
+                                                 blocks=b, unroll=u))
+                if kind == "sym" and cc.nvls_available() and nb >= 4096:
+                    for b in blocks_bw + [222, 296]:
+                        for u in (2, 4, 8):
+                            cands.append(attempt("nvls", lambda: cc.allreduce(t, algo="nvls", stream=stream, blocks=b, unroll=u), nb,
+                                                 blocks=b, unroll=u))
+                if kind == "user" and nb >= 32768:
+                    for b in ([64, 96, 128, 148] if not args.quick else [96, 148]):
+                        for tile in (256, 1024, 4096):
+                            cands.append(attempt("pipelined", lambda: cc.allreduce(t, algo="pipelined", stream=stream, blocks=b, tile=tile), nb,
+                                                 blocks=b, tile=tile))
+                best = record("allreduce", kind, nb, cands)
+                if best:
+                    bus = nb / (best["us"] * 1e-6) / 1e9 * 2 * (P - 1) / P
+                    say(f"allreduce {kind:4s} {nb:>11d} B  best {best['algo']:9s} {best}  busbw {bus:8.1f} GB/s"
+                        + (f"  nccl {ref['us']} us" if ref and ref.get("us") else ""))
+            if ref:
+                results.append(dict(ref, coll="allreduce", kind="nccl", bytes=nb))
+            del sym, reg, plain
+            torch.cuda.synchronize()
+            gb.barrier(ctx)
+
+    # ---- data movement: CTA count (and LL vs barrier for the small ones) ----------------------------
+    def movement(coll):
+        for nbytes in sizes:
+            per = max(16, nbytes // P // 16 * 16)  # bytes per rank block
+            total = per * P
+            if total > (1 << 30):
+                continue
+            out = cc.empty(total, torch.uint8)
+            inp = torch.ones(total, dtype=torch.uint8, device="cuda")
+            torch.cuda.synchronize()
+            cands = []
+            ref = None
+            if coll == "allgather":
+                call = lambda: cc.allgather(out, inp[:per], stream=stream)  # noqa: E731
+                if nccl is not None:
+                    ref = attempt("nccl", lambda: nccl.allgather(inp.data_ptr(), out.data_ptr(), per, int(gb.DataType.UINT8), stream.cuda_stream), total)
+            elif coll == "alltoall":
+                call = lambda: cc.alltoall(out, inp, stream=stream)  # noqa: E731
+                if nccl is not None:
+                    ref = attempt("nccl", lambda: nccl.alltoall(inp.data_ptr(), out.data_ptr(), per, int(gb.DataType.UINT8), stream.cuda_stream), total)
+            elif coll == "broadcast":
+                call = lambda: cc.broadcast(out, root=0, stream=stream)  # noqa: E731
+                if nccl is not None:
+                    ref = attempt("nccl", lambda: nccl.broadcast(out.data_ptr(), out.data_ptr(), total, int(gb.DataType.UINT8), 0, stream.cuda_stream), total)
+            else:  # reduce_scatter (float32)
+                fin = cc.empty(total // 4, torch.float32)
+                fout = torch.empty(per // 4, device="cuda")
+                fin.fill_(1)
+                call = lambda: cc.reduce_scatter(fout, fin, stream=stream)  # noqa: E731
+                if nccl is not None:
+                    ref = attempt("nccl", lambda: nccl.reduce_scatter(fin.data_ptr(), fout.data_ptr(), per // 4, int(gb.DataType.FLOAT32), 1, stream.cuda_stream), total)
+            small = per <= ll_max and coll in ("allgather", "alltoall")
+            if small:
+                cu.tuning_clear()
+                cu.set_tuning({"ll_max_bytes": ll_max})
+                cands.append(attempt("ll", call, total, blocks=0))
+                cu.set_tuning({"ll_max_bytes": 0})
+            for b in blocks_light:
+                cu.tuning_clear()
+                cu.tuning_load_string(f"{coll} P={P} buf=reg maxbytes=inf algo=push blocks={b}\n"
+                                      f"{coll} P={P} buf=sym maxbytes=inf algo=push blocks={b}\n")
+                cu.set_tuning({"copy_blocks": 512, "max_blocks": b})
+                cands.append(attempt("push", call, total, blocks=b))
+            cu.tuning_clear()
+            cu.set_tuning({"ll_max_bytes": 16384, "copy_blocks": 296, "max_blocks": 128})
+            best = record(coll, "reg", per if coll != "broadcast" else total, cands)
+            if best:
+                bw = total / (best["us"] * 1e-6) / 1e9 * ((P - 1) / P if coll != "broadcast" else 1.0)
+                say(f"{coll:14s} {total:>11d} B  best {best}  busbw {bw:8.1f} GB/s" + (f"  nccl {ref['us']} us" if ref and ref.get("us") else ""))
+            if ref:
+                results.append(dict(ref, coll=coll, kind="nccl", bytes=total))
+            del out, inp
+            torch.cuda.synchronize()
+            gb.barrier(ctx)
+
+    for coll in ("allgather", "alltoall", "reduce_scatter", "broadcast"):
+        if coll in collectives and world > 1:
+            movement(coll)
+
+    # ---- compress into a table ---------------------------------------------------------------------------
+    lines = [f"# gloo_b200 tuning table: P={P} dtype={args.dtype} device={torch.cuda.get_device_name(local)}",
+             f"# measured by gloo_b200.tune ({len(results)} measurements); {cores} SMs"]
+    groups = {}
+    for coll, kind, nb, best in table:
+        groups.setdefault((coll, kind), []).append((nb, best))
+    for (coll, kind), rows in sorted(groups.items()):
+        rows.sort(key=lambda r: r[0])
+        merged = []
+        for nb, best in rows:
+            key = (best["algo"], best.get("blocks", 0), best.get("unroll", 0), best.get("tile", 0))
+            if merged and merged[-1][1] == key:
+                merged[-1][0] = nb
+            else:
+                merged.append([nb, key, best["us"]])
+        for i, (nb, key, us) in enumerate(merged):
+            last = i == len(merged) - 1
+            # boundary: geometric midpoint between this size and the next measured size
+            nxt = None if last else next(r[0] for r in rows if r[0] > nb)
+            bound = "inf" if last else str(int((nb * nxt) ** 0.5))
+            algo, b, u, tl = key
+            line = f"{coll} P={P} buf={kind} maxbytes={bound} algo={algo} blocks={b}"
+            if u:
+                line += f" unroll={u}"
+            if tl:
+                line += f" tile={tl}"
+            lines.append(line)
+    text = "\n".join(lines) + "\n"
+    if rank == 0:
+        os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)
+        with open(args.out + ".tune", "w") as f:
+            f.write(text)
+        with open(args.out + ".json", "w") as f:
+            json.dump({"world": world, "dtype": args.dtype, "describe": cc.describe(), "results": results}, f)
+        print(text, flush=True)
+    torch.cuda.synchronize()
+    gb.barrier(ctx)
+    ctx.close_connections()
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -16,8 +16,15 @@ from typing import Any, Callable, List, Optional
 from .. import _C
 
 
-def create_device(hostname: str = "127.0.0.1", iface: str = "", lazy: bool = False, num_loops: int = 1):
-    return _C.create_tcp_device(hostname, iface, lazy, num_loops)
+def create_device(hostname: str = "127.0.0.1", iface: str = "", lazy: bool = False, num_loops: int = 1,
+                  nvl: bool = False, cuda_device: int = -1):
+    """A transport device. ``nvl=True`` wraps the TCP device in the NVLink peer-memory
+    transport: CUDA pointers become unbound buffers whose send / recv / put / get run over
+    NVLink (``hasGPUDirect``), host pointers keep using TCP."""
+    dev = _C.create_tcp_device(hostname, iface, lazy, num_loops)
+    if nvl:
+        dev = _C.create_nvl_device(dev, cuda_device)
+    return dev
 
 
 def init_context(rank: int, size: int, store=None, path: Optional[str] = None, prefix: Optional[str] = None,
@@ -44,7 +51,7 @@ def init_context(rank: int, size: int, store=None, path: Optional[str] = None, p
 
 def spawn_threads(size: int, fn: Callable[..., Any], *args, base: int = 2, timeout_ms: int = 30000,
                   lazy: bool = False, shared_device: bool = False, cuda_device: Optional[int] = None,
-                  **kwargs) -> List[Any]:
+                  nvl: bool = False, **kwargs) -> List[Any]:
     """Run ``fn(ctx, *args, **kwargs)`` on ``size`` threads acting as ranks; returns per-rank results.
 
     ``cuda_device``: make that GPU current in every rank thread and give each rank
@@ -61,6 +68,11 @@ def spawn_threads(size: int, fn: Callable[..., Any], *args, base: int = 2, timeo
     def run(rank: int):
         try:
             dev = shared if shared is not None else create_device(lazy=lazy)
+            if nvl:
+                import torch
+
+                torch.cuda.set_device(cuda_device or 0)
+                dev = _C.create_nvl_device(dev, cuda_device or 0)
             ctx = _C.Context(rank, size, base)
             ctx.set_timeout(timeout_ms)
             ctx.connect_full_mesh(store, dev)

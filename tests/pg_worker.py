@@ -88,6 +88,21 @@ def main():
         reqs = [dist.isend(torch.full((2,), float(rank)), dst=right, tag=5), dist.irecv(got[:2], src=left, tag=5)]
         [r.wait() for r in reqs]
         assert got[0] == left
+        # Every rank posts isend first, then irecv, with payloads above the single-copy
+        # threshold (256 KiB): a synchronous isend would wait for the peer's recv forever.
+        big = torch.full((200_000,), float(rank))  # 800 KB
+        inbox = torch.zeros(200_000)
+        reqs = [dist.isend(big, dst=right, tag=6), dist.irecv(inbox, src=left, tag=6)]
+        [r.wait() for r in reqs]
+        assert inbox[0] == left and inbox[-1] == left
+        ops = [dist.P2POp(dist.isend, big, right, tag=7), dist.P2POp(dist.irecv, inbox, left, tag=7)]
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+        assert inbox[12345] == left
+        strided = torch.zeros(4, 50_000).t()  # non-contiguous receive buffer
+        reqs = [dist.isend(big, dst=right, tag=8), dist.irecv(strided, src=left, tag=8)]
+        [r.wait() for r in reqs]
+        assert strided[0, 0] == left and strided[-1, -1] == left
 
     if size > 1:  # recv without a source: whoever sends first
         if rank == 0:

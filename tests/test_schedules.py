@@ -95,3 +95,63 @@ if given is not None:
     @given(base=st.integers(2, 5), size=st.integers(2, 16), count=st.integers(1, 2000))
     def test_bcube_any_base(base, size, count):
         simulate("bcube", size, count, base=base)
+
+
+# ---- pipelined halving-doubling: several steps share one barrier phase (sync flag) ------------
+
+def simulate_phased(name, size, count, chunks=2, pack=4):
+    tables = [build(name, r, size, count, chunks, pack) for r in range(size)]
+    phases = []
+    for t in tables:
+        ph = []
+        for st in t:
+            if st["sync"] or not ph:
+                ph.append([])
+            ph[-1].append(st)
+        phases.append(ph)
+    assert len({len(p) for p in phases}) == 1, "ranks disagree on the number of barrier phases"
+    bufs = [np.arange(count, dtype=np.float64) * size + r for r in range(size)]
+    for k in range(len(phases[0])):
+        prev = [b.copy() for b in bufs]
+        writes = [[] for _ in range(size)]
+        for r in range(size):
+            for st in phases[r][k]:
+                lo, hi = st["off"], st["off"] + st["len"]
+                if st["len"] == 0:
+                    continue
+                assert hi <= count and not st["from_stage"] and st["mode"] in (0, 1)
+                if st["mode"] == 1:
+                    bufs[r][lo:hi] = prev[st["peers"][0]][lo:hi]
+                else:
+                    acc = prev[r][lo:hi].copy()
+                    for p in st["peers"]:
+                        acc += prev[p][lo:hi]
+                    bufs[r][lo:hi] = acc
+                for w in writes[r]:
+                    assert hi <= w[0] or lo >= w[1], "two steps of one phase write overlapping ranges"
+                writes[r].append((lo, hi))
+        for r in range(size):
+            for st in phases[r][k]:
+                lo, hi = st["off"], st["off"] + st["len"]
+                for p in st["peers"] if st["len"] else []:
+                    for w in writes[p]:
+                        assert hi <= w[0] or lo >= w[1], f"phase {k}: rank {r} reads what rank {p} writes"
+    exp = np.arange(count, dtype=np.float64) * size * size + size * (size - 1) / 2
+    for r in range(size):
+        np.testing.assert_array_equal(bufs[r], exp)
+    return len(phases[0])
+
+
+@pytest.mark.parametrize("size", [2, 3, 4, 5, 6, 8, 12, 16])
+@pytest.mark.parametrize("chunks", [1, 2, 3, 4])
+def test_halving_doubling_pipelined_is_an_allreduce(size, chunks):
+    for count in (1, 63, 1000, 40000):
+        simulate_phased("halving_doubling_pipelined", size, count, chunks)
+
+
+def test_halving_doubling_pipelined_overlaps_chunks():
+    # 2 chunks skewed by one step: 2 lg P + 1 phases instead of 2 x 2 lg P sequential steps
+    plain = len(build("halving_doubling", 0, 8, 1 << 20, 2, 4))
+    assert simulate_phased("halving_doubling_pipelined", 8, 1 << 16, 2) == plain + 1
+    steps = build("halving_doubling_pipelined", 0, 8, 1 << 16, 2, 4)
+    assert len(steps) == 2 * plain and sum(s["sync"] for s in steps) == plain + 1

@@ -170,8 +170,11 @@ def run_ours(args):
     def latency(fn, iters, nbytes):
         """Per-call events with the L2 flushed in between; the whole batch is queued behind a
         5 ms spin so that host jitter cannot starve the GPU queue. -> (p50, p99, min) in us."""
-        for _ in range(max(3, args.warmup)):
-            fn()
+        with torch.cuda.stream(stream):
+            for _ in range(max(3, args.warmup)):  # dry batch under the same conditions (flushed L2)
+                if nbytes < (128 << 20):
+                    flush.fill_(0)
+                fn()
         sync_all()
         evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(iters)]
         with torch.cuda.stream(stream):
@@ -739,8 +742,9 @@ def run_reference(args):
         if e2e is not None:
             out["e2e"] = e2e
         print(json.dumps(out), flush=True)
-    for d in glob.glob(base + "_*"):
-        shutil.rmtree(d, ignore_errors=True)
+    if rank == 0:  # only rank 0: the others may finish while it still reads the e2e files
+        for d in glob.glob(base + "_*"):
+            shutil.rmtree(d, ignore_errors=True)
 
 
 def main():

@@ -144,19 +144,24 @@ __device__ __forceinline__ __nv_bfloat16 fromAcc<__nv_bfloat16, float>(float x) 
 // `ll.p[r]` is the LL region of rank r's pool: [parity][source rank][line]. A launch uses
 // parity = seq & 1; two halves suffice because a rank can run at most one launch ahead of
 // its slowest peer (it needs that peer's lines of launch s+1 to finish launch s+1).
+// Latency-critical: every loop over ranks / extra pointers is unrolled over a constant range
+// with a guard, so kernel parameters are only ever indexed with constants (a dynamic index
+// would make the compiler copy the parameter structs to local memory at kernel entry).
 template <typename T, typename TO>
 __global__ void __launch_bounds__(kThreads)
-llAllreduceKernel(CommArgs a, const T* in, TO* out, size_t count, DevOp op, float scale, PeerPtrs ll,
+llAllreduceKernel(CommArgs a, const T* in, TO* out, size_t count, DevOp op, float scale, PeerPtrs ll, char* myLL,
                   size_t srcStride, size_t parityStride, LocalPtrs extra) {
   constexpr int K = 8 / sizeof(T);
   using A = typename AccType<T>::type;
-  const uint32_t seq = ld_relaxed_sys(&a.sig[a.rank]->llSeq) + 1u;
+  const uint32_t seq = ld_relaxed_sys(&a.self->llSeq) + 1u;
   const size_t base = (seq & 1u) * parityStride;
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
   const size_t nunits = (count + K - 1) / K;
   const int P = a.nranks;
-  char* myRegion = static_cast<char*>(ll.p[a.rank]) + base;
+  const int me = a.rank;
+  const char* myRegion = myLL + base;
+  const size_t mySlot = base + static_cast<size_t>(me) * srcStride;
   const bool inAligned = reinterpret_cast<uintptr_t>(in) % 8 == 0;
   bool alive = true;
 
@@ -175,38 +180,47 @@ llAllreduceKernel(CommArgs a, const T* in, TO* out, size_t count, DevOp op, floa
         if (i0 + k < count) t[k] = in[i0 + k];
       }
     }
-    for (int e = 0; e < extra.n; e++) {
-      const T* x = static_cast<const T*>(extra.p[e]);
+    if (extra.n > 0) {
 #pragma unroll
-      for (int k = 0; k < K; k++) {
-        if (i0 + k < count) t[k] = PackTraits<T>::combineOne(t[k], x[i0 + k], op);
+      for (int e = 0; e < kMaxLocal; e++) {
+        if (e < extra.n) {
+          const T* x = static_cast<const T*>(extra.p[e]);
+#pragma unroll
+          for (int k = 0; k < K; k++) {
+            if (i0 + k < count) t[k] = PackTraits<T>::combineOne(t[k], x[i0 + k], op);
+          }
+        }
       }
     }
-    // push to every peer (rotated so that the P senders hit P different targets)
-    for (int i = 1; i < P; i++) {
-      const int r = (a.rank + i) % P;
-      llStore(static_cast<char*>(ll.p[r]) + base + static_cast<size_t>(a.rank) * srcStride + u * 16, w[0], w[1], seq);
+    // push to every peer: posted NVLink stores, no round trip
+#pragma unroll
+    for (int r = 0; r < kMaxRanks; r++) {
+      if (r < P && r != me) llStore(static_cast<char*>(ll.p[r]) + mySlot + u * 16, w[0], w[1], seq);
     }
     // gather in rank order: every rank sums in the same order -> bit-identical results
     A acc[K];
 #pragma unroll
     for (int k = 0; k < K; k++) acc[k] = A(0);
-    for (int r = 0; r < P; r++) {
-      uint32_t d[2];
-      if (r == a.rank) {
-        d[0] = w[0];
-        d[1] = w[1];
-      } else if (!llLoad(a, myRegion + static_cast<size_t>(r) * srcStride + u * 16, seq, d[0], d[1], r)) {
-        alive = false;
-        break;
-      }
-      const T* x = reinterpret_cast<const T*>(d);
-      if (r == 0) {
 #pragma unroll
-        for (int k = 0; k < K; k++) acc[k] = toAcc<T>(x[k]);
-      } else {
+    for (int r = 0; r < kMaxRanks; r++) {
+      if (r < P && alive) {
+        uint32_t d[2];
+        if (r == me) {
+          d[0] = w[0];
+          d[1] = w[1];
+        } else if (!llLoad(a, myRegion + static_cast<size_t>(r) * srcStride + u * 16, seq, d[0], d[1], r)) {
+          alive = false;
+        }
+        if (alive) {
+          const T* x = reinterpret_cast<const T*>(d);
+          if (r == 0) {
 #pragma unroll
-        for (int k = 0; k < K; k++) acc[k] = applyOp<A>(acc[k], toAcc<T>(x[k]), op);
+            for (int k = 0; k < K; k++) acc[k] = toAcc<T>(x[k]);
+          } else {
+#pragma unroll
+            for (int k = 0; k < K; k++) acc[k] = applyOp<A>(acc[k], toAcc<T>(x[k]), op);
+          }
+        }
       }
     }
     if (!alive) break;
@@ -222,12 +236,23 @@ llAllreduceKernel(CommArgs a, const T* in, TO* out, size_t count, DevOp op, floa
         const TO o = fromAcc<TO, A>(acc[k]);
         out[i0 + k] = o;
         if constexpr (std::is_same<T, TO>::value) {
-          for (int e = 0; e < extra.n; e++) static_cast<TO*>(extra.p[e])[i0 + k] = o;
+          if (extra.n > 0) {
+#pragma unroll
+            for (int e = 0; e < kMaxLocal; e++) {
+              if (e < extra.n) static_cast<TO*>(extra.p[e])[i0 + k] = o;
+            }
+          }
         }
       }
     }
   }
-  retire(a, 0, 0, 1);
+  // Publish the new sequence number. A single-CTA launch needs no completion ticket.
+  if (gridDim.x == 1) {
+    __syncthreads();
+    if (threadIdx.x == 0) a.self->llSeq = seq;
+  } else {
+    retire(a, 0, 0, 1);
+  }
 }
 
 // ---- one-shot ---------------------------------------------------------------------
@@ -242,7 +267,7 @@ oneShotPushAllreduceKernel(CommArgs a, const T* in, T* out, size_t count, DevOp 
                            size_t halfBytes, size_t slotBytes, LocalPtrs extra) {
   using PT = PackTraits<T>;
   const uint32_t e = loadEpoch(a);
-  const uint32_t parity = ld_relaxed_sys(&a.sig[a.rank]->stageSeq) & 1u;
+  const uint32_t parity = ld_relaxed_sys(&a.self->stageSeq) & 1u;
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
   const size_t base = parity * halfBytes;
@@ -289,7 +314,7 @@ oneShotAllreduceKernel(CommArgs a, const T* in, T* out, size_t count, DevOp op, 
                        size_t halfBytes, LocalPtrs extra) {
   using PT = PackTraits<T>;
   const uint32_t e = loadEpoch(a);
-  const uint32_t parity = ld_relaxed_sys(&a.sig[a.rank]->stageSeq) & 1u;
+  const uint32_t parity = ld_relaxed_sys(&a.self->stageSeq) & 1u;
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
   const size_t stageOff = parity * halfBytes;
@@ -729,7 +754,8 @@ void launchLLAllreduce(const CommArgs& a, const void* in, void* out, size_t coun
   const DevOp dop = static_cast<DevOp>(op);
 #define GLB_LL(TI, TO)                                                                                              \
   llAllreduceKernel<TI, TO><<<blocks, threads, 0, stream>>>(a, static_cast<const TI*>(in), static_cast<TO*>(out), \
-                                                           count, dop, scale, ll, srcStride, parityStride, extra)
+                                                           count, dop, scale, ll, static_cast<char*>(ll.p[a.rank]), \
+                                                           srcStride, parityStride, extra)
   if (dt != outDt) {
     if (dt == DataType::FLOAT32 && outDt == DataType::FLOAT16) GLB_LL(float, __half);
     else if (dt == DataType::FLOAT32 && outDt == DataType::BFLOAT16) GLB_LL(float, __nv_bfloat16);

@@ -71,6 +71,44 @@ __device__ __forceinline__ void gridCopyBody(char* dst, const char* src, size_t 
   }
 }
 
+// Body copy for a source that is 4-byte (not 8-byte) congruent with the 16-byte aligned
+// destination: instead of four 4-byte loads per pack, load the two ALIGNED packs that straddle
+// it and pick the words (the second load of one pack is the first load of the next and hits L1/L2).
+// The first and last pack use word loads so that no byte outside [src, src + 16 * nvec) is read.
+__device__ __forceinline__ void gridCopyBodyShifted(char* dst, const char* src, size_t nvec, size_t tid, size_t nthreads) {
+  const int shift = static_cast<int>((reinterpret_cast<uintptr_t>(src) % 16) / 4);  // 1..3 words
+  const char* base = src - shift * 4;                                                // 16-byte aligned
+  if (tid == 0 && nvec > 0) st128_stream(dst, ldPackWords<unsigned int>(src));
+  if (tid == 1 % nthreads && nvec > 1) st128_stream(dst + (nvec - 1) * 16, ldPackWords<unsigned int>(src + (nvec - 1) * 16));
+  constexpr int U = 4;
+  for (size_t v0 = 1 + tid; v0 + 1 < nvec; v0 += nthreads * U) {
+    Pack16 lo[U], hi[U];
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t v = v0 + u * nthreads;
+      if (v + 1 < nvec) {
+        lo[u] = ld128(base + v * 16);
+        hi[u] = ld128(base + v * 16 + 16);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const size_t v = v0 + u * nthreads;
+      if (v + 1 < nvec) {
+        Pack16 o;
+        if (shift == 1) {
+          o.w[0] = lo[u].w[1]; o.w[1] = lo[u].w[2]; o.w[2] = lo[u].w[3]; o.w[3] = hi[u].w[0];
+        } else if (shift == 2) {
+          o.w[0] = lo[u].w[2]; o.w[1] = lo[u].w[3]; o.w[2] = hi[u].w[0]; o.w[3] = hi[u].w[1];
+        } else {
+          o.w[0] = lo[u].w[3]; o.w[1] = hi[u].w[0]; o.w[2] = hi[u].w[1]; o.w[3] = hi[u].w[2];
+        }
+        st128_stream(dst + v * 16, o);
+      }
+    }
+  }
+}
+
 // Copy `bytes` from src to dst with the whole grid. The DESTINATION side (usually a peer,
 // i.e. NVLink stores) always moves in 128-bit stores: a byte-wise head brings dst to a
 // 16-byte boundary, the body loads with the widest access the (local) source allows at
@@ -98,7 +136,7 @@ __device__ __forceinline__ void gridCopy(char* dst, const char* src, size_t byte
   } else if (srcBody % 8 == 0) {
     gridCopyBody<unsigned long long>(dst + head, src + head, nvec, tid, nthreads);
   } else {
-    gridCopyBody<unsigned int>(dst + head, src + head, nvec, tid, nthreads);
+    gridCopyBodyShifted(dst + head, src + head, nvec, tid, nthreads);
   }
   for (size_t i = head + nvec * 16 + tid; i < bytes; i += nthreads) dst[i] = src[i];
 }
@@ -303,7 +341,7 @@ alltoallPushKernel(CommArgs a, const char* __restrict__ in, PeerPtrs outs, VArgs
   const int P = a.nranks;
   // v-variant: publish where I expect each source's chunk; peers read it after the
   // barrier (every CTA writes the same values, so no cross-CTA ordering is needed).
-  if (exchange && threadIdx.x < P) a.sig[a.rank]->xchg[threadIdx.x] = myRecv.off[threadIdx.x];
+  if (exchange && threadIdx.x < P) a.self->xchg[threadIdx.x] = myRecv.off[threadIdx.x];
   if (!blockBarrier(a, e + 1)) {
     retire(a, 2, 0);
     return;
@@ -545,7 +583,7 @@ __device__ __forceinline__ void store8(char* p, size_t avail, bool aligned, uint
 __global__ void __launch_bounds__(kThreads)
 llExchangeKernel(CommArgs a, const char* __restrict__ in, char* __restrict__ out, size_t bytes, int mode, PeerPtrs ll,
                  size_t srcStride, size_t parityStride) {
-  const uint32_t seq = ld_relaxed_sys(&a.sig[a.rank]->llSeq) + 1u;
+  const uint32_t seq = ld_relaxed_sys(&a.self->llSeq) + 1u;
   const size_t base = (seq & 1u) * parityStride;
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;

@@ -195,7 +195,7 @@ void runLL(PeerContext& pc, const void* in, void* out, size_t count, DataType dt
   const size_t units = ceilDiv(count * es, size_t(8));
   int threads = static_cast<int>(std::min<size_t>(kThreads, roundUp(std::max<size_t>(units, 32), 32)));
   int blocks = static_cast<int>(ceilDiv(units, static_cast<size_t>(threads)));
-  blocks = std::max(1, std::min({blocks, blocksHint > 0 ? blocksHint : 16, pc.maxBlocks()}));
+  blocks = std::max(1, std::min({blocks, blocksHint > 0 ? blocksHint : 16, pc.maxBlocks()}));  // no barrier: no co-residency need
   launchLLAllreduce(pc.comm(), in, out, count, dt, outDt, op, scale, pc.llPtrs(), pc.llSrcStride(), pc.llParityStride(),
                     extra, blocks, threads, stream);
 }
@@ -215,7 +215,7 @@ void runPipelined(PeerContext& pc, const void* in, void* out, size_t count, Data
   const size_t es = elementSize(dt);
   const size_t groups = ceilDiv(count * es, size_t(16));
   const bool mc = pc.nvlsAvailable() && pc.size > 2 && nvlsSupports(dt, op);
-  const void* kernel = pipelinedKernelFor(dt, mc);
+  const void* kernel = pipelinedKernelFor(dt, mc, pc.size);
   int blocks = plan.cfg.blocks > 0 ? plan.cfg.blocks : tuning().maxBlocks;
   blocks = std::max(1, std::min(blocks, pc.coResidentBlocks(kernel)));
   // Tile: a power of two, small enough for three slots in the bulk region and for a few
@@ -228,7 +228,9 @@ void runPipelined(PeerContext& pc, const void* in, void* out, size_t count, Data
   while (tile > 16 && (3 * chunkBytes(tile, blocks) > l.bulkBytes || groups * 16 < 4 * chunkBytes(tile, blocks))) tile /= 2;
   while (blocks > 1 && groups * 16 < chunkBytes(tile, blocks)) blocks = (blocks + 1) / 2;  // tiny messages: fewer CTAs
   GLB_ENFORCE_LE(3 * chunkBytes(tile, blocks), l.bulkBytes, "staging pool too small for the pipelined allreduce; raise GLB_CUDA_STAGE_MB");
-  int xthreads = std::max(32, std::min(kThreads - 32, tuning().pipeExchangeThreads / 32 * 32));
+  // cfg.unroll doubles as "exchange warps" for this kernel (0 = the pipeExchangeThreads knob).
+  int xthreads = plan.cfg.unroll > 0 ? plan.cfg.unroll * 32 : tuning().pipeExchangeThreads;
+  xthreads = std::max(32, std::min(kThreads - 32, xthreads / 32 * 32));
   launchPipelinedAllreduce(pc.comm(), in, out, count, dt, op, scale, pc.stagePtrs(l.bulkOff),
                            mc ? pc.stageMc(l.bulkOff) : nullptr, tile, xthreads, extra, blocks, stream);
 }
@@ -347,6 +349,7 @@ void allreduce(PeerContext& pc, const void* in, void* out, size_t count, DataTyp
     algo = plan.algo;
   }
   if (ep.blocks > 0) plan.cfg.blocks = ep.blocks;
+  if (ep.unroll > 0) plan.cfg.unroll = ep.unroll;
   if (ep.tile > 0) plan.tile = ep.tile;
   if (outDt != dt) {
     GLB_ENFORCE_LE(bytes, pc.llMaxBytes(), "allreduce with a dtype conversion on plain pointers is limited to ",

@@ -48,6 +48,8 @@ struct CommArgs {
   int rank;
   int nranks;
   SignalPad* sig[kMaxRanks];  // sig[r] = rank r's pad as mapped in this process
+  SignalPad* self;            // == sig[rank]; a plain field so that kernels need no dynamic
+                              // index into their parameter space to reach their own pad
   // Failure detection: a barrier that waits longer than this sets the abort word,
   // reports through `hostStatus` (mapped pinned host memory) and lets the kernel exit.
   unsigned long long timeoutNs;  // 0 = wait forever

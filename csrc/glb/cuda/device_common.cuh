@@ -82,7 +82,7 @@ static __device__ __noinline__ uint32_t waitFlagSlow(const uint32_t* flag, uint3
 // own time-out) and the host.
 __device__ __forceinline__ void reportAbort(const CommArgs& a, uint32_t code, int missingPeer) {
   if (code == kAbortTimeout) {
-    a.sig[a.rank]->abortRank = static_cast<uint32_t>(missingPeer);
+    a.self->abortRank = static_cast<uint32_t>(missingPeer);
     for (int r = 0; r < a.nranks; r++) {
       if (r != a.rank) st_relaxed_sys(&a.sig[r]->abort, static_cast<uint32_t>(kAbortPeer));
     }
@@ -96,7 +96,7 @@ __device__ __forceinline__ void reportAbort(const CommArgs& a, uint32_t code, in
 // Spin until *flag has reached `want` (wrap-safe). Returns false when the wait was abandoned.
 __device__ __forceinline__ bool waitFlag(const CommArgs& a, const uint32_t* flag, uint32_t want, int peer) {
   if (static_cast<int32_t>(ld_acquire_sys(flag) - want) >= 0) return true;
-  const uint32_t rc = waitFlagSlow(flag, want, &a.sig[a.rank]->abort, a.timeoutNs);
+  const uint32_t rc = waitFlagSlow(flag, want, &a.self->abort, a.timeoutNs);
   if (rc == 0u) return true;
   reportAbort(a, rc, peer);
   return false;
@@ -120,21 +120,21 @@ __device__ __forceinline__ bool blockBarrier(const CommArgs& a, uint32_t epoch) 
     } else {
       st_relaxed_sys(&a.sig[peer]->flag[blockIdx.x][a.rank], epoch);
     }
-    ok = waitFlag(a, &a.sig[a.rank]->flag[blockIdx.x][peer], epoch, peer) ? 1 : 0;
+    ok = waitFlag(a, &a.self->flag[blockIdx.x][peer], epoch, peer) ? 1 : 0;
   }
   return __syncthreads_and(ok) != 0;
 }
 
 // Read the epoch at kernel entry (all CTAs see the same value: it only changes
 // when the LAST CTA of a launch retires, after every CTA has read it).
-__device__ __forceinline__ uint32_t loadEpoch(const CommArgs& a) { return ld_relaxed_sys(&a.sig[a.rank]->epoch); }
+__device__ __forceinline__ uint32_t loadEpoch(const CommArgs& a) { return ld_relaxed_sys(&a.self->epoch); }
 
 // Called by every CTA at the very end; the last one publishes the new counters.
 __device__ __forceinline__ void retire(const CommArgs& a, uint32_t barriersUsed, uint32_t stagedLaunch,
                                        uint32_t llLaunch = 0) {
   __syncthreads();
   if (threadIdx.x == 0) {
-    SignalPad* me = a.sig[a.rank];
+    SignalPad* me = a.self;
     // No fences: the ticket is an L2 atomic (the last CTA sees every earlier arrival) and
     // the counters are next read by the NEXT launch, after this kernel has retired.
     uint32_t ticket = atomicAdd(&me->done, 1u);
@@ -177,7 +177,7 @@ static __device__ __noinline__ uint32_t llLoadSlow(const void* p, uint32_t seq, 
 }
 __device__ __forceinline__ bool llLoad(const CommArgs& a, const void* p, uint32_t seq, uint32_t& d0, uint32_t& d1, int peer) {
   if (llTryLoad(p, seq, d0, d1)) return true;
-  const uint32_t rc = llLoadSlow(p, seq, d0, d1, &a.sig[a.rank]->abort, a.timeoutNs);
+  const uint32_t rc = llLoadSlow(p, seq, d0, d1, &a.self->abort, a.timeoutNs);
   if (rc == 0u) return true;
   reportAbort(a, rc, peer);
   return false;

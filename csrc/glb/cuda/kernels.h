@@ -45,7 +45,7 @@ const void* nvlsKernelFor(DataType dt, int unroll);
 const void* castKernelFor(DataType in, DataType out);
 
 // pipeline_kernels.cu — arbitrary pointers through the pool, 3-stage in-kernel pipeline.
-const void* pipelinedKernelFor(DataType dt, bool mc);
+const void* pipelinedKernelFor(DataType dt, bool mc, int nranks);
 void launchPipelinedAllreduce(const CommArgs& a, const void* in, void* out, size_t count, DataType dt, ReduceOp op,
                               float scale, const PeerPtrs& stage, void* mcStage, int tileVecs, int exchangeThreads,
                               const LocalPtrs& extra, int blocks, cudaStream_t stream);

@@ -273,5 +273,15 @@ void NcclComm::alltoall(const void* src, void* dst, size_t countPerRank, DataTyp
   check(a.ncclGroupEnd(), "ncclGroupEnd");
 }
 
+void NcclComm::sendrecv(const void* src, int dst, void* dstBuf, int srcRank, size_t count, DataType dt,
+                        cudaStream_t stream) {
+  DeviceGuard g(device_);
+  const auto& a = api();
+  check(a.ncclGroupStart(), "ncclGroupStart");
+  check(a.ncclSend(src, count, toType(dt), dst, static_cast<ncclComm_t>(comm_), stream), "ncclSend");
+  check(a.ncclRecv(dstBuf, count, toType(dt), srcRank, static_cast<ncclComm_t>(comm_), stream), "ncclRecv");
+  check(a.ncclGroupEnd(), "ncclGroupEnd");
+}
+
 }  // namespace cuda
 }  // namespace glb

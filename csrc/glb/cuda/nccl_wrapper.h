@@ -41,6 +41,8 @@ class NcclComm {
   // alltoall through grouped send/recv (what NCCL users write by hand).
   void alltoall(const void* src, void* dst, size_t countPerRank, DataType dt, cudaStream_t stream);
 
+  // Grouped ncclSend + ncclRecv: the neighbour exchange of ring attention / pipeline stages.
+  void sendrecv(const void* src, int dst, void* dstBuf, int srcRank, size_t count, DataType dt, cudaStream_t stream);
   // NCCL-owned, communicator-registered buffers (ncclMemAlloc + ncclCommRegister).
   void* memAlloc(size_t bytes);
   void memFree(void* p);

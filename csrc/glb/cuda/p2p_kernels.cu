@@ -69,7 +69,7 @@ __device__ __forceinline__ bool ctaWait(const CommArgs& a, const uint32_t* flag,
 __global__ void __launch_bounds__(kThreads)
 p2pKernel(CommArgs a, const char* sendPtr, size_t sendBytes, int dst, char* recvPtr, size_t recvBytes, int src,
           PeerPtrs mailbox, size_t boxStride, size_t slotBytes, int nslots, int lanes, int sendLanes) {
-  SignalPad* me = a.sig[a.rank];
+  SignalPad* me = a.self;
   const size_t stripe = slotBytes / static_cast<size_t>(lanes) / 16 * 16;
   const size_t chunkBytes = stripe * lanes;
   if (static_cast<int>(blockIdx.x) < sendLanes) {

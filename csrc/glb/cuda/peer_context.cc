@@ -1,11 +1,13 @@
 #include "glb/cuda/peer_context.h"
 
+#include <dlfcn.h>
 #include <sys/socket.h>
 #include <sys/un.h>
 #include <poll.h>
 #include <unistd.h>
 
 #include <atomic>
+#include <cctype>
 #include <cerrno>
 #include <cstring>
 #include <set>
@@ -13,6 +15,7 @@
 
 #include "glb/allgather.h"
 #include "glb/barrier.h"
+#include "glb/common/linux.h"
 #include "glb/common/utils.h"
 #include "glb/cuda/kernels.h"
 #include "glb/cuda/tuning.h"
@@ -204,6 +207,7 @@ PeerContext::PeerContext(std::shared_ptr<Context> context, int dev, PeerOptions 
   comm_.rank = rank;
   comm_.nranks = size;
   for (int i = 0; i < kMaxRanks; i++) comm_.sig[i] = static_cast<SignalPad*>(i < size ? pool_->peer[i] : nullptr);
+  comm_.self = comm_.sig[rank];
   // Status word the kernels raise when a device-side wait gives up.
   GLB_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&hostStatus_), 64, cudaHostAllocMapped | cudaHostAllocPortable));
   *hostStatus_ = 0;
@@ -256,6 +260,33 @@ void PeerContext::hostBarrier() {
   barrier(o);
 }
 
+namespace {
+// NVLink state through NVML, loaded at run time (the library ships with the driver).
+void queryNvlink(const char* pciBusId, int32_t* active, int32_t* version) {
+  *active = -1;
+  *version = -1;
+  static void* lib = dlopen("libnvidia-ml.so.1", RTLD_NOW);
+  if (lib == nullptr) return;
+  using Handle = void*;
+  auto init = reinterpret_cast<int (*)()>(dlsym(lib, "nvmlInit_v2"));
+  auto byPci = reinterpret_cast<int (*)(const char*, Handle*)>(dlsym(lib, "nvmlDeviceGetHandleByPciBusId_v2"));
+  auto state = reinterpret_cast<int (*)(Handle, unsigned, unsigned*)>(dlsym(lib, "nvmlDeviceGetNvLinkState"));
+  auto ver = reinterpret_cast<int (*)(Handle, unsigned, unsigned*)>(dlsym(lib, "nvmlDeviceGetNvLinkVersion"));
+  if (init == nullptr || byPci == nullptr || state == nullptr || init() != 0) return;
+  Handle h = nullptr;
+  if (byPci(pciBusId, &h) != 0) return;
+  int n = 0;
+  for (unsigned link = 0; link < 32; link++) {
+    unsigned on = 0;
+    if (state(h, link, &on) != 0) break;
+    n += on ? 1 : 0;
+  }
+  *active = n;
+  unsigned v = 0;
+  if (ver != nullptr && ver(h, 0, &v) == 0) *version = static_cast<int32_t>(v);
+}
+}  // namespace
+
 void PeerContext::exchangeTopology() {
   DeviceInfo me;
   std::memset(&me, 0, sizeof(me));
@@ -271,6 +302,20 @@ void PeerContext::exchangeTopology() {
   me.ccMinor = prop.minor;
   me.totalMem = prop.totalGlobalMem;
   std::strncpy(me.fdSocket, fdChannel_->name().c_str(), sizeof(me.fdSocket) - 1);
+  queryNvlink(me.pciBusId, &me.nvlinkActive, &me.nvlinkVersion);
+  me.nicDistance = -1;
+  {
+    // lower-case bus id as sysfs spells it
+    std::string gpu(me.pciBusId);
+    for (auto& c : gpu) c = static_cast<char>(std::tolower(static_cast<unsigned char>(c)));
+    for (const auto& nic : pciDevices(kPCIClassNetwork, 0xff0000)) {
+      const int d = pciDistance(gpu, nic);
+      if (d >= 0 && (me.nicDistance < 0 || d < me.nicDistance)) {
+        me.nicDistance = d;
+        std::strncpy(me.nearestNic, nic.c_str(), sizeof(me.nearestNic) - 1);
+      }
+    }
+  }
   try {
     const auto& d = driver();
     CUdevice cudev;
@@ -340,7 +385,9 @@ std::string PeerContext::describe() const {
   os << "PeerContext rank " << rank << "/" << size << " dev " << device << " (" << infos_[rank].pciBusId
      << ", " << infos_[rank].smCount << " SMs, sm_" << infos_[rank].ccMajor << infos_[rank].ccMinor << ")"
      << " peerAccess=" << peerOk_ << " alloc=" << (vmm_ ? "vmm+fd" : "cudaIpc")
-     << " nvls=" << (nvlsAvailable() ? "yes" : "no") << " ranksOnDevice=" << ranksOnMyDevice_
+     << " nvls=" << (nvlsAvailable() ? "yes" : "no") << " nvlinks=" << infos_[rank].nvlinkActive << "(v"
+     << infos_[rank].nvlinkVersion << ") nic=" << (infos_[rank].nearestNic[0] ? infos_[rank].nearestNic : "?") << "@"
+     << infos_[rank].nicDistance << " ranksOnDevice=" << ranksOnMyDevice_
      << " maxBlocks=" << maxBlocks_ << " stageMB=" << (stageBytes_ >> 20);
   return os.str();
 }
@@ -445,6 +492,7 @@ CommArgs PeerContext::loopbackComm(int virtualRanks) const {
   c.rank = 0;
   c.nranks = virtualRanks;
   SignalPad* me = static_cast<SignalPad*>(pool_->local);
+  c.self = me;
   for (int i = 0; i < kMaxRanks; i++) {
     // sig[i]->flag[b][0] aliases me->flag[b][i]
     c.sig[i] = i < virtualRanks ? reinterpret_cast<SignalPad*>(reinterpret_cast<uint32_t*>(me) + i) : nullptr;

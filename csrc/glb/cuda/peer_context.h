@@ -48,13 +48,20 @@ struct DeviceInfo {
   int32_t multicastSupported;
   uint64_t totalMem;
   char fdSocket[64];  // abstract unix socket that accepts SCM_RIGHTS messages for this rank
+  // NVLink state from NVML (-1 when the library is unavailable) and the PCI position of the
+  // GPU relative to the box's network controllers (the reference knows GPU <-> NIC distances
+  // only: cuda_private.h:64-100, common/linux.cc).
+  int32_t nvlinkActive;     // links in the "active" state
+  int32_t nvlinkVersion;    // NVML's NVLink version of link 0 (e.g. 7 for NVLink 5)
+  int32_t nicDistance;      // PCI hops to the closest network controller, -1 unknown
+  char nearestNic[24];      // its bus id
 };
 
 struct PeerOptions {
   size_t stageBytes = 128ull << 20;  // staging area for unregistered buffers (per rank)
   bool useVmm = true;                // try cuMem + fd passing before cudaIpc
   bool useNvls = true;               // bind symmetric memory to a multicast object when possible
-  size_t llMaxBytes = 64 * 1024;     // largest message of the flag-in-data (LL) kernels
+  size_t llMaxBytes = 256 * 1024;    // largest message of the flag-in-data (LL) kernels
   size_t p2pSlotBytes = 512 * 1024;  // one slot of a point-to-point mailbox ring
   int p2pSlots = 4;                  // slots per (source, destination) ring
   int p2pLanes = 16;                 // CTAs per direction of a point-to-point transfer

@@ -58,12 +58,12 @@ __device__ __forceinline__ void storeGroupP(T* base, size_t g, size_t count, boo
 
 }  // namespace
 
-template <typename T, bool MC>
+template <typename T, bool MC, int NR>
 __global__ void __launch_bounds__(kThreads)
 pipelinedAllreduceKernel(CommArgs a, const T* in, T* out, size_t count, DevOp op, float scale, PeerPtrs stage,
                          char* mcStage, int tileVecs, int exchangeThreads, LocalPtrs extra) {
   using PT = PackTraits<T>;
-  const int P = a.nranks;
+  const int P = NR > 0 ? NR : a.nranks;
   const int G = gridDim.x;
   const int b = blockIdx.x;
   const size_t T_ = static_cast<size_t>(tileVecs);  // power of two (host enforces)
@@ -113,23 +113,43 @@ pipelinedAllreduceKernel(CommArgs a, const T* in, T* out, size_t count, DevOp op
             }
           }
         } else {
-          for (size_t o = xt; o < T_; o += xn) {
-            const size_t off = slot + (w0 + o) * 16;
-            Pack16 v[kMaxRanks];
+          // Peer exchange inside the pool, like the two-shot kernel: kSlots x U independent
+          // 128-bit loads in flight per thread (an NVLink round trip is ~2 us).
+          constexpr int kSlots = NR > 0 ? NR : kMaxRanks;
+          constexpr int U = NR == 2 ? 8 : (NR == 4 ? 4 : (NR == 8 ? 2 : 1));
+          char* peer[kSlots];
 #pragma unroll
-            for (int q = 0; q < kMaxRanks; q++) {
-              if (q < P) v[q] = ld128_stream(static_cast<const char*>(stage.p[(a.rank + q) % P]) + off);
+          for (int q = 0; q < kSlots; q++) {
+            peer[q] = q < P ? static_cast<char*>(stage.p[(a.rank + q) % P]) + slot + w0 * 16 : nullptr;
+          }
+          for (size_t o0 = xt; o0 < T_; o0 += static_cast<size_t>(xn) * U) {
+            Pack16 v[U][kSlots];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+              const size_t o = o0 + static_cast<size_t>(u) * xn;
+              if (o < T_) {
+#pragma unroll
+                for (int q = 0; q < kSlots; q++) {
+                  if (q < P) v[u][q] = ld128_stream(peer[q] + o * 16);
+                }
+              }
             }
-            typename PT::AccPack acc = PT::widen(v[0]);
 #pragma unroll
-            for (int q = 1; q < kMaxRanks; q++) {
-              if (q < P) PT::combine(acc, v[q], op);
-            }
-            if (scale != 1.0f) PT::scale(acc, scale);
-            const Pack16 res = PT::narrow(acc);
+            for (int u = 0; u < U; u++) {
+              const size_t o = o0 + static_cast<size_t>(u) * xn;
+              if (o < T_) {
+                typename PT::AccPack acc = PT::widen(v[u][0]);
 #pragma unroll
-            for (int q = 0; q < kMaxRanks; q++) {
-              if (q < P) st128_stream(static_cast<char*>(stage.p[(a.rank + q) % P]) + off, res);
+                for (int q = 1; q < kSlots; q++) {
+                  if (q < P) PT::combine(acc, v[u][q], op);
+                }
+                if (scale != 1.0f) PT::scale(acc, scale);
+                const Pack16 res = PT::narrow(acc);
+#pragma unroll
+                for (int q = 0; q < kSlots; q++) {
+                  if (q < P) st128_stream(peer[q] + o * 16, res);
+                }
+              }
             }
           }
         }
@@ -201,39 +221,45 @@ pipelinedAllreduceKernel(CommArgs a, const T* in, T* out, size_t count, DevOp op
 
 namespace {
 template <typename T>
-const void* pipeFn(bool mc) {
-  if constexpr (std::is_same<T, float>::value || std::is_same<T, __half>::value || std::is_same<T, __nv_bfloat16>::value) {
-    if (mc) return reinterpret_cast<const void*>(pipelinedAllreduceKernel<T, true>);
+const void* pipeFn(bool mc, int nranks) {
+  constexpr bool hot = std::is_same<T, float>::value || std::is_same<T, __half>::value || std::is_same<T, __nv_bfloat16>::value;
+  if constexpr (hot) {
+    if (mc) return reinterpret_cast<const void*>(pipelinedAllreduceKernel<T, true, 0>);
+    if (nranks == 2) return reinterpret_cast<const void*>(pipelinedAllreduceKernel<T, false, 2>);
+    if (nranks == 4) return reinterpret_cast<const void*>(pipelinedAllreduceKernel<T, false, 4>);
+    if (nranks == 8) return reinterpret_cast<const void*>(pipelinedAllreduceKernel<T, false, 8>);
   }
-  return reinterpret_cast<const void*>(pipelinedAllreduceKernel<T, false>);
+  return reinterpret_cast<const void*>(pipelinedAllreduceKernel<T, false, 0>);
 }
 
-const void* pipeKernelForImpl(DataType dt, bool mc) {
+const void* pipeKernelForImpl(DataType dt, bool mc, int nranks) {
   switch (dt) {
-    case DataType::INT8: return pipeFn<int8_t>(false);
-    case DataType::UINT8: return pipeFn<uint8_t>(false);
-    case DataType::INT16: return pipeFn<int16_t>(false);
-    case DataType::INT32: return pipeFn<int32_t>(false);
-    case DataType::UINT32: return pipeFn<uint32_t>(false);
-    case DataType::INT64: return pipeFn<long long>(false);
-    case DataType::UINT64: return pipeFn<unsigned long long>(false);
-    case DataType::FLOAT32: return pipeFn<float>(mc);
-    case DataType::FLOAT64: return pipeFn<double>(false);
-    case DataType::FLOAT16: return pipeFn<__half>(mc);
-    case DataType::BFLOAT16: return pipeFn<__nv_bfloat16>(mc);
+    case DataType::INT8: return pipeFn<int8_t>(false, nranks);
+    case DataType::UINT8: return pipeFn<uint8_t>(false, nranks);
+    case DataType::INT16: return pipeFn<int16_t>(false, nranks);
+    case DataType::INT32: return pipeFn<int32_t>(false, nranks);
+    case DataType::UINT32: return pipeFn<uint32_t>(false, nranks);
+    case DataType::INT64: return pipeFn<long long>(false, nranks);
+    case DataType::UINT64: return pipeFn<unsigned long long>(false, nranks);
+    case DataType::FLOAT32: return pipeFn<float>(mc, nranks);
+    case DataType::FLOAT64: return pipeFn<double>(false, nranks);
+    case DataType::FLOAT16: return pipeFn<__half>(mc, nranks);
+    case DataType::BFLOAT16: return pipeFn<__nv_bfloat16>(mc, nranks);
   }
   return nullptr;
 }
 }  // namespace
 
-const void* pipelinedKernelFor(DataType dt, bool mc) { return pipeKernelForImpl(dt, mc); }
+const void* pipelinedKernelFor(DataType dt, bool mc, int nranks) { return pipeKernelForImpl(dt, mc, nranks); }
 
 void preloadPipelineKernels() {
   for (DataType dt : {DataType::INT8, DataType::UINT8, DataType::INT16, DataType::INT32, DataType::UINT32, DataType::INT64,
                       DataType::UINT64, DataType::FLOAT32, DataType::FLOAT64, DataType::FLOAT16, DataType::BFLOAT16}) {
     for (bool mc : {false, true}) {
-      cudaFuncAttributes attr;
-      cudaFuncGetAttributes(&attr, pipeKernelForImpl(dt, mc));
+      for (int nr : {0, 2, 4, 8}) {
+        cudaFuncAttributes attr;
+        cudaFuncGetAttributes(&attr, pipeKernelForImpl(dt, mc, nr));
+      }
     }
   }
   cudaGetLastError();
@@ -243,7 +269,7 @@ void launchPipelinedAllreduce(const CommArgs& a, const void* in, void* out, size
                               float scale, const PeerPtrs& stage, void* mcStage, int tileVecs, int exchangeThreads,
                               const LocalPtrs& extra, int blocks, cudaStream_t stream) {
   const bool mc = mcStage != nullptr && nvlsSupports(dt, op);
-  const void* k = pipeKernelForImpl(dt, mc);
+  const void* k = pipeKernelForImpl(dt, mc, a.nranks);
   CommArgs ca = a;
   PeerPtrs st = stage;
   LocalPtrs ex = extra;

@@ -325,13 +325,13 @@ std::vector<SelfTestResult> loopbackSelfTest(PeerContext& pc, cudaStream_t strea
 
   // ---- pipelined kernel for plain pointers (P virtual ranks alias my pool) ---------------------
   for (int P : {2, 8}) {
-    R.run(strcat_all("pipelinedAllreduceKernel<float,false> P=", P), [&]() -> std::string {
+    R.run(strcat_all("pipelinedAllreduceKernel<float,false,", P, ">"), [&]() -> std::string {
       const CommArgs ca = pc.loopbackComm(P);
       const size_t bulkOff = 2 * half;
       PeerPtrs st;
       std::memset(&st, 0, sizeof(st));
       for (int r = 0; r < P; r++) st.p[r] = myStage + bulkOff;
-      const int blocks = std::min(pc.coResidentBlocks(pipelinedKernelFor(DataType::FLOAT32, false)), 8), tile = 64;
+      const int blocks = std::min(pc.coResidentBlocks(pipelinedKernelFor(DataType::FLOAT32, false, P)), 8), tile = 64;
       const size_t chunkVecs = static_cast<size_t>(P) * blocks * tile;
       GLB_ENFORCE_LE(3 * chunkVecs * 16, pc.stageBytes() - bulkOff, "pool too small for the pipelined self-test");
       DevBuf in(n * 4), out(n * 4);
@@ -432,7 +432,7 @@ bool loopbackTimeoutTest(PeerContext& pc, cudaStream_t stream, int timeoutMs, do
   // Virtual rank 1's pad lives elsewhere: my flag for it lands there, its flag for me never comes.
   DevBuf lonely(sizeof(SignalPad));
   GLB_CUDA_CHECK(cudaMemsetAsync(lonely.p, 0, sizeof(SignalPad), stream));
-  ca.sig[1] = static_cast<SignalPad*>(lonely.p);
+  ca.sig[1] = static_cast<SignalPad*>(lonely.p);  // (ca.self stays my real pad)
   ca.timeoutNs = static_cast<unsigned long long>(timeoutMs) * 1000000ull;
   cudaEvent_t a, b;
   GLB_CUDA_CHECK(cudaEventCreate(&a));
@@ -474,7 +474,7 @@ std::vector<SelfTestResult> localOpsSelfTest(const std::vector<int>& devices, si
   GLB_ENFORCE_GE(n, 1);
   std::vector<CudaDevicePointer<float>> ptrs;
   std::vector<CudaStream> streams;
-  const int nptr = std::max(n, 3);
+  const int nptr = n >= 2 ? n : 3;  // several devices: one pointer each (what the NCCL flavours need)
   for (int i = 0; i < nptr; i++) {
     const int dev = devices[i % n];
     DeviceGuard g(dev);

@@ -61,7 +61,11 @@ void registerCuda(py::module_& root) {
       .def_readonly("cc_minor", &DeviceInfo::ccMinor)
       .def_readonly("vmm_supported", &DeviceInfo::vmmSupported)
       .def_readonly("multicast_supported", &DeviceInfo::multicastSupported)
-      .def_readonly("total_mem", &DeviceInfo::totalMem);
+      .def_readonly("total_mem", &DeviceInfo::totalMem)
+      .def_readonly("nvlink_active", &DeviceInfo::nvlinkActive)
+      .def_readonly("nvlink_version", &DeviceInfo::nvlinkVersion)
+      .def_readonly("nic_distance", &DeviceInfo::nicDistance)
+      .def_property_readonly("nearest_nic", [](const DeviceInfo& d) { return std::string(d.nearestNic); });
 
   py::class_<PeerBuffer, std::shared_ptr<PeerBuffer>>(m, "PeerBuffer")
       .def_property_readonly("ptr", [](const PeerBuffer& b) { return reinterpret_cast<uintptr_t>(b.local); })
@@ -163,14 +167,14 @@ void registerCuda(py::module_& root) {
 
   m.def("allreduce", [](PeerContext& pc, uintptr_t in, uintptr_t out, size_t count, int dtype, int op, int algo,
                         uintptr_t stream, double scale, int outDtype, std::vector<uintptr_t> extra, int blocks,
-                        int tile) {
-    const Epilogue ep = makeEpilogue(scale, outDtype, extra, blocks, 0, tile);
+                        int tile, int unroll) {
+    const Epilogue ep = makeEpilogue(scale, outDtype, extra, blocks, unroll, tile);
     py::gil_scoped_release nogil;
     allreduce(pc, P(in), P(out), count, static_cast<DataType>(dtype), static_cast<ReduceOp>(op),
               static_cast<AllreduceAlgo>(algo), S(stream), ep);
   }, py::arg("pc"), py::arg("input"), py::arg("output"), py::arg("count"), py::arg("dtype"), py::arg("op") = 1,
      py::arg("algo") = 0, py::arg("stream") = 0, py::arg("scale") = 1.0, py::arg("out_dtype") = -1,
-     py::arg("extra") = std::vector<uintptr_t>(), py::arg("blocks") = 0, py::arg("tile") = 0);
+     py::arg("extra") = std::vector<uintptr_t>(), py::arg("blocks") = 0, py::arg("tile") = 0, py::arg("unroll") = 0);
 
   m.def("allreduce_cast", [](PeerContext& pc, const PeerBuffer& in, size_t inOff, const PeerBuffer& out, size_t outOff,
                              size_t count, int dtype, int outDtype, int op, uintptr_t stream, double scale, int blocks) {

@@ -90,6 +90,9 @@ void registerCudaAlgorithms(py::module_& m) {
       .def("alltoall", [](NcclComm& c, uintptr_t src, uintptr_t dst, size_t n, int dt, uintptr_t st) {
         c.alltoall(P(src), P(dst), n, static_cast<DataType>(dt), S(st));
       })
+      .def("sendrecv", [](NcclComm& c, uintptr_t src, int dst, uintptr_t dstBuf, int srcRank, size_t n, int dt, uintptr_t st) {
+        c.sendrecv(P(src), dst, P(dstBuf), srcRank, n, static_cast<DataType>(dt), S(st));
+      })
       .def("mem_alloc", [](NcclComm& c, size_t bytes) { return reinterpret_cast<uintptr_t>(c.memAlloc(bytes)); },
            "ncclMemAlloc: a buffer NCCL can register for NVLS / zero-copy.")
       .def("mem_free", [](NcclComm& c, uintptr_t p) { c.memFree(P(p)); })

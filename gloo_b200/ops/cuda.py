@@ -167,7 +167,7 @@ class CudaContext:
                 _cu.allreduce_registered(self.pc, buf, off, n, int(dt), int(op), _algo(algo), s, scale, ex, blocks,
                                          unroll, tile)
                 return tensor
-            _cu.allreduce(self.pc, ptr, ptr, n, int(dt), int(op), _algo(algo), s, scale, -1, ex, blocks, tile)
+            _cu.allreduce(self.pc, ptr, ptr, n, int(dt), int(op), _algo(algo), s, scale, -1, ex, blocks, tile, unroll)
             return tensor
         _, _, odt, _ = describe(out)
         if odt != dt:
@@ -177,9 +177,9 @@ class CudaContext:
                 _cu.allreduce_cast(self.pc, ibuf, ioff, obuf, ooff, n, int(dt), int(odt), int(op), s, scale, blocks)
                 return out
             _cu.allreduce(self.pc, ptr, out.data_ptr(), n, int(dt), int(op), _algo(algo), s, scale, int(odt), ex, blocks,
-                          tile)
+                          tile, unroll)
             return out
-        _cu.allreduce(self.pc, ptr, out.data_ptr(), n, int(dt), int(op), _algo(algo), s, scale, -1, ex, blocks, tile)
+        _cu.allreduce(self.pc, ptr, out.data_ptr(), n, int(dt), int(op), _algo(algo), s, scale, -1, ex, blocks, tile, unroll)
         return out
 
     def plan(self, tensor, op: ReduceOp = ReduceOp.SUM) -> dict:

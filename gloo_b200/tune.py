@@ -35,6 +35,77 @@ def geometric_sizes(lo: int, hi: int, per_octave: int = 1):
     return sorted(set(max(4, s) for s in out))
 
 
+def compress(results, P, dtype_name="float32", device_name="NVIDIA B200", cores=148):
+    """Measurements -> table lines (see the module docstring)."""
+    # ---- compress into a table ---------------------------------------------------------------------------
+    # Raw "fastest candidate per size" is noisy: shapes within a few percent of each other trade
+    # places from size to size. Per (collective, buffer kind): (1) pick the fastest ALGORITHM per
+    # size; (2) for every run of consecutive sizes with the same algorithm pick ONE launch shape
+    # if some shape is within TOL of the best at every size of the run, else split the run.
+    TOL = 1.04
+    lines = [f"# gloo_b200 tuning table: P={P} dtype={dtype_name} device={device_name}",
+             f"# measured by gloo_b200.tune ({len(results)} measurements); {cores} SMs; shapes merged within {int((TOL - 1) * 100)} % of the best"]
+    by = {}
+    for r in results:
+        if r.get("us") and r["kind"] != "nccl":
+            by.setdefault((r["coll"], r["kind"]), {}).setdefault(r["bytes"], []).append(r)
+
+    def shape(c):
+        return (c.get("blocks", 0), c.get("unroll", 0), c.get("tile", 0))
+
+    def pick(run):
+        """run: list of (bytes, [candidates of the chosen algo]) -> list of (last_bytes, shape)."""
+        common = None
+        for _, cands in run:
+            best = min(c["us"] for c in cands)
+            ok = {shape(c) for c in cands if c["us"] <= best * TOL}
+            common = ok if common is None else (common & ok)
+        if common:
+            # among the shapes good everywhere take the one with the smallest total time
+            tot = {sh: sum(min(c["us"] for c in cands if shape(c) == sh) for _, cands in run) for sh in common}
+            return [(run[-1][0], min(tot, key=tot.get))]
+        if len(run) == 1:
+            return [(run[0][0], shape(min(run[0][1], key=lambda c: c["us"])))]
+        mid = len(run) // 2
+        return pick(run[:mid]) + pick(run[mid:])
+
+    for (coll, kind), per_size in sorted(by.items()):
+        sizes_here = sorted(per_size)
+        chosen = []  # (bytes, algo, candidates of that algo)
+        for nb in sizes_here:
+            best = min(per_size[nb], key=lambda c: c["us"])
+            chosen.append((nb, best["algo"], [c for c in per_size[nb] if c["algo"] == best["algo"]]))
+        entries = []  # (last_bytes, algo, shape)
+        i = 0
+        while i < len(chosen):
+            j = i
+            while j + 1 < len(chosen) and chosen[j + 1][1] == chosen[i][1]:
+                j += 1
+            for last, sh in pick([(c[0], c[2]) for c in chosen[i:j + 1]]):
+                entries.append((last, chosen[i][1], sh))
+            i = j + 1
+        # merge neighbours that ended up identical
+        merged = []
+        for e in entries:
+            if merged and merged[-1][1:] == e[1:]:
+                merged[-1] = e
+            else:
+                merged.append(e)
+        for k, (last, algo, (bl, un, tl)) in enumerate(merged):
+            if k == len(merged) - 1:
+                bound = "inf"
+            else:
+                nxt = next(x for x in sizes_here if x > last)
+                bound = str(int((last * nxt) ** 0.5))  # geometric midpoint between measured sizes
+            line = f"{coll} P={P} buf={kind} maxbytes={bound} algo={algo} blocks={bl}"
+            if un:
+                line += f" unroll={un}"
+            if tl:
+                line += f" tile={tl}"
+            lines.append(line)
+    return lines
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="gpurun_out/tune")
@@ -47,7 +118,13 @@ def main(argv=None):
     ap.add_argument("--kinds", default="sym,reg,user")
     ap.add_argument("--no-nccl", action="store_true")
     ap.add_argument("--stage-mb", type=int, default=256)
+    ap.add_argument("--compress-json", default="", help="no measurement: rebuild the table from a saved <out>.json")
     args = ap.parse_args(argv)
+    if args.compress_json:
+        with open(args.compress_json) as f:
+            saved = json.load(f)
+        print("\n".join(compress(saved["results"], saved["world"], saved.get("dtype", "float32"))))
+        return 0
 
     import torch
 
@@ -146,7 +223,9 @@ def main(argv=None):
                 t = {"sym": sym, "reg": reg, "user": plain}[kind]
                 cands = []
                 if nb <= ll_max:
-                    for b in (1, 4, 16):
+                    for b in (1, 4, 16, 64):
+                        if b > 1 and nb < b * 512:
+                            continue  # more CTAs than 8-byte units to hand out
                         cands.append(attempt("ll", lambda: cc.allreduce(t, algo="ll", stream=stream, blocks=b), nb, blocks=b))
                 if nb * P <= (256 << 10) * 2 and nb <= (128 << 10):
                     for b in (2, 8, 16):
@@ -163,10 +242,12 @@ def main(argv=None):
                             cands.append(attempt("nvls", lambda: cc.allreduce(t, algo="nvls", stream=stream, blocks=b, unroll=u), nb,
                                                  blocks=b, unroll=u))
                 if kind == "user" and nb >= 32768:
-                    for b in ([64, 96, 128, 148] if not args.quick else [96, 148]):
+                    for b in ([64, 128, 148] if not args.quick else [148]):
                         for tile in (256, 1024, 4096):
-                            cands.append(attempt("pipelined", lambda: cc.allreduce(t, algo="pipelined", stream=stream, blocks=b, tile=tile), nb,
-                                                 blocks=b, tile=tile))
+                            for xw in (4, 8, 12):  # exchange warps of the 16 per CTA
+                                cands.append(attempt("pipelined", lambda: cc.allreduce(t, algo="pipelined", stream=stream, blocks=b,
+                                                                                       tile=tile, unroll=xw), nb,
+                                                     blocks=b, tile=tile, unroll=xw))
                 best = record("allreduce", kind, nb, cands)
                 if best:
                     bus = nb / (best["us"] * 1e-6) / 1e9 * 2 * (P - 1) / P
@@ -237,33 +318,7 @@ def main(argv=None):
         if coll in collectives and world > 1:
             movement(coll)
 
-    # ---- compress into a table ---------------------------------------------------------------------------
-    lines = [f"# gloo_b200 tuning table: P={P} dtype={args.dtype} device={torch.cuda.get_device_name(local)}",
-             f"# measured by gloo_b200.tune ({len(results)} measurements); {cores} SMs"]
-    groups = {}
-    for coll, kind, nb, best in table:
-        groups.setdefault((coll, kind), []).append((nb, best))
-    for (coll, kind), rows in sorted(groups.items()):
-        rows.sort(key=lambda r: r[0])
-        merged = []
-        for nb, best in rows:
-            key = (best["algo"], best.get("blocks", 0), best.get("unroll", 0), best.get("tile", 0))
-            if merged and merged[-1][1] == key:
-                merged[-1][0] = nb
-            else:
-                merged.append([nb, key, best["us"]])
-        for i, (nb, key, us) in enumerate(merged):
-            last = i == len(merged) - 1
-            # boundary: geometric midpoint between this size and the next measured size
-            nxt = None if last else next(r[0] for r in rows if r[0] > nb)
-            bound = "inf" if last else str(int((nb * nxt) ** 0.5))
-            algo, b, u, tl = key
-            line = f"{coll} P={P} buf={kind} maxbytes={bound} algo={algo} blocks={b}"
-            if u:
-                line += f" unroll={u}"
-            if tl:
-                line += f" tile={tl}"
-            lines.append(line)
+    lines = compress(results, P, args.dtype, torch.cuda.get_device_name(local), cores)
     text = "\n".join(lines) + "\n"
     if rank == 0:
         os.makedirs(os.path.dirname(args.out) or ".", exist_ok=True)

@@ -91,6 +91,61 @@ def main():
     torch.testing.assert_close(rs.double().cpu(), exp_sum(n)[off:off + counts[rank]], rtol=1e-5, atol=0)
     if rank == 0:
         torch.testing.assert_close(red.double().cpu(), exp_sum(n), rtol=1e-5, atol=0)
+    # ---- round 2: fused epilogues, LL, pipelined plain pointers, p2p, one-sided, CUDA graphs ----
+    for algo in ["ll", "one_shot", "two_shot", "pipelined"] + (["nvls"] if cc.nvls_available() else []):
+        n = 1000 if algo in ("ll", "one_shot") else 3_000_001
+        t = cc.empty(n, torch.float32) if algo in ("nvls", "two_shot") else torch.empty(n, device="cuda")
+        t.copy_(inp(n))
+        cc.allreduce(t, algo=algo, average=True)
+        cc.synchronize()
+        torch.testing.assert_close(t.double().cpu(), exp_sum(n) / size, rtol=1e-5, atol=1e-6)
+    a32, o16 = cc.empty(1 << 20, torch.float32), cc.empty(1 << 20, torch.bfloat16)
+    a32.fill_(float(rank + 1))
+    cc.allreduce(a32, out=o16, average=True)   # NVLS ld_reduce + cast when multicast-bound
+    cc.synchronize()
+    assert float(o16[0]) == (size + 1) / 2 and float(o16[-1]) == (size + 1) / 2
+    # multi-pointer class: fold + exchange + fan-out in one launch
+    ts = [cc.empty(200_000, torch.float32), torch.empty(200_000, device="cuda")]
+    for i, t in enumerate(ts):
+        t.fill_(float(rank * 2 + i))
+    mp = gcu.CudaAllreduceRingChunked(ctx, ts)
+    assert mp.launches_per_run() == 1
+    mp.run()
+    tot = 2 * size
+    assert float(ts[0][0]) == tot * (tot - 1) / 2 and float(ts[1][-1]) == tot * (tot - 1) / 2
+    # point to point ring + one-sided
+    right, left = (rank + 1) % size, (rank - 1) % size
+    s_t, r_t = torch.full((5_000_001,), float(rank), device="cuda"), torch.zeros(5_000_001, device="cuda")
+    cc.sendrecv(s_t, right, r_t, left)
+    win = cc.empty(1024, torch.float32)
+    win.fill_(-1.0)
+    cc.synchronize()
+    cc.pc.host_barrier()
+    cc.put(torch.full((8,), float(rank), device="cuda"), win, right, remote_offset=8 * rank)
+    cc.synchronize()
+    cc.barrier()
+    cc.synchronize()
+    assert float(r_t[0]) == left and float(r_t[-1]) == left and float(win[8 * left]) == left
+    # CUDA graph: fill + three allreduces captured once, replayed
+    gs = torch.cuda.Stream()
+    gt = cc.empty(1 << 18, torch.float32)
+    galgo = gcu.CudaAllreduceRingChunked(ctx, gt, streams=[gs])
+    small = torch.empty(256, device="cuda")
+    F32 = int(gb.DataType.FLOAT32)
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph, stream=gs):
+        gb._C.cuda.fill(gt.data_ptr(), gt.numel(), F32, float(rank), 0.0, gs.cuda_stream)
+        gb._C.cuda.fill(small.data_ptr(), 256, F32, 1.0, 0.0, gs.cuda_stream)
+        galgo.run()
+        cc.allreduce(small, stream=gs)          # LL kernel inside the graph
+        galgo.run()
+    for _ in range(4):
+        graph.replay()
+    torch.cuda.synchronize()
+    cc.check_health()
+    tri = size * (size - 1) / 2
+    assert float(gt[0]) == tri * size and float(gt[-1]) == tri * size and float(small[7]) == size
     cc.pc.host_barrier()
     print(f"WORKER {rank} OK", flush=True)
 

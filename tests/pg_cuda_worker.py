@@ -56,6 +56,21 @@ def main():
             dist.recv(got, src=left)
             dist.send(torch.full((4,), float(rank), device=dev), dst=right)
         assert float(got[0]) == left
+        # NVLink p2p: everybody posts isend then irecv, payload larger than the mailbox ring
+        big = torch.full((3_000_000,), float(rank), device=dev)
+        inbox = torch.zeros(3_000_000, device=dev)
+        reqs = [dist.isend(big, dst=right), dist.irecv(inbox, src=left)]
+        [r.wait() for r in reqs]
+        torch.cuda.synchronize()
+        assert float(inbox[0]) == left and float(inbox[-1]) == left
+        ops = [dist.P2POp(dist.isend, big, right), dist.P2POp(dist.irecv, inbox, left)]
+        for r in dist.batch_isend_irecv(ops):
+            r.wait()
+        torch.cuda.synchronize()
+        assert float(inbox[12345]) == left
+    avg = torch.full((1 << 20,), float(rank + 1), device=dev)
+    dist.all_reduce(avg, op=dist.ReduceOp.AVG)   # fused scale epilogue, pipelined plain-pointer kernel
+    assert abs(float(avg[-1]) - tri / size) < 1e-5
     dist.barrier()
     torch.manual_seed(0)
     model = torch.nn.parallel.DistributedDataParallel(torch.nn.Linear(8, 4).to(dev), device_ids=[dev.index])

@@ -381,6 +381,11 @@ def run_ours(args):
         sync_all()
         put_ms = time_k(lambda: cc.put(src, win, (rank + 1) % world, stream=stream), k=10)
         peer_copy_gbs = round((256 << 20) / (put_ms * 1e-3) / 1e9, 1)
+        cu.set_tuning({"tma_copies": True})   # the same copy through cp.async.bulk (TMA, one issuing thread per CTA)
+        tma_ms = time_k(lambda: cc.put(src, win, (rank + 1) % world, stream=stream), k=10)
+        cu.set_tuning({"tma_copies": False})
+        extra["peer_copy_gbs_tma"] = round((256 << 20) / (tma_ms * 1e-3) / 1e9, 1)
+        peer_copy_gbs = max(peer_copy_gbs, extra["peer_copy_gbs_tma"])
         del win, src
         # ---- same size on plain cudaMalloc'ed buffers: registered (cudaIpc) and unregistered ---------
         pts, palgo = make(E, symmetric=False)

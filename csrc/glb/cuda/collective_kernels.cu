@@ -3,6 +3,7 @@
 // single kernels bracketed by device-side flag barriers; payload moves with
 // 128-bit peer loads/stores (or multimem.st through the NVSwitch where a multicast
 // alias exists). None of these has a CUDA variant in the reference.
+#include "glb/cuda/bulk_copy.cuh"
 #include "glb/cuda/device_common.cuh"
 #include "glb/cuda/kernels.h"
 
@@ -320,12 +321,61 @@ gatherPushKernel(CommArgs a, const char* __restrict__ in, PeerPtrs outs, char* m
   retire(a, 2, 0);
 }
 
+// Same protocol (two barriers, same CTA count) with the payload moved by the TMA: every CTA loads
+// its slice of my block into shared memory ONCE (cp.async.bulk) and stores it to every peer from
+// there; one thread per CTA issues, no data passes through registers.
+__global__ void __launch_bounds__(128)
+gatherBulkKernel(CommArgs a, const char* __restrict__ in, PeerPtrs outs, VArgs va, int onlyDst) {
+  extern __shared__ __align__(128) char smem[];
+  __shared__ BulkRing ring;
+  bulkRingInit(ring);
+  const uint32_t e = loadEpoch(a);
+  const int P = a.nranks;
+  if (!blockBarrier<false>(a, e + 1)) {
+    retire(a, 2, 0);
+    return;
+  }
+  const size_t off = va.off[a.rank], len = va.len[a.rank];
+  const size_t units = len / 16;
+  const size_t per = (units + gridDim.x - 1) / gridDim.x;
+  const size_t lo = static_cast<size_t>(blockIdx.x) * per, hi = lo + per < units ? lo + per : units;
+  char* dst[kMaxRanks];
+  int ndst = 0;
+#pragma unroll
+  for (int i = 0; i < kMaxRanks; i++) {
+    dst[i] = nullptr;
+    if (onlyDst < 0 && i < P) dst[ndst++] = static_cast<char*>(outs.p[(a.rank + i) % P]) + off + lo * 16;
+  }
+  if (onlyDst >= 0) dst[ndst++] = static_cast<char*>(outs.p[onlyDst]) + off + lo * 16;
+  if (lo < hi) ctaBulkCopy<kMaxRanks>(ring, smem, in + lo * 16, dst, ndst, (hi - lo) * 16);
+  if (blockIdx.x == 0) {  // sub-16-byte tail
+    for (size_t i = units * 16 + threadIdx.x; i < len; i += blockDim.x) {
+      const char c = in[i];
+      if (onlyDst >= 0) {
+        (static_cast<char*>(outs.p[onlyDst]) + off)[i] = c;
+      } else {
+        for (int r = 0; r < P; r++) (static_cast<char*>(outs.p[r]) + off)[i] = c;
+      }
+    }
+  }
+  blockBarrier(a, e + 2);
+  retire(a, 2, 0);
+}
+
 void launchGatherPush(const CommArgs& a, const void* in, const PeerPtrs& outs, void* mcOut, const size_t* offs,
-                      const size_t* lens, int onlyDst, bool vec, int blocks, cudaStream_t stream) {
+                      const size_t* lens, int onlyDst, bool vec, int blocks, cudaStream_t stream, bool tma) {
   VArgs va;
   for (int i = 0; i < kMaxRanks; i++) {
     va.off[i] = i < a.nranks ? offs[i] : 0;
     va.len[i] = i < a.nranks ? lens[i] : 0;
+  }
+  // The TMA variant needs 16-byte aligned source, offset and destinations; a rank whose
+  // pointers do not qualify runs the LDG/STG kernel with the SAME grid and barrier protocol.
+  bool aligned = vec && reinterpret_cast<uintptr_t>(in) % 16 == 0 && va.off[a.rank] % 16 == 0 && mcOut == nullptr;
+  for (int i = 0; i < a.nranks; i++) aligned = aligned && reinterpret_cast<uintptr_t>(outs.p[i]) % 16 == 0;
+  if (tma && aligned) {
+    gatherBulkKernel<<<blocks, 128, kBulkSmemBytes, stream>>>(a, static_cast<const char*>(in), outs, va, onlyDst);
+    return;
   }
   gatherPushKernel<<<blocks, kThreads, 0, stream>>>(a, static_cast<const char*>(in), outs, static_cast<char*>(mcOut),
                                                     va, onlyDst, vec);
@@ -628,6 +678,7 @@ void launchLLExchange(const CommArgs& a, const void* in, void* out, size_t bytes
 
 const void* broadcastKernelPtr() { return reinterpret_cast<const void*>(broadcastKernel); }
 const void* gatherPushKernelPtr() { return reinterpret_cast<const void*>(gatherPushKernel); }
+const void* gatherBulkKernelPtr() { return reinterpret_cast<const void*>(gatherBulkKernel); }
 const void* alltoallPushKernelPtr() { return reinterpret_cast<const void*>(alltoallPushKernel); }
 const void* reducePullKernelPtr(DataType dt, int nranks) {
 #define GLB_RP(E, T)                                                                                   \
@@ -665,6 +716,9 @@ void preloadCollectiveKernels() {
   };
   touch(reinterpret_cast<const void*>(broadcastKernel));
   touch(reinterpret_cast<const void*>(gatherPushKernel));
+  cudaFuncSetAttribute(reinterpret_cast<const void*>(gatherBulkKernel), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       static_cast<int>(kBulkSmemBytes));
+  touch(reinterpret_cast<const void*>(gatherBulkKernel));
   touch(reinterpret_cast<const void*>(alltoallPushKernel));
   touch(reinterpret_cast<const void*>(llExchangeKernel));
 #define GLB_TOUCH_RP(T) touch(reinterpret_cast<const void*>(reducePullKernel<T, 0, 1>));

@@ -52,6 +52,7 @@ Tuning& tuning() {
     x.bcastDirectMaxBytes = static_cast<size_t>(envInt("CUDA_BCAST_DIRECT_MAX", static_cast<long>(x.bcastDirectMaxBytes)));
     x.pipeTile = static_cast<int>(envInt("CUDA_PIPE_TILE", x.pipeTile));
     x.pipeExchangeThreads = static_cast<int>(envInt("CUDA_PIPE_XTHREADS", x.pipeExchangeThreads));
+    x.tmaCopies = envFlag("CUDA_TMA", x.tmaCopies);
     return x;
   }();
   return t;
@@ -885,7 +886,8 @@ void put(PeerContext& pc, const void* local, const PeerBuffer& remote, size_t re
   if (bytes == 0) return;
   DeviceGuard g(pc.device);
   pc.checkHealth();
-  launchPeerCopy(static_cast<char*>(remote.peer[peer]) + remoteOffset, local, bytes, bwBlocks(pc, "put", nullptr, bytes), stream);
+  launchPeerCopy(static_cast<char*>(remote.peer[peer]) + remoteOffset, local, bytes, bwBlocks(pc, "put", nullptr, bytes), stream,
+                 tuning().tmaCopies);
   checkLaunch("put");
 }
 
@@ -896,7 +898,8 @@ void get(PeerContext& pc, void* local, const PeerBuffer& remote, size_t remoteOf
   if (bytes == 0) return;
   DeviceGuard g(pc.device);
   pc.checkHealth();
-  launchPeerCopy(local, static_cast<const char*>(remote.peer[peer]) + remoteOffset, bytes, bwBlocks(pc, "get", nullptr, bytes), stream);
+  launchPeerCopy(local, static_cast<const char*>(remote.peer[peer]) + remoteOffset, bytes, bwBlocks(pc, "get", nullptr, bytes), stream,
+                 tuning().tmaCopies);
   checkLaunch("get");
 }
 

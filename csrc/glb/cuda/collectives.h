@@ -56,6 +56,8 @@ struct Tuning {
   size_t bcastDirectMaxBytes = 256 * 1024;  // <= : root pushes everything itself
   int pipeTile = 1024;                  // 16-byte groups per tile of the pipelined kernel (power of two)
   int pipeExchangeThreads = 256;        // threads of each CTA that drive NVLink in the pipelined kernel
+  bool tmaCopies = false;               // put / get / large allgather through cp.async.bulk (TMA) instead of LDG/STG
+                                        // when no table entry decides (GLB_CUDA_TMA)
 };
 Tuning& tuning();
 // Number of collective kernels launched by this process so far.

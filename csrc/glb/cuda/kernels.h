@@ -54,7 +54,7 @@ void launchPipelinedAllreduce(const CommArgs& a, const void* in, void* out, size
 void launchBroadcast(const CommArgs& a, const PeerPtrs& bufs, void* mc, size_t bytes, int root, int mode, bool vec,
                      int blocks, cudaStream_t stream);
 void launchGatherPush(const CommArgs& a, const void* in, const PeerPtrs& outs, void* mcOut, const size_t* offs,
-                      const size_t* lens, int onlyDst, bool vec, int blocks, cudaStream_t stream);
+                      const size_t* lens, int onlyDst, bool vec, int blocks, cudaStream_t stream, bool tma = false);
 void launchAlltoallPush(const CommArgs& a, const void* in, const PeerPtrs& outs, const size_t* sendOff,
                         const size_t* sendLen, const size_t* dstOff, const size_t* recvOffTable, int onlySrc,
                         bool vec, int blocks, cudaStream_t stream);
@@ -64,6 +64,7 @@ void launchReducePull(const CommArgs& a, const PeerPtrs& ins, void* mcIn, void* 
 // Entry points, for occupancy queries (every CTA of a collective kernel must be resident).
 const void* broadcastKernelPtr();
 const void* gatherPushKernelPtr();
+const void* gatherBulkKernelPtr();
 const void* alltoallPushKernelPtr();
 const void* reducePullKernelPtr(DataType dt, int nranks);
 // Flag-in-data exchange for small messages (no barrier): mode 0 = allgather (my block to
@@ -77,7 +78,9 @@ void launchP2p(const CommArgs& a, const void* sendPtr, size_t sendBytes, int dst
                int src, const PeerPtrs& mailbox, size_t boxStride, size_t slotBytes, int nslots, int lanes,
                cudaStream_t stream);
 // One-sided copy between my memory and a peer-mapped pointer (put / get), whole grid.
-void launchPeerCopy(void* dst, const void* src, size_t bytes, int blocks, cudaStream_t stream);
+// tma: stream through shared memory with cp.async.bulk (one issuing thread per CTA) when the
+// pointers are 16-byte aligned; LDG/STG otherwise.
+void launchPeerCopy(void* dst, const void* src, size_t bytes, int blocks, cudaStream_t stream, bool tma = false);
 
 // reduce_kernels.cu — local element-wise ops: dst = dst (op) src, and
 // multi-source reduce / broadcast between buffers visible to one device.

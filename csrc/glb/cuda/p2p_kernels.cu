@@ -13,6 +13,7 @@
 //
 // Also here: the whole-grid copy kernel behind the one-sided put / get on peer-mapped
 // memory (RemoteKey semantics, transport/unbound_buffer.h:128-152).
+#include "glb/cuda/bulk_copy.cuh"
 #include "glb/cuda/device_common.cuh"
 #include "glb/cuda/kernels.h"
 
@@ -142,10 +143,30 @@ __global__ void __launch_bounds__(kThreads) peerCopyKernel(char* dst, const char
   }
 }
 
+// put / get through the TMA: every CTA streams one contiguous slice (one issuing thread).
+__global__ void __launch_bounds__(128) peerBulkCopyKernel(char* dst, const char* src, size_t bytes) {
+  extern __shared__ __align__(128) char smem[];
+  __shared__ BulkRing ring;
+  bulkRingInit(ring);
+  const size_t units = bytes / 16;
+  const size_t per = (units + gridDim.x - 1) / gridDim.x;
+  const size_t lo = static_cast<size_t>(blockIdx.x) * per, hi = lo + per < units ? lo + per : units;
+  if (lo < hi) {
+    char* const d[1] = {dst + lo * 16};
+    ctaBulkCopy<1>(ring, smem, src + lo * 16, d, 1, (hi - lo) * 16);
+  }
+  if (blockIdx.x == 0) {
+    for (size_t i = units * 16 + threadIdx.x; i < bytes; i += blockDim.x) dst[i] = src[i];
+  }
+}
+
 void preloadP2pKernels() {
+  cudaFuncSetAttribute(reinterpret_cast<const void*>(peerBulkCopyKernel), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       static_cast<int>(kBulkSmemBytes));
   cudaFuncAttributes attr;
   cudaFuncGetAttributes(&attr, reinterpret_cast<const void*>(p2pKernel));
   cudaFuncGetAttributes(&attr, reinterpret_cast<const void*>(peerCopyKernel));
+  cudaFuncGetAttributes(&attr, reinterpret_cast<const void*>(peerBulkCopyKernel));
   cudaGetLastError();
 }
 
@@ -160,9 +181,14 @@ void launchP2p(const CommArgs& a, const void* sendPtr, size_t sendBytes, int dst
                                                             boxStride, slotBytes, nslots, lanes, sendLanes);
 }
 
-void launchPeerCopy(void* dst, const void* src, size_t bytes, int blocks, cudaStream_t stream) {
+void launchPeerCopy(void* dst, const void* src, size_t bytes, int blocks, cudaStream_t stream, bool tma) {
   if (bytes == 0) return;
-  peerCopyKernel<<<blocks, kThreads, 0, stream>>>(static_cast<char*>(dst), static_cast<const char*>(src), bytes);
+  const bool aligned = (reinterpret_cast<uintptr_t>(dst) | reinterpret_cast<uintptr_t>(src)) % 16 == 0;
+  if (tma && aligned && bytes >= 64 * 1024) {
+    peerBulkCopyKernel<<<blocks, 128, kBulkSmemBytes, stream>>>(static_cast<char*>(dst), static_cast<const char*>(src), bytes);
+  } else {
+    peerCopyKernel<<<blocks, kThreads, 0, stream>>>(static_cast<char*>(dst), static_cast<const char*>(src), bytes);
+  }
 }
 
 }  // namespace cuda

@@ -318,6 +318,7 @@ void registerCuda(py::module_& root) {
     if (d.contains("pipe_tile")) t.pipeTile = d["pipe_tile"].cast<int>();
     if (d.contains("pipe_exchange_threads")) t.pipeExchangeThreads = d["pipe_exchange_threads"].cast<int>();
     if (d.contains("alltoallv_blocks")) t.alltoallvBlocks = d["alltoallv_blocks"].cast<int>();
+    if (d.contains("tma_copies")) t.tmaCopies = d["tma_copies"].cast<bool>();
   });
 
   // ---- local ops / helpers ------------------------------------------------------------

@@ -302,6 +302,12 @@ def main(argv=None):
                                       f"{coll} P={P} buf=sym maxbytes=inf algo=push blocks={b}\n")
                 cu.set_tuning({"copy_blocks": 512, "max_blocks": b})
                 cands.append(attempt("push", call, total, blocks=b))
+            if coll == "allgather" and per >= (256 << 10):
+                for b in (37, 74, 148):  # TMA variant: cp.async.bulk through shared memory, 1 CTA per SM
+                    cu.tuning_clear()
+                    cu.tuning_load_string(f"allgather P={P} buf=reg maxbytes=inf algo=tma blocks={b}\n")
+                    cu.set_tuning({"copy_blocks": 512, "max_blocks": 148})
+                    cands.append(attempt("tma", call, total, blocks=b))
             cu.tuning_clear()
             cu.set_tuning({"ll_max_bytes": 16384, "copy_blocks": 296, "max_blocks": 128})
             best = record(coll, "reg", per if coll != "broadcast" else total, cands)

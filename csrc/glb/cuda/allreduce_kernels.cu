@@ -255,6 +255,74 @@ llAllreduceKernel(CommArgs a, const T* in, TO* out, size_t count, DevOp op, floa
   }
 }
 
+// Small reduce_scatter with the same protocol: rank r ships slice j of its input straight to
+// rank j as LL lines and reduces the P contributions to its own slice (rank order). Every
+// rank hears from every peer, so the two-parity argument of the LL allreduce holds.
+template <typename T>
+__global__ void __launch_bounds__(kThreads)
+llReduceScatterKernel(CommArgs a, const T* in, T* out, size_t per, DevOp op, float scale, PeerPtrs ll, char* myLL,
+                      size_t srcStride, size_t parityStride) {
+  constexpr int K = 8 / sizeof(T);
+  using A = typename AccType<T>::type;
+  const uint32_t seq = ld_relaxed_sys(&a.self->llSeq) + 1u;
+  const size_t base = (seq & 1u) * parityStride;
+  const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+  const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
+  const size_t nunits = (per + K - 1) / K;
+  const int P = a.nranks;
+  const int me = a.rank;
+  const size_t mySlot = base + static_cast<size_t>(me) * srcStride;
+  // send: item = (destination j, unit u)
+  for (size_t it = tid; it < static_cast<size_t>(P) * nunits; it += nthreads) {
+    const int j = static_cast<int>(it / nunits);
+    if (j == me) continue;
+    const size_t u = it % nunits;
+    uint32_t w[2] = {0u, 0u};
+    T* t = reinterpret_cast<T*>(w);
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      if (u * K + k < per) t[k] = in[static_cast<size_t>(j) * per + u * K + k];
+    }
+    llStore(static_cast<char*>(ll.p[j]) + mySlot + u * 16, w[0], w[1], seq);
+  }
+  // reduce my slice
+  const char* myRegion = myLL + base;
+  bool alive = true;
+  for (size_t u = tid; u < nunits && alive; u += nthreads) {
+    A acc[K];
+#pragma unroll
+    for (int k = 0; k < K; k++) acc[k] = A(0);
+    for (int r = 0; r < P && alive; r++) {
+      uint32_t d[2] = {0u, 0u};
+      if (r == me) {
+        T* t = reinterpret_cast<T*>(d);
+#pragma unroll
+        for (int k = 0; k < K; k++) {
+          if (u * K + k < per) t[k] = in[static_cast<size_t>(me) * per + u * K + k];
+        }
+      } else if (!llLoad(a, myRegion + static_cast<size_t>(r) * srcStride + u * 16, seq, d[0], d[1], r)) {
+        alive = false;
+        break;
+      }
+      const T* x = reinterpret_cast<const T*>(d);
+#pragma unroll
+      for (int k = 0; k < K; k++) acc[k] = r == 0 ? toAcc<T>(x[k]) : applyOp<A>(acc[k], toAcc<T>(x[k]), op);
+    }
+    if (!alive) break;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+      if (u * K + k < per) {
+        A v = acc[k];
+        if constexpr (std::is_floating_point<A>::value) {
+          if (scale != 1.0f) v = static_cast<A>(v * scale);
+        }
+        out[u * K + k] = fromAcc<T, A>(v);
+      }
+    }
+  }
+  retire(a, 0, 0, 1);
+}
+
 // ---- one-shot ---------------------------------------------------------------------
 
 // Push flavour: every rank STORES its contribution into slot `rank` of every peer's pool
@@ -708,6 +776,7 @@ void preloadAllreduceKernels() {
     dispatchType(dt, [&](auto tag) {
       using T = decltype(tag);
       touch(fn(llAllreduceKernel<T, T>));
+      touch(fn(llReduceScatterKernel<T>));
       touch(fn(oneShotAllreduceKernel<T>));
       touch(fn(oneShotPushAllreduceKernel<T>));
       touch(twoShotFn<T>(0, 0));
@@ -768,6 +837,17 @@ void launchLLAllreduce(const CommArgs& a, const void* in, void* out, size_t coun
     GLB_LL(T, T);
   });
 #undef GLB_LL
+}
+
+void launchLLReduceScatter(const CommArgs& a, const void* in, void* out, size_t perRank, DataType dt, ReduceOp op,
+                           float scale, const PeerPtrs& ll, size_t srcStride, size_t parityStride, int blocks, int threads,
+                           cudaStream_t stream) {
+  dispatchType(dt, [&](auto tag) {
+    using T = decltype(tag);
+    llReduceScatterKernel<T><<<blocks, threads, 0, stream>>>(a, static_cast<const T*>(in), static_cast<T*>(out), perRank,
+                                                            static_cast<DevOp>(op), scale, ll,
+                                                            static_cast<char*>(ll.p[a.rank]), srcStride, parityStride);
+  });
 }
 
 void launchOneShotAllreduce(const CommArgs& a, const void* in, void* out, size_t count, DataType dt, ReduceOp op,

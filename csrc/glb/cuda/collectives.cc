@@ -766,6 +766,32 @@ void reducePullCommon(PeerContext& pc, const PeerPtrs& ins, void* mcIn, bool vec
 }
 }  // namespace
 
+namespace {
+// Small reduce_scatter with equal shares: flag-in-data lines, no barrier, any input pointer.
+bool tryLLReduceScatter(PeerContext& pc, const void* in, void* out, const std::vector<size_t>& counts, DataType dt,
+                        ReduceOp op, double scaleD, cudaStream_t stream) {
+  if (pc.size < 2 || !allEqual(counts) || counts[0] == 0 || envFlag("CUDA_LL_DISABLE", false)) return false;
+  const size_t bytes = counts[0] * elementSize(dt);
+  size_t limit = std::min(tuning().llMaxBytes, pc.llMaxBytes());
+  if (const TuneEntry* e = TuningTable::get().lookup("reduce_scatter", pc.size, BufKind::REGISTERED, bytes)) {
+    if (e->algo != "ll") return false;
+    limit = pc.llMaxBytes();
+  }
+  if (bytes > limit) return false;
+  Epilogue ep;
+  ep.scale = scaleD;
+  const float scale = scaleOf(ep, dt);
+  const size_t units = ceilDiv(bytes, size_t(8)) * pc.size;
+  int threads = static_cast<int>(std::min<size_t>(kThreads, roundUp(std::max<size_t>(units, 32), 32)));
+  int blocks = static_cast<int>(std::min<size_t>(ceilDiv(units, static_cast<size_t>(threads)), 16));
+  prologue(pc, stream);
+  launchLLReduceScatter(pc.comm(), in, out, counts[0], dt, op, scale, pc.llPtrs(), pc.llSrcStride(), pc.llParityStride(),
+                        std::max(1, blocks), threads, stream);
+  finish(pc, stream, "reduce_scatter(ll)");
+  return true;
+}
+}  // namespace
+
 void reduce_scatter(PeerContext& pc, const PeerBuffer& in, size_t inOffset, void* out,
                     const std::vector<size_t>& counts, DataType dt, ReduceOp op, cudaStream_t stream, double scale) {
   DeviceGuard g(pc.device);
@@ -777,6 +803,8 @@ void reduce_scatter(PeerContext& pc, const PeerBuffer& in, size_t inOffset, void
     if (src != out && counts[0] > 0) GLB_CUDA_CHECK(cudaMemcpyAsync(out, src, counts[0] * es, cudaMemcpyDeviceToDevice, stream));
     return;
   }
+  GLB_ENFORCE(op != ReduceOp::CUSTOM, "custom reductions run on the host path only");
+  if (tryLLReduceScatter(pc, static_cast<const char*>(in.local) + inOffset, out, counts, dt, op, scale, stream)) return;
   reducePullCommon(pc, in.ptrsAt(inOffset), in.mc ? static_cast<char*>(in.mc) + inOffset : nullptr,
                    in.vectorOk && inOffset % 16 == 0, out, counts, dt, op, scale, stream);
 }
@@ -790,6 +818,8 @@ void reduce_scatter(PeerContext& pc, const void* in, void* out, const std::vecto
     if (in != out && counts[0] > 0) GLB_CUDA_CHECK(cudaMemcpyAsync(out, in, counts[0] * es, cudaMemcpyDeviceToDevice, stream));
     return;
   }
+  GLB_ENFORCE(op != ReduceOp::CUSTOM, "custom reductions run on the host path only");
+  if (tryLLReduceScatter(pc, in, out, counts, dt, op, scale, stream)) return;
   auto st = stagedBulk(pc, off.back() * es, "reduce_scatter");
   if (off.back() > 0) GLB_CUDA_CHECK(cudaMemcpyAsync(st.mine, in, off.back() * es, cudaMemcpyDeviceToDevice, stream));
   reducePullCommon(pc, st.ptrs, st.mc, true, out, counts, dt, op, scale, stream);

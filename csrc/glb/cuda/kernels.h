@@ -23,6 +23,10 @@ void launchBarrier(const CommArgs& a, cudaStream_t stream);
 void launchLLAllreduce(const CommArgs& a, const void* in, void* out, size_t count, DataType dt, DataType outDt,
                        ReduceOp op, float scale, const PeerPtrs& ll, size_t srcStride, size_t parityStride,
                        const LocalPtrs& extra, int blocks, int threads, cudaStream_t stream);
+// Small reduce_scatter (equal shares of `perRank` elements), flag-in-data, no barrier.
+void launchLLReduceScatter(const CommArgs& a, const void* in, void* out, size_t perRank, DataType dt, ReduceOp op,
+                           float scale, const PeerPtrs& ll, size_t srcStride, size_t parityStride, int blocks, int threads,
+                           cudaStream_t stream);
 void launchOneShotAllreduce(const CommArgs& a, const void* in, void* out, size_t count, DataType dt, ReduceOp op,
                             float scale, const PeerPtrs& stage, size_t halfBytes, const LocalPtrs& extra, int blocks,
                             cudaStream_t stream);

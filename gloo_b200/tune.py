@@ -290,7 +290,7 @@ def main(argv=None):
                 call = lambda: cc.reduce_scatter(fout, fin, stream=stream)  # noqa: E731
                 if nccl is not None:
                     ref = attempt("nccl", lambda: nccl.reduce_scatter(fin.data_ptr(), fout.data_ptr(), per // 4, int(gb.DataType.FLOAT32), 1, stream.cuda_stream), total)
-            small = per <= ll_max and coll in ("allgather", "alltoall")
+            small = per <= ll_max and coll in ("allgather", "alltoall", "reduce_scatter")
             if small:
                 cu.tuning_clear()
                 cu.set_tuning({"ll_max_bytes": ll_max})

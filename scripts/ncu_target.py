@@ -1,61 +1,37 @@
 #!/usr/bin/env python
-"""Small deterministic workloads for Nsight Compute captures.
+"""Target for Nsight Compute (one GPU, one process): the N=1 flagship step on the benchmark's
+400 MB buffers and the virtual-rank loopback of the collective kernels on 64 MB buffers, so
+that `ncu --set full -k regex:...` captures the hot kernels at a realistic size.
 
-  local   : 1 rank, CudaAllreduceRingChunked with 2 local buffers (localReduceMany +
-            localBroadcast kernels; safe for kernel replay)
-  twoshot : 2 ranks as threads on cuda:0, one fused two-shot allreduce on 64 MB
-            (use --replay-mode application: the kernel waits for its peer, so it cannot
-            be replayed in isolation)
-  oneshot : same with a 16 KB one-shot
+  ncu --set full --clock-control none --import-source on -k regex:'localAllreduceMany|twoShotAllreduce|pipelinedAllreduce|gatherBulk|peerBulkCopy' \
+      -c 8 -o gpurun_out/prof_r2 python scripts/ncu_target.py
 """
 import os
 import sys
 
-os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 import torch  # noqa: E402
 
 import gloo_b200 as gb  # noqa: E402
 from gloo_b200.ops import cuda as gcu  # noqa: E402
 
-mode = sys.argv[1] if len(sys.argv) > 1 else "local"
 
-if mode.startswith("loop_"):
-    # Single-rank loopback of a collective kernel (GLB_CUDA_FORCE_KERNELS=1): same code,
-    # all "peers" are this GPU, so the kernel can be replayed by ncu.
-    os.environ["GLB_CUDA_FORCE_KERNELS"] = "1"
-    algo = mode[len("loop_"):]
-    n = (256 << 20) // 4 if algo == "two_shot" else 4096
+def fn(ctx):
+    cc = gcu.CudaContext(ctx, 0, stage_bytes=256 << 20)
+    n = 100_000_000
+    a, b = torch.ones(n, device="cuda"), torch.ones(n, device="cuda")
+    step = gcu.CudaAllreduceRingChunked(ctx, [a, b])
+    for _ in range(3):
+        step.run()
+    del a, b, step
+    torch.cuda.synchronize()
+    res = cc.pc.loopback_selftest(torch.cuda.current_stream().cuda_stream, int(os.environ.get("GLB_NCU_COUNT", 1 << 24)))
+    bad = [r for r in res if not r["ok"]]
+    assert not bad, bad
+    return len(res)
 
-    def fn(ctx):
-        cc = gcu.CudaContext(ctx, 0, stage_bytes=8 << 20)
-        t = cc.empty(n, torch.float32)
-        t.fill_(1)
-        for _ in range(3):
-            cc.allreduce(t, algo=algo)
-        torch.cuda.current_stream().synchronize()
-        return float(t[0])
+
+if __name__ == "__main__":
     print(gb.spawn_threads(1, fn, cuda_device=0))
-elif mode == "local":
-    def fn(ctx):
-        n = 100_000_000
-        ts = [torch.ones(n, device="cuda") for _ in range(2)]
-        algo = gcu.CudaAllreduceRingChunked(ctx, ts)
-        for _ in range(4):
-            algo.run()
-        return float(ts[0][0])
-    print(gb.spawn_threads(1, fn, cuda_device=0))
-else:
-    n = (64 << 20) // 4 if mode == "twoshot" else 4096
-
-    def fn(ctx):
-        cc = gcu.CudaContext(ctx, 0, stage_bytes=8 << 20)
-        t = torch.ones(n, device="cuda")
-        cc.register(t)
-        for _ in range(3):
-            cc.allreduce(t, algo="two_shot" if mode == "twoshot" else "one_shot")
-        torch.cuda.current_stream().synchronize()
-        cc.pc.host_barrier()
-        return float(t[0])
-    print(gb.spawn_threads(2, fn, cuda_device=0))

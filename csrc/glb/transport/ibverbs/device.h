@@ -1,15 +1,13 @@
-// transport::ibverbs — availability probe and API surface of the reference's InfiniBand
-// transport (gloo/transport/ibverbs/device.h:24-60).
-//
-// What the reference used it for — zero-copy one-sided transfers and handing GPU memory to
-// the transport without staging — is served here by two other pieces that exist and are
-// tested: `UnboundBuffer::getRemoteKey/put/get` on the tcp transport (software one-sided,
-// single-copy between ranks of one host) and `cuda::PeerContext` (NVLink / NVSwitch peer
-// memory, NVLS multicast). A verbs data path is NOT implemented: the image ships neither
-// the rdma-core headers nor an HCA to run it against, and a B200 HGX box reaches its peers
-// over NVSwitch, not over a NIC. `CreateDevice` therefore reports precisely what is missing
-// instead of pretending; `probe()` lets callers (and the benchmark's --transport=ibverbs)
-// fall back to tcp cleanly.
+// transport::ibverbs — InfiniBand / RoCE transport (reliable-connected queue pairs), the
+// counterpart of gloo/transport/ibverbs/{device,pair,buffer,unbound_buffer,remote_key}.
+// libibverbs is loaded at run time through a vendored ABI mirror (verbs_abi.h): the build
+// needs no rdma-core headers. Protocol and design notes are in transport.cc.
+//   * bound buffers: memory-region exchange + RDMA WRITE WITH IMMEDIATE;
+//   * unbound buffers: eager SENDs up to 8 KB, RTS / RDMA READ / FIN rendezvous above (zero
+//     copy), recv-from-any matched locally; getRemoteKey / put / get = RDMA WRITE / READ;
+//   * device memory registers like host memory when nvidia_peermem is loaded (hasGPUDirect()).
+// `probe()` never throws and lets callers (and the benchmark's --transport=ibverbs) fall back
+// to tcp cleanly when there is no library or no HCA.
 #pragma once
 
 #include <memory>
@@ -42,8 +40,8 @@ Probe probe();
 // Reference: gloo/transport/ibverbs/device.h getDeviceNames().
 std::vector<std::string> getDeviceNames();
 
-// Throws InvalidOperationException naming the missing piece (library, device, or the
-// verbs data path of this build).
+// Opens the HCA (first device when `name` is empty). Throws InvalidOperationException naming
+// the missing piece when libibverbs or an RDMA device is absent.
 std::shared_ptr<::glb::transport::Device> CreateDevice(const struct attr&);
 
 }  // namespace ibverbs

@@ -2,6 +2,7 @@
 ibverbs (probe + precise error), MPI bootstrap (run against a thread-world MPI), and the
 benchmark CLI's --transport switch (reference: gloo/benchmark/options.cc:149-180)."""
 import os
+import sys
 import shutil
 import subprocess
 import tempfile
@@ -38,6 +39,37 @@ def test_uv_device_runs_new_style_collectives():
     [t.start() for t in ths]
     [t.join(60) for t in ths]
     assert out == [(6.0, [0, 1, 2])] * 3
+
+
+def _build_fake_ibverbs():
+    cxx = "/usr/bin/g++" if os.path.exists("/usr/bin/g++") else "g++"
+    out = os.path.join(tempfile.mkdtemp(prefix="glb_fakeibv_"), "libfakeibverbs.so")
+    subprocess.check_call([cxx, "-shared", "-fPIC", "-std=c++17", "-O1", "-pthread", f"-I{os.path.join(ROOT, 'csrc')}",
+                           os.path.join(ROOT, "tests", "fake_ibverbs", "fake_ibverbs.cc"), "-o", out])
+    return out
+
+
+@pytest.mark.parametrize("size", [2, 3, 4])
+def test_ibverbs_transport_over_software_verbs(size):
+    """The verbs data path (RC queue pairs, eager / rendezvous unbound messages, bound buffers over
+    RDMA WRITE WITH IMMEDIATE, remote-key put / get) against tests/fake_ibverbs: an in-process
+    software provider with the libibverbs ABI (the image has neither rdma-core nor an HCA).
+    Parity: gloo/test/{send_recv,remote_key,allreduce}_test.cc run with Transport::IBVERBS."""
+    lib = _build_fake_ibverbs()
+    env = dict(os.environ, GLB_IBVERBS_LIB=lib)
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ibverbs_worker.py"), str(size)], env=env,
+                         capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and f"IBVERBS OK {size}" in out.stdout, (out.stdout[-2000:], out.stderr[-4000:])
+
+
+def test_ibverbs_on_a_real_hca():
+    """Same worker against the real libibverbs when the box has one and an RDMA device."""
+    p = _C.ibverbs_probe()
+    if not p["library"] or not p["devices"]:
+        pytest.skip(f"no RDMA device: {p['detail']}")
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ibverbs_worker.py"), "2"], capture_output=True,
+                         text=True, timeout=300)
+    assert out.returncode == 0 and "IBVERBS OK 2" in out.stdout, (out.stdout[-2000:], out.stderr[-4000:])
 
 
 def test_ibverbs_probe_and_error():

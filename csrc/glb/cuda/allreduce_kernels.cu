@@ -626,6 +626,98 @@ nvlsAllreduceKernel(CommArgs a, char* mcBase, PeerPtrs bufs, size_t count, float
   retire(a, 2, 0);
 }
 
+// ---- NVLS + peer-to-peer hybrid ---------------------------------------------------------------
+// Measured on 8 x B200: the in-switch reduction saturates at ~0.75 of the link rate and gets
+// SLOWER with more CTAs in flight (tune_P8: 32 CTAs x unroll 2 beats 296 x 8 by 9-30 %), i.e.
+// the bound is the switch's reduction path, not NVLink. The links therefore have headroom that
+// a plain peer-to-peer two-shot can use at the same time: the vector is cut in two, CTAs
+// [0, nvlsBlocks) run the multimem path on the first part, the remaining CTAs run the two-shot
+// exchange on the second part, under the same two barriers.
+template <typename T, int NR>
+__global__ void __launch_bounds__(kThreads)
+hybridAllreduceKernel(CommArgs a, char* mcBase, PeerPtrs bufs, size_t count, float scale, int nvlsBlocks,
+                      unsigned p2pPermille) {
+  using PT = PackTraits<T>;
+  constexpr int P = NR;
+  constexpr int UP = NR == 2 ? 4 : 2;  // unroll of the peer-to-peer part
+  const uint32_t e = loadEpoch(a);
+  if (!blockBarrier<false>(a, e + 1)) {
+    retire(a, 2, 0);
+    return;
+  }
+  const size_t nvec = count / PT::kElems;
+  // split on a multiple of P packs so that both parts share evenly
+  size_t p2pVec = nvec / 1000 * p2pPermille / P * P;
+  if (gridDim.x <= static_cast<unsigned>(nvlsBlocks)) p2pVec = 0;
+  const size_t nvlsVec = nvec - p2pVec;
+  if (static_cast<int>(blockIdx.x) < nvlsBlocks) {
+    const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
+    const size_t nthreads = static_cast<size_t>(nvlsBlocks) * blockDim.x;
+    size_t vb, ve;
+    shareOf(nvlsVec, P, a.rank, vb, ve);
+    constexpr int U = 2;
+    for (size_t v0 = vb + tid; v0 < ve; v0 += nthreads * U) {
+      Pack16 r[U];
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const size_t v = v0 + static_cast<size_t>(u) * nthreads;
+        if (v < ve) r[u] = Multimem<T>::ldReduceAdd(mcBase + v * 16);
+      }
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const size_t v = v0 + static_cast<size_t>(u) * nthreads;
+        if (v < ve) multimemSt128(mcBase + v * 16, scale != 1.0f ? scalePack<T>(r[u], scale) : r[u]);
+      }
+    }
+  } else {
+    const size_t tid = static_cast<size_t>(blockIdx.x - nvlsBlocks) * blockDim.x + threadIdx.x;
+    const size_t nthreads = static_cast<size_t>(gridDim.x - nvlsBlocks) * blockDim.x;
+    size_t vb, ve;
+    shareOf(p2pVec, P, a.rank, vb, ve);
+    vb += nvlsVec;
+    ve += nvlsVec;
+    char* peer[P];
+#pragma unroll
+    for (int i = 0; i < P; i++) peer[i] = static_cast<char*>(bufs.p[(a.rank + i) % P]);
+    for (size_t v0 = vb + tid; v0 < ve; v0 += nthreads * UP) {
+      Pack16 p[UP][P];
+#pragma unroll
+      for (int u = 0; u < UP; u++) {
+        const size_t v = v0 + static_cast<size_t>(u) * nthreads;
+        if (v < ve) {
+#pragma unroll
+          for (int i = 0; i < P; i++) p[u][i] = ld128_stream(peer[i] + v * 16);
+        }
+      }
+#pragma unroll
+      for (int u = 0; u < UP; u++) {
+        const size_t v = v0 + static_cast<size_t>(u) * nthreads;
+        if (v < ve) {
+          typename PT::AccPack acc = PT::widen(p[u][0]);
+#pragma unroll
+          for (int i = 1; i < P; i++) PT::combine(acc, p[u][i], DevOp::SUM);
+          if (scale != 1.0f) PT::scale(acc, scale);
+          const Pack16 res = PT::narrow(acc);
+#pragma unroll
+          for (int i = 0; i < P; i++) st128_stream(peer[i] + v * 16, res);
+        }
+      }
+    }
+    // sub-pack tail: peer-to-peer group, split like the two-shot tail
+    const size_t tailStart = nvec * PT::kElems;
+    size_t tb, te;
+    shareOf(count - tailStart, P, a.rank, tb, te);
+    for (size_t i = tailStart + tb + tid; i < tailStart + te; i += nthreads) {
+      T acc = static_cast<const T*>(bufs.p[0])[i];
+      for (int r = 1; r < P; r++) acc = PT::combineOne(acc, static_cast<const T*>(bufs.p[r])[i], DevOp::SUM);
+      if (scale != 1.0f) acc = PT::scaleOne(acc, scale);
+      for (int r = 0; r < P; r++) static_cast<T*>(bufs.p[r])[i] = acc;
+    }
+  }
+  blockBarrier(a, e + 2);
+  retire(a, 2, 0);
+}
+
 // ---- cast epilogue: out-of-place, output dtype != input dtype --------------------------------
 // Rank r reduces items [share r) of every rank's input (peer loads, or multimem.ld_reduce
 // when `mcIn` is set), scales, rounds ONCE to TO and stores into every rank's output.
@@ -788,6 +880,9 @@ void preloadAllreduceKernels() {
       }
     });
   }
+  for (DataType dt : {DataType::FLOAT32, DataType::FLOAT16, DataType::BFLOAT16}) {
+    for (int P : {2, 4, 8}) touch(hybridKernelFor(dt, P));
+  }
   touch(fn(llAllreduceKernel<float, __half>));
   touch(fn(llAllreduceKernel<float, __nv_bfloat16>));
   touch(fn(llAllreduceKernel<__half, float>));
@@ -911,6 +1006,38 @@ void launchNvlsAllreduce(const CommArgs& a, void* mcPtr, const PeerPtrs& bufs, s
   LocalPtrs ex = extra;
   void* args[] = {&ca, &mc, &pb, &count, &scale, &ex};
   launch(k, cfg.blocks, kThreads, args, stream);
+}
+
+namespace {
+template <typename T>
+const void* hybridFn(int P) {
+  switch (P) {
+    case 2: return fn(hybridAllreduceKernel<T, 2>);
+    case 4: return fn(hybridAllreduceKernel<T, 4>);
+    case 8: return fn(hybridAllreduceKernel<T, 8>);
+    default: return nullptr;
+  }
+}
+}  // namespace
+
+const void* hybridKernelFor(DataType dt, int nranks) {
+  switch (dt) {
+    case DataType::FLOAT32: return hybridFn<float>(nranks);
+    case DataType::FLOAT16: return hybridFn<__half>(nranks);
+    case DataType::BFLOAT16: return hybridFn<__nv_bfloat16>(nranks);
+    default: return nullptr;
+  }
+}
+
+void launchHybridAllreduce(const CommArgs& a, void* mcPtr, const PeerPtrs& bufs, size_t count, DataType dt, float scale,
+                           int blocks, int nvlsBlocks, unsigned p2pPermille, cudaStream_t stream) {
+  const void* k = hybridKernelFor(dt, a.nranks);
+  if (k == nullptr) return;
+  CommArgs ca = a;
+  char* mc = static_cast<char*>(mcPtr);
+  PeerPtrs pb = bufs;
+  void* args[] = {&ca, &mc, &pb, &count, &scale, &nvlsBlocks, &p2pPermille};
+  launch(k, blocks, kThreads, args, stream);
 }
 
 const void* castKernelFor(DataType in, DataType out) {

@@ -18,6 +18,7 @@ const char* allreduceAlgoName(AllreduceAlgo a) {
     case AllreduceAlgo::NVLS: return "nvls";
     case AllreduceAlgo::LL: return "ll";
     case AllreduceAlgo::PIPELINED: return "pipelined";
+    case AllreduceAlgo::HYBRID: return "hybrid";
     case AllreduceAlgo::RING: return "ring";
     case AllreduceAlgo::RING_CHUNKED: return "ring_chunked";
     case AllreduceAlgo::HALVING_DOUBLING: return "halving_doubling";
@@ -29,7 +30,8 @@ const char* allreduceAlgoName(AllreduceAlgo a) {
 
 AllreduceAlgo allreduceAlgoFromName(const std::string& n) {
   for (AllreduceAlgo a : {AllreduceAlgo::AUTO, AllreduceAlgo::ONE_SHOT, AllreduceAlgo::TWO_SHOT, AllreduceAlgo::NVLS,
-                          AllreduceAlgo::LL, AllreduceAlgo::PIPELINED, AllreduceAlgo::RING, AllreduceAlgo::RING_CHUNKED,
+                          AllreduceAlgo::LL, AllreduceAlgo::PIPELINED, AllreduceAlgo::HYBRID, AllreduceAlgo::RING,
+                          AllreduceAlgo::RING_CHUNKED,
                           AllreduceAlgo::HALVING_DOUBLING, AllreduceAlgo::BCUBE,
                           AllreduceAlgo::HALVING_DOUBLING_PIPELINED}) {
     if (n == allreduceAlgoName(a)) return a;
@@ -138,6 +140,8 @@ AllreducePlan planAllreduce(PeerContext& pc, size_t bytes, DataType dt, ReduceOp
       case AllreduceAlgo::LL: return bytes <= pc.llMaxBytes();
       case AllreduceAlgo::ONE_SHOT: return roundUp(bytes, 16) <= l.half;
       case AllreduceAlgo::NVLS: return kind == BufKind::SYMMETRIC && nvlsSupports(dt, op);
+      case AllreduceAlgo::HYBRID:
+        return kind == BufKind::SYMMETRIC && nvlsSupports(dt, op) && hybridKernelFor(dt, pc.size) != nullptr;
       case AllreduceAlgo::TWO_SHOT: return kind != BufKind::USER;
       case AllreduceAlgo::PIPELINED: return kind == BufKind::USER;
       default: return false;
@@ -269,6 +273,10 @@ void allreduce(PeerContext& pc, const PeerBuffer& buf, size_t byteOffset, size_t
   if (algo == AllreduceAlgo::AUTO) {
     plan = planAllreduce(pc, bytes, dt, op, kind);
     algo = plan.algo;
+    if (algo == AllreduceAlgo::HYBRID && ep.extra.n > 0) {  // the hybrid kernel takes one pointer
+      algo = AllreduceAlgo::NVLS;
+      plan.cfg = LaunchCfg();
+    }
   }
   if (ep.blocks > 0) plan.cfg.blocks = ep.blocks;
   if (ep.unroll > 0) plan.cfg.unroll = ep.unroll;
@@ -289,6 +297,18 @@ void allreduce(PeerContext& pc, const PeerBuffer& buf, size_t byteOffset, size_t
                                ceilDiv(bytes, size_t(16)) / pc.size, cfg.unroll);
       launchNvlsAllreduce(pc.comm(), static_cast<char*>(buf.mc) + byteOffset, buf.ptrsAt(byteOffset), count, dt, scale,
                           ep.extra, cfg, stream);
+      break;
+    }
+    case AllreduceAlgo::HYBRID: {
+      GLB_ENFORCE(hasMc && nvlsSupports(dt, op) && hybridKernelFor(dt, pc.size) != nullptr && ep.extra.n == 0,
+                  "hybrid allreduce: sum of f32/f16/bf16 on a multicast-bound buffer, 4 or 8 ranks, one pointer");
+      // cfg.blocks = all CTAs, cfg.unroll = CTAs of the NVLS part, tile = per-mille of the vector done peer to peer
+      int blocks = plan.cfg.blocks > 0 ? plan.cfg.blocks : 148;
+      blocks = std::max(2, std::min(blocks, pc.coResidentBlocks(hybridKernelFor(dt, pc.size))));
+      const int nvlsBlocks = std::max(1, std::min(plan.cfg.unroll > 0 ? plan.cfg.unroll : 32, blocks - 1));
+      const int permille = std::max(0, std::min((ep.tile > 0 ? ep.tile : plan.tile > 0 ? plan.tile : 175), 900));
+      launchHybridAllreduce(pc.comm(), static_cast<char*>(buf.mc) + byteOffset, buf.ptrsAt(byteOffset), count, dt, scale,
+                            blocks, nvlsBlocks, static_cast<unsigned>(permille), stream);
       break;
     }
     case AllreduceAlgo::TWO_SHOT: {
@@ -907,6 +927,25 @@ void recv(PeerContext& pc, void* ptr, size_t bytes, int src, cudaStream_t stream
 void sendrecv(PeerContext& pc, const void* sendPtr, size_t sendBytes, int dst, void* recvPtr, size_t recvBytes,
               int src, cudaStream_t stream) {
   p2pCommon(pc, sendPtr, sendBytes, dst, recvPtr, recvBytes, src, stream);
+}
+
+void exchange(PeerContext& pc, const void* sendPtr, size_t sendBytes, int dst, const PeerBuffer& recvBuf,
+              size_t recvOffset, size_t recvBytes, int src, cudaStream_t stream) {
+  GLB_TRACE_RANGE("glb::cuda::exchange");
+  DeviceGuard g(pc.device);
+  GLB_ENFORCE(sendBytes == 0 || (dst >= 0 && dst < pc.size && dst != pc.rank), "exchange: invalid destination rank ", dst);
+  GLB_ENFORCE(recvBytes == 0 || (src >= 0 && src < pc.size && src != pc.rank), "exchange: invalid source rank ", src);
+  if (sendBytes == 0 && recvBytes == 0) return;
+  GLB_ENFORCE(sendBytes == 0 || recvBuf.peer[dst] != nullptr, "exchange: rank ", dst, " has no mapping of the receive buffer");
+  GLB_ENFORCE_LE(recvOffset + std::max(sendBytes, recvBytes), recvBuf.bytes, "exchange: range exceeds the receive buffer");
+  pc.checkHealth();
+  // Pairwise like send / recv: no barrier epoch, no host rendezvous. The arrival counter
+  // counts CTAs, so the grid is a job-wide value.
+  const int blocks = std::max(1, std::min(pc.options().exchangeBlocks, pc.maxBlocks()));
+  char* remote = sendBytes ? static_cast<char*>(recvBuf.peer[dst]) + recvOffset : nullptr;
+  launchExchange(pc.comm(), sendPtr, sendBytes, sendBytes ? dst : 0, remote, recvBytes, recvBytes ? src : 0, blocks,
+                 tuning().tmaCopies && std::max(sendBytes, recvBytes) >= 64 * 1024, stream);
+  checkLaunch("exchange");
 }
 
 void put(PeerContext& pc, const void* local, const PeerBuffer& remote, size_t remoteOffset, size_t bytes, int peer,

@@ -28,6 +28,7 @@ enum class AllreduceAlgo : int {
   NVLS = 3,
   LL = 4,         // flag-in-data one-shot, no barrier (smallest messages)
   PIPELINED = 5,  // arbitrary pointers: in-kernel copy-in / exchange / copy-out pipeline through the pool
+  HYBRID = 6,     // NVLS on one part of the vector + peer-to-peer two-shot on the rest, concurrently
   // Literal schedules of the reference's named algorithms, executed by the
   // step-table kernel over peer pointers (schedule_kernels.cu).
   RING = 10,
@@ -168,6 +169,15 @@ void sendrecv(PeerContext& pc, const void* sendPtr, size_t sendBytes, int dst, v
 // at remoteOffset. Completion is stream order on the initiator; the target learns about it
 // through a later collective / barrier / message (RDMA semantics, as
 // gloo/transport/unbound_buffer.h:128-152).
+// Zero-copy sendrecv for a peer-mapped receive buffer that every rank uses at the same offset
+// (ring attention's K/V double buffer, a pipeline stage's activation slot): my `sendBytes` are
+// written straight into recvBuf on `dst` at recvOffset, `src` writes into mine. One kernel, one
+// pass over the data, one flag round trip per call. After it completes on `stream`, my
+// recvBuf[recvOffset, +recvBytes) holds src's payload; my sendPtr may be reused. The receive
+// range must not be read or written by work queued behind the PREVIOUS exchange's consumer
+// until this call is enqueued (the kernel start is the "ready to be overwritten" signal).
+void exchange(PeerContext& pc, const void* sendPtr, size_t sendBytes, int dst, const PeerBuffer& recvBuf,
+              size_t recvOffset, size_t recvBytes, int src, cudaStream_t stream);
 void put(PeerContext& pc, const void* local, const PeerBuffer& remote, size_t remoteOffset, size_t bytes, int peer,
          cudaStream_t stream);
 void get(PeerContext& pc, void* local, const PeerBuffer& remote, size_t remoteOffset, size_t bytes, int peer,

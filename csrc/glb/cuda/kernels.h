@@ -38,6 +38,11 @@ void setOneShotPush(bool on);  // tuning / A-B testing of the push flavour of on
 bool oneShotPushEnabled();
 void launchNvlsAllreduce(const CommArgs& a, void* mcPtr, const PeerPtrs& bufs, size_t count, DataType dt, float scale,
                          const LocalPtrs& extra, const LaunchCfg& cfg, cudaStream_t stream);
+// NVLS on the first part of the vector + peer-to-peer two-shot on the rest, concurrently
+// (P = 4 or 8, sum of f32 / f16 / bf16, multicast-bound buffer).
+const void* hybridKernelFor(DataType dt, int nranks);
+void launchHybridAllreduce(const CommArgs& a, void* mcPtr, const PeerPtrs& bufs, size_t count, DataType dt, float scale,
+                           int blocks, int nvlsBlocks, unsigned p2pPermille, cudaStream_t stream);
 // Output dtype != input dtype (f32 <-> f16/bf16): out-of-place on registered buffers.
 bool castSupported(DataType in, DataType out);
 void launchCastAllreduce(const CommArgs& a, const PeerPtrs& ins, void* mcIn, const PeerPtrs& outs, size_t count,
@@ -85,6 +90,11 @@ void launchP2p(const CommArgs& a, const void* sendPtr, size_t sendBytes, int dst
 // tma: stream through shared memory with cp.async.bulk (one issuing thread per CTA) when the
 // pointers are 16-byte aligned; LDG/STG otherwise.
 void launchPeerCopy(void* dst, const void* src, size_t bytes, int blocks, cudaStream_t stream, bool tma = false);
+// Zero-copy neighbour exchange: write `sendBytes` straight into `remote` (the peer mapping of
+// dst's receive buffer) once dst has signalled ready, and wait for src's data to have landed in
+// my own buffer. `blocks` must be the same on both ends of a transfer.
+void launchExchange(const CommArgs& a, const void* sendPtr, size_t sendBytes, int dst, void* remote, size_t recvBytes,
+                    int src, int blocks, bool tma, cudaStream_t stream);
 
 // reduce_kernels.cu — local element-wise ops: dst = dst (op) src, and
 // multi-source reduce / broadcast between buffers visible to one device.

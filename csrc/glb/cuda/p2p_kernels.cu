@@ -117,6 +117,68 @@ p2pKernel(CommArgs a, const char* sendPtr, size_t sendBytes, int dst, char* recv
   }
 }
 
+// ---- zero-copy neighbour exchange ----------------------------------------------------------------
+// sendrecv() above costs two passes (sender -> mailbox, mailbox -> user buffer) and a flag
+// round trip per 32 KB stripe: 73-100 GB/s measured on B200 against a ~690 GB/s link. When
+// the RECEIVE buffer is peer-mapped (a registered / symmetric buffer that every rank uses at
+// the same offset - the double-buffered K/V block of ring attention, a pipeline stage's
+// activation slot) the sender can write straight into it. What is left of the protocol is
+// one "ready" flag (receiver -> sender: my kernel has started, so everything that read the
+// buffer earlier on my stream is done) and one arrival counter (sender CTAs -> receiver).
+// Lane kXchgLane of the p2p counters carries both, lane kXchgTicket the retire ticket.
+constexpr int kXchgLane = kP2pLanes - 1;
+constexpr int kXchgTicket = kP2pLanes - 2;
+
+template <bool kBulk>
+__global__ void __launch_bounds__(kBulk ? 128 : kThreads)
+exchangeKernel(CommArgs a, const char* sendPtr, size_t sendBytes, int dst, char* remote, size_t recvBytes, int src) {
+  extern __shared__ __align__(128) char smem[];
+  __shared__ BulkRing ring;
+  SignalPad* me = a.self;
+  // counters only change when the LAST CTA retires, after every CTA has read them
+  const uint32_t sent = sendBytes ? me->p2pSent[kXchgLane][dst] : 0u;
+  const uint32_t recvd = recvBytes ? me->p2pRecvd[kXchgLane][src] : 0u;
+  if (recvBytes && blockIdx.x == 0 && threadIdx.x == 0) {
+    st_release_sys(&a.sig[src]->p2pTail[kXchgLane][a.rank], recvd + 1u);
+  }
+  if (kBulk) bulkRingInit(ring);
+  bool ok = true;
+  if (sendBytes) {
+    ok = ctaWait(a, &me->p2pTail[kXchgLane][dst], sent + 1u, dst);
+    if (ok) {
+      const size_t units = sendBytes / 16;
+      const size_t per = (units + gridDim.x - 1) / gridDim.x;
+      const size_t lo = static_cast<size_t>(blockIdx.x) * per, hi = lo + per < units ? lo + per : units;
+      if (lo < hi) {
+        if (kBulk) {
+          char* const d[1] = {remote + lo * 16};
+          ctaBulkCopy<1>(ring, smem, sendPtr + lo * 16, d, 1, (hi - lo) * 16);
+        } else {
+          ctaCopy(remote + lo * 16, sendPtr + lo * 16, (hi - lo) * 16);
+        }
+      }
+      if (blockIdx.x == gridDim.x - 1) {
+        for (size_t i = units * 16 + threadIdx.x; i < sendBytes; i += blockDim.x) remote[i] = sendPtr[i];
+      }
+      __syncthreads();
+      if (threadIdx.x == 0) {
+        __threadfence_system();
+        atomicAdd_system(&a.sig[dst]->p2pHead[kXchgLane][a.rank], 1u);
+      }
+    }
+  }
+  if (recvBytes && ok) ok = ctaWait(a, &me->p2pHead[kXchgLane][src], (recvd + 1u) * gridDim.x, src);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t* ticket = sendBytes ? &me->p2pSent[kXchgTicket][dst] : &me->p2pRecvd[kXchgTicket][src];
+    if (atomicAdd(ticket, 1u) == gridDim.x - 1) {
+      *ticket = 0u;
+      if (sendBytes) me->p2pSent[kXchgLane][dst] = sent + 1u;
+      if (recvBytes) me->p2pRecvd[kXchgLane][src] = recvd + 1u;
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kThreads) peerCopyKernel(char* dst, const char* src, size_t bytes) {
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
@@ -167,6 +229,10 @@ void preloadP2pKernels() {
   cudaFuncGetAttributes(&attr, reinterpret_cast<const void*>(p2pKernel));
   cudaFuncGetAttributes(&attr, reinterpret_cast<const void*>(peerCopyKernel));
   cudaFuncGetAttributes(&attr, reinterpret_cast<const void*>(peerBulkCopyKernel));
+  cudaFuncGetAttributes(&attr, reinterpret_cast<const void*>(exchangeKernel<false>));
+  cudaFuncGetAttributes(&attr, reinterpret_cast<const void*>(exchangeKernel<true>));
+  cudaFuncSetAttribute(reinterpret_cast<const void*>(exchangeKernel<true>), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                       kBulkSmemBytes);
   cudaGetLastError();
 }
 
@@ -179,6 +245,18 @@ void launchP2p(const CommArgs& a, const void* sendPtr, size_t sendBytes, int dst
   p2pKernel<<<sendLanes + recvLanes, kThreads, 0, stream>>>(a, static_cast<const char*>(sendPtr), sendBytes, dst,
                                                             static_cast<char*>(recvPtr), recvBytes, src, mailbox,
                                                             boxStride, slotBytes, nslots, lanes, sendLanes);
+}
+
+void launchExchange(const CommArgs& a, const void* sendPtr, size_t sendBytes, int dst, void* remote, size_t recvBytes,
+                    int src, int blocks, bool tma, cudaStream_t stream) {
+  const bool aligned = (reinterpret_cast<uintptr_t>(remote) | reinterpret_cast<uintptr_t>(sendPtr)) % 16 == 0;
+  if (tma && (aligned || sendBytes == 0)) {
+    exchangeKernel<true><<<blocks, 128, kBulkSmemBytes, stream>>>(a, static_cast<const char*>(sendPtr), sendBytes, dst,
+                                                                 static_cast<char*>(remote), recvBytes, src);
+  } else {
+    exchangeKernel<false><<<blocks, kThreads, 0, stream>>>(a, static_cast<const char*>(sendPtr), sendBytes, dst,
+                                                          static_cast<char*>(remote), recvBytes, src);
+  }
 }
 
 void launchPeerCopy(void* dst, const void* src, size_t bytes, int blocks, cudaStream_t stream, bool tma) {

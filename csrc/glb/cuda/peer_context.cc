@@ -178,6 +178,11 @@ PeerContext::PeerContext(std::shared_ptr<Context> context, int dev, PeerOptions 
   opts_.useNvls = envOverride("CUDA_NVLS", opts_.useNvls);
   long stageMb = envInt("CUDA_STAGE_MB", -1);
   if (stageMb > 0) opts_.stageBytes = static_cast<size_t>(stageMb) << 20;
+  // Point-to-point shape (must be the same on every rank, like every other option here).
+  if (long v = envInt("CUDA_P2P_LANES", -1); v > 0) opts_.p2pLanes = static_cast<int>(v);
+  if (long v = envInt("CUDA_P2P_SLOTS", -1); v > 0) opts_.p2pSlots = static_cast<int>(v);
+  if (long v = envInt("CUDA_P2P_SLOT_KB", -1); v > 0) opts_.p2pSlotBytes = static_cast<size_t>(v) << 10;
+  if (long v = envInt("CUDA_EXCHANGE_BLOCKS", -1); v > 0) opts_.exchangeBlocks = static_cast<int>(v);
 
   DeviceGuard g(device);
   GLB_CUDA_CHECK(cudaFree(nullptr));
@@ -195,7 +200,7 @@ PeerContext::PeerContext(std::shared_ptr<Context> context, int dev, PeerOptions 
   // Symmetric pool: [SignalPad | LL lines | p2p mailboxes | staging]. Zero-initialised
   // (epoch 0, no LL line carries a valid sequence number).
   opts_.llMaxBytes = roundUp(std::max<size_t>(opts_.llMaxBytes, 1024), 1024);
-  opts_.p2pLanes = std::max(1, std::min(opts_.p2pLanes, kP2pLanes));
+  opts_.p2pLanes = std::max(1, std::min(opts_.p2pLanes, kP2pLanes - 2));  // the last two lanes belong to exchange()
   opts_.p2pSlots = std::max(2, opts_.p2pSlots);
   opts_.p2pSlotBytes = roundUp(std::max<size_t>(opts_.p2pSlotBytes, 16u * 1024), static_cast<size_t>(opts_.p2pLanes) * 16);
   llOffset_ = roundUp(sizeof(SignalPad), 4096);

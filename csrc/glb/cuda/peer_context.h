@@ -65,6 +65,7 @@ struct PeerOptions {
   size_t p2pSlotBytes = 512 * 1024;  // one slot of a point-to-point mailbox ring
   int p2pSlots = 4;                  // slots per (source, destination) ring
   int p2pLanes = 16;                 // CTAs per direction of a point-to-point transfer
+  int exchangeBlocks = 32;           // CTAs of a zero-copy exchange (same value on every rank)
 };
 
 // A buffer that every rank can address: peer[r] is rank r's copy as mapped here.

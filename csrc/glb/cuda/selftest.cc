@@ -394,6 +394,26 @@ std::vector<SelfTestResult> loopbackSelfTest(PeerContext& pc, cudaStream_t strea
     return "";
   });
 
+  for (bool tma : {false, true}) {
+    R.run(tma ? "exchangeKernel<true> (zero-copy sendrecv, TMA)" : "exchangeKernel<false> (zero-copy sendrecv)",
+          [&]() -> std::string {
+            const CommArgs ca = pc.loopbackComm(2);
+            const size_t bytes = (5u << 20) + 16 + 4;
+            DevBuf src(bytes), dst(bytes);
+            for (int round = 0; round < 2; round++) {  // twice: the counters must carry over
+              launchFill(src.p, bytes / 4, DataType::FLOAT32, 0.0, 1.0 + round, stream);
+              GLB_CUDA_CHECK(cudaMemsetAsync(dst.p, 0, bytes, stream));
+              launchExchange(ca, src.p, bytes, 1, dst.p, bytes, 1, std::min(pc.maxBlocks(), 24), tma, stream);
+              noteLaunch();
+              auto h = download(dst.p, bytes / 4, stream);
+              for (size_t i = 0; i < bytes / 4; i++) {
+                if (!close(h[i], static_cast<double>(i) * (1.0 + round))) return strcat_all("round ", round, " element ", i, ": got ", h[i]);
+              }
+            }
+            return "";
+          });
+  }
+
   R.run("peerBulkCopyKernel (put / get, TMA)", [&]() -> std::string {
     const size_t bytes = (3u << 20) + 48 + 5;  // 16-byte body + a byte tail
     DevBuf src(bytes), dst(bytes);

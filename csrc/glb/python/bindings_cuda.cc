@@ -216,6 +216,12 @@ void registerCuda(py::module_& root) {
     sendrecv(pc, P(sp), sbytes, dst, P(rp), rbytes, src, S(st));
   }, py::arg("pc"), py::arg("send_ptr"), py::arg("send_bytes"), py::arg("dst"), py::arg("recv_ptr"),
      py::arg("recv_bytes"), py::arg("src"), py::arg("stream") = 0);
+  m.def("exchange", [](PeerContext& pc, uintptr_t sp, size_t sbytes, int dst, const PeerBuffer& rbuf, size_t roff,
+                       size_t rbytes, int src, uintptr_t st) {
+    py::gil_scoped_release nogil;
+    exchange(pc, P(sp), sbytes, dst, rbuf, roff, rbytes, src, S(st));
+  }, py::arg("pc"), py::arg("send_ptr"), py::arg("send_bytes"), py::arg("dst"), py::arg("recv_buf"),
+     py::arg("recv_offset"), py::arg("recv_bytes"), py::arg("src"), py::arg("stream") = 0);
   m.def("put", [](PeerContext& pc, uintptr_t local, const PeerBuffer& remote, size_t off, size_t bytes, int peer,
                   uintptr_t st) {
     py::gil_scoped_release nogil;

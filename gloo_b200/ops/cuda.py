@@ -20,7 +20,7 @@ from ..types import DataType, ReduceOp, describe, element_size
 
 _cu = _C.cuda
 
-ALGOS = {"auto": 0, "one_shot": 1, "two_shot": 2, "nvls": 3, "ll": 4, "pipelined": 5, "ring": 10, "ring_chunked": 11,
+ALGOS = {"auto": 0, "one_shot": 1, "two_shot": 2, "nvls": 3, "ll": 4, "pipelined": 5, "hybrid": 6, "ring": 10, "ring_chunked": 11,
          "halving_doubling": 12, "bcube": 13, "halving_doubling_pipelined": 14}
 
 
@@ -216,6 +216,19 @@ class CudaContext:
                      recv_tensor.data_ptr(), recv_tensor.numel() * recv_tensor.element_size(), src, _stream(stream))
         return recv_tensor
 
+    def exchange(self, send_tensor, dst: int, recv_tensor, src: int, stream=None):
+        """Zero-copy sendrecv: ``recv_tensor`` is a registered / symmetric tensor that EVERY rank passes at the
+        same offset; my payload is written straight into ``dst``'s copy of it, ``src`` writes into mine.
+
+        One kernel and one pass over the data (sendrecv() stages through a mailbox ring). Falls back to
+        sendrecv() when ``recv_tensor`` is not registered."""
+        buf, off = self.lookup(recv_tensor)
+        if buf is None:
+            return self.sendrecv(send_tensor, dst, recv_tensor, src, stream)
+        _cu.exchange(self.pc, send_tensor.data_ptr(), send_tensor.numel() * send_tensor.element_size(), dst, buf, off,
+                     recv_tensor.numel() * recv_tensor.element_size(), src, _stream(stream))
+        return recv_tensor
+
     def put(self, local, remote, peer: int, remote_offset: int = 0, stream=None):
         """One-sided: copy ``local`` into rank ``peer``'s copy of the registered tensor ``remote``."""
         buf, off = self.lookup(remote)
@@ -339,7 +352,7 @@ def _make_allreduce_class(name: str, algo: str):
             self.tensors = tensors
             _, n, dt, _ = describe(tensors[0])
             st = [_stream(s) for s in streams] if streams else []
-            assert variant in ("auto", "one_shot", "two_shot", "nvls", "ll", "pipelined")
+            assert variant in ("auto", "one_shot", "two_shot", "nvls", "ll", "pipelined", "hybrid")
             self._impl = _cu.CudaAllreduce(ctx, [t.data_ptr() for t in tensors], n, int(dt), int(op), st,
                                            ALGOS[algo] if literal else ALGOS[variant], host_workspace)
 

@@ -202,10 +202,15 @@ class UlyssesAttention(_Base):
 class RingExchange(_Base):
     """Neighbour exchange for ring attention (KV rotation) and pipeline parallelism.
 
-    CPU tensors go through UnboundBuffer send/recv. CUDA tensors use the fused NVLink
-    send+recv kernel (``CudaContext.sendrecv``): one launch streams ``send`` into the right
-    neighbour's mailbox ring while draining what the left neighbour streams into ours.
+    CPU tensors go through UnboundBuffer send/recv. CUDA tensors: when ``recv`` is a symmetric /
+    registered tensor (``kv_buffers``) the zero-copy kernel writes ``send`` straight into the right
+    neighbour's copy of it (``CudaContext.exchange``: one pass, ~link rate); any other tensor goes
+    through the fused send+recv kernel and its mailbox ring (``CudaContext.sendrecv``).
     """
+
+    def kv_buffers(self, numel: int, dtype):
+        """Two symmetric buffers to rotate between (every rank must call this in the same order)."""
+        return self.cc.empty(numel, dtype), self.cc.empty(numel, dtype)
 
     def rotate(self, send, recv, step: int = 1):
         right, left = (self.rank + step) % self.size, (self.rank - step) % self.size
@@ -213,7 +218,7 @@ class RingExchange(_Base):
             recv.copy_(send)
             return recv
         if _is_cuda(send):
-            self.cc.sendrecv(send, right, recv, left)
+            self.cc.exchange(send, right, recv, left)   # falls back to sendrecv() for unregistered tensors
             return recv
         from ..types import describe
 

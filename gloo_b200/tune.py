@@ -118,6 +118,7 @@ def main(argv=None):
     ap.add_argument("--kinds", default="sym,reg,user")
     ap.add_argument("--no-nccl", action="store_true")
     ap.add_argument("--stage-mb", type=int, default=256)
+    ap.add_argument("--focus", default="", help="'nvls': only the multicast kernels (NVLS with few CTAs, NVLS + P2P hybrid) on symmetric buffers")
     ap.add_argument("--compress-json", default="", help="no measurement: rebuild the table from a saved <out>.json")
     args = ap.parse_args(argv)
     if args.compress_json:
@@ -222,26 +223,36 @@ def main(argv=None):
             for kind in kinds:
                 t = {"sym": sym, "reg": reg, "user": plain}[kind]
                 cands = []
-                if nb <= ll_max:
+                focus = args.focus == "nvls"
+                if nb <= ll_max and not focus:
                     for b in (1, 4, 16, 64):
                         if b > 1 and nb < b * 512:
                             continue  # more CTAs than 8-byte units to hand out
                         cands.append(attempt("ll", lambda: cc.allreduce(t, algo="ll", stream=stream, blocks=b), nb, blocks=b))
-                if nb * P <= (256 << 10) * 2 and nb <= (128 << 10):
+                if nb * P <= (256 << 10) * 2 and nb <= (128 << 10) and not focus:
                     for b in (2, 8, 16):
                         cands.append(attempt("one_shot", lambda: cc.allreduce(t, algo="one_shot", stream=stream, blocks=b), nb, blocks=b))
-                if kind in ("sym", "reg") and nb >= 4096:
+                if kind in ("sym", "reg") and nb >= 4096 and not focus:
                     unrolls = {2: (2, 4, 8), 4: (1, 2, 4), 8: (1, 2)}.get(P, (0,))
                     for b in blocks_bw:
                         for u in unrolls:
                             cands.append(attempt("two_shot", lambda: cc.allreduce(t, algo="two_shot", stream=stream, blocks=b, unroll=u), nb,
                                                  blocks=b, unroll=u))
                 if kind == "sym" and cc.nvls_available() and nb >= 4096:
-                    for b in blocks_bw + [222, 296]:
-                        for u in (2, 4, 8):
+                    nvls_blocks = [4, 8, 16, 24, 32, 48, 64, 96] if args.focus == "nvls" else blocks_bw + [222, 296]
+                    for b in nvls_blocks:
+                        for u in ((2, 4) if args.focus == "nvls" else (2, 4, 8)):
                             cands.append(attempt("nvls", lambda: cc.allreduce(t, algo="nvls", stream=stream, blocks=b, unroll=u), nb,
                                                  blocks=b, unroll=u))
-                if kind == "user" and nb >= 32768:
+                if kind == "sym" and cc.nvls_available() and nb >= (1 << 20) and P in (2, 4, 8) and args.focus == "nvls":
+                    # blocks = all CTAs, unroll = CTAs of the multicast part, tile = per-mille done peer to peer
+                    for b in (64, 96, 148):
+                        for nb_mc in (16, 32):
+                            for pm in (100, 175, 250, 350):
+                                cands.append(attempt("hybrid", lambda: cc.allreduce(t, algo="hybrid", stream=stream, blocks=b,
+                                                                                    unroll=nb_mc, tile=pm), nb,
+                                                     blocks=b, unroll=nb_mc, tile=pm))
+                if kind == "user" and nb >= 32768 and args.focus != "nvls":
                     for b in ([64, 128, 148] if not args.quick else [148]):
                         for tile in (256, 1024, 4096):
                             for xw in (4, 8, 12):  # exchange warps of the 16 per CTA

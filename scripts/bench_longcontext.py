@@ -86,9 +86,27 @@ def main():
             ring.rotate(src, nxt)
         stream.synchronize()
         assert float(nxt.flatten()[0]) == left and float(nxt.flatten()[-1]) == left, "ring rotation delivered the wrong block"
+        # the same rotation between two symmetric buffers: zero-copy exchange kernel
+        ka, kb = ring.kv_buffers(kv.numel(), torch.bfloat16)
+        ka.copy_(kv.view(-1))
+        with torch.cuda.stream(stream):
+            us = timed(lambda: ring.rotate(ka, kb), nbytes)
+        row["ring_rotate_symmetric_us"] = round(us, 2)
+        row["ring_rotate_symmetric_gbs_per_dir"] = round(nbytes / (us * 1e-6) / 1e9, 1)
+        stream.synchronize()
+        gb.barrier(ctx)
+        ka.fill_(float(rank))
+        torch.cuda.synchronize()
+        gb.barrier(ctx)
+        with torch.cuda.stream(stream):
+            ring.rotate(ka, kb)
+        stream.synchronize()
+        assert float(kb[0]) == left and float(kb[-1]) == left, "symmetric ring rotation delivered the wrong block"
+        gb.barrier(ctx)
         if nccl is not None:
             us = timed(lambda: nccl.sendrecv(kv.data_ptr(), right, nxt.data_ptr(), left, kv.numel(), BF16, stream.cuda_stream), nbytes)
             row["nccl_ring_rotate_us"] = round(us, 2)
+            row["nccl_ring_rotate_gbs_per_dir"] = round(nbytes / (us * 1e-6) / 1e9, 1)
         # Ulysses: q/k/v projections of this shard, heads scattered across ranks
         x = torch.randn(shard, args.heads, args.head_dim, device="cuda").to(torch.bfloat16)
         xin = x.view(shard, world, args.heads // world, args.head_dim).transpose(0, 1).contiguous()  # [P, S/P, H/P, D]
@@ -104,7 +122,7 @@ def main():
         rows.append(row)
         if rank == 0:
             print(json.dumps(row), flush=True)
-        del kv, nxt, src, x, xin, out
+        del kv, nxt, src, x, xin, out, ka, kb
         torch.cuda.synchronize()
         gb.barrier(ctx)
     if rank == 0 and args.out:

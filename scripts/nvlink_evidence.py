@@ -22,9 +22,11 @@ from gloo_b200.ops import cuda as gcu  # noqa: E402
 
 
 def counters(index: int):
-    """(tx_bytes, rx_bytes) summed over the links of one GPU, or None."""
+    """(tx_bytes, rx_bytes) summed over the links of one GPU, or None. The GPU is named by UUID:
+    torch's index is relative to CUDA_VISIBLE_DEVICES, nvidia-smi's is not."""
     try:
-        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", str(index)], capture_output=True, text=True, timeout=20).stdout
+        gpu = "GPU-" + str(torch.cuda.get_device_properties(index).uuid)
+        out = subprocess.run(["nvidia-smi", "nvlink", "-gt", "d", "-i", gpu], capture_output=True, text=True, timeout=30).stdout
     except Exception:  # noqa: BLE001
         return None
     tx = [int(x) for x in re.findall(r"Data Tx:\s*(\d+)\s*KiB", out)]
@@ -61,17 +63,28 @@ def main():
     else:
         cases[-1] = ("pipelined", plain, "pipelined", 2 * S * (P - 1) / P, 2 * S * (P - 1) / P)
     for name, t, algo, alg_tx, alg_rx in cases:
-        t.fill_(1.0)
+        t.fill_(0.0)   # sums stay finite however many steps run
+        if rank == 0:
+            t.fill_(1.0)
         for _ in range(3):
             cc.allreduce(t, algo=algo, stream=stream)
         stream.synchronize()
         gb.barrier(ctx)
-        before = counters(local)
+        # pass 1: time (no nvidia-smi anywhere near: the query takes 0.1-1 s and a different time on
+        # every rank, which the first kernel of the loop would wait out)
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record(stream)
         for _ in range(args.steps):
             cc.allreduce(t, algo=algo, stream=stream)
         b.record(stream)
+        stream.synchronize()
+        gb.barrier(ctx)
+        # pass 2: the same steps between two counter reads
+        torch.cuda.synchronize()
+        before = counters(local)
+        gb.barrier(ctx)
+        for _ in range(args.steps):
+            cc.allreduce(t, algo=algo, stream=stream)
         stream.synchronize()
         gb.barrier(ctx)
         after = counters(local)

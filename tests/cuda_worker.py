@@ -126,6 +126,25 @@ def main():
     cc.barrier()
     cc.synchronize()
     assert float(r_t[0]) == left and float(r_t[-1]) == left and float(win[8 * left]) == left
+    # zero-copy exchange into a symmetric double buffer: three ring steps, alternating halves
+    m = 2_000_003
+    kv = cc.empty(2 * m, torch.float32)
+    kv[:m].fill_(float(rank))
+    cc.synchronize()
+    cc.pc.host_barrier()
+    for step in range(3):
+        cur, nxt = kv[(step % 2) * m:(step % 2 + 1) * m], kv[((step + 1) % 2) * m:((step + 1) % 2 + 1) * m]
+        cc.exchange(cur, right, nxt, left)
+        cc.synchronize()
+        assert float(nxt[0]) == (rank - step - 1) % size and float(nxt[-1]) == (rank - step - 1) % size, (step, float(nxt[0]))
+    # NVLS + peer-to-peer hybrid
+    if cc.nvls_available() and size in (2, 4, 8):
+        for n, split in ((3_000_001, 300), (5_000_000, 0), (40_000, 900)):
+            t = cc.empty(n, torch.float32)
+            t.copy_(inp(n))
+            cc.allreduce(t, algo="hybrid", average=True, blocks=48, unroll=16, tile=split)
+            cc.synchronize()
+            torch.testing.assert_close(t.double().cpu(), exp_sum(n) / size, rtol=1e-5, atol=1e-6)
     # CUDA graph: fill + three allreduces captured once, replayed
     gs = torch.cuda.Stream()
     gt = cc.empty(1 << 18, torch.float32)

@@ -368,6 +368,38 @@ def test_p2p_ring_sendrecv_put_get(size):
     assert all(gb.spawn_threads(size, fn, cuda_device=0))
 
 
+@pytest.mark.parametrize("size", [2, 3, 4])
+def test_zero_copy_exchange_ring(size):
+    """exchange(): the sender writes straight into the neighbour's symmetric buffer; counters carry over
+    from call to call, every payload size (sub-16-byte tail, TMA and LDG/STG variants)."""
+    def fn(ctx):
+        cc = gcu.CudaContext(ctx, 0, stage_bytes=8 << 20)
+        right, left = (ctx.rank + 1) % size, (ctx.rank - 1) % size
+        for n in (1, 1001, 70_001, 2_000_003):
+            kv = cc.empty(2 * n + 8, torch.float32)
+            halves = [kv[:n], kv[n + (-n) % 4:2 * n + (-n) % 4]]   # both 16-byte aligned
+            halves[0].fill_(float(ctx.rank))
+            _sync()
+            cc.pc.host_barrier()
+            for step in range(size + 1):
+                cur, nxt = halves[step % 2], halves[(step + 1) % 2]
+                cc.exchange(cur, right, nxt, left)
+                _sync()
+                want = float((ctx.rank - step - 1) % size)
+                assert float(nxt[0]) == want and float(nxt[-1]) == want and float(nxt[n // 2]) == want, (n, step)
+            cc.pc.host_barrier()
+        # unregistered receive tensor: falls back to the mailbox path
+        r = torch.zeros(5000, device="cuda")
+        cc.exchange(torch.full((5000,), float(ctx.rank), device="cuda"), right, r, left)
+        _sync()
+        assert float(r[-1]) == left
+        cc.check_health()
+        cc.pc.host_barrier()
+        return True
+
+    assert all(gb.spawn_threads(size, fn, cuda_device=0))
+
+
 # ---- ordering across streams, literal pipelined schedule ------------------------------------------------------------
 
 def test_collectives_on_two_streams_are_ordered():

@@ -530,6 +530,36 @@ def run_ours(args):
                 row["nccl_p50_us"], row["nccl_p99_us"] = round(n50, 2), round(n99, 2)
             sweep.append(row)
             del ts, algo
+    # ---- small messages inside a CUDA graph: 32 allreduces per graph, per-op time of a replay --------
+    # (the per-iteration events above pay a launch + two event records per call; a training loop that
+    # captures its step pays neither)
+    graph_rows = []
+    if not args.no_sweep and world > 1:
+        OPS = 32
+        for n in (1, 256, 4096):
+            small = torch.ones(n, device=dev)
+            row = {"elements": n, "bytes": n * 4, "ops_per_graph": OPS}
+            for name in ("ours", "nccl"):
+                if name == "nccl" and nccl is None:
+                    continue
+                try:
+                    sync_all()
+                    g = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(g, stream=stream):
+                        for _ in range(OPS):
+                            if name == "ours":
+                                cc.allreduce(small, stream=stream)
+                            else:
+                                nccl.allreduce(small.data_ptr(), small.data_ptr(), n, F32, 1, stream.cuda_stream)
+                    p50, p99, mn = latency(g.replay, 30, n * 4)
+                    key = "" if name == "ours" else "nccl_"
+                    row[key + "p50_us_per_op"], row[key + "p99_us_per_op"] = round(p50 / OPS, 2), round(p99 / OPS, 2)
+                    del g
+                except Exception as e:  # noqa: BLE001
+                    row[name + "_error"] = f"{type(e).__name__}: {str(e)[:120]}"
+            graph_rows.append(row)
+            del small
+        extra["graph_small_allreduce"] = graph_rows
     sync_all()
     cc.check_health()
     del nccl

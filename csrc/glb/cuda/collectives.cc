@@ -52,6 +52,7 @@ Tuning& tuning() {
     x.nvlsReduceScatter = envFlag("CUDA_NVLS_REDUCE_SCATTER", x.nvlsReduceScatter);
     setOneShotPush(envFlag("CUDA_ONESHOT_PUSH", true));
     x.bcastDirectMaxBytes = static_cast<size_t>(envInt("CUDA_BCAST_DIRECT_MAX", static_cast<long>(x.bcastDirectMaxBytes)));
+    x.bcastRelayMinBytes = static_cast<size_t>(envInt("CUDA_BCAST_RELAY_MIN", static_cast<long>(x.bcastRelayMinBytes)));
     x.pipeTile = static_cast<int>(envInt("CUDA_PIPE_TILE", x.pipeTile));
     x.pipeExchangeThreads = static_cast<int>(envInt("CUDA_PIPE_XTHREADS", x.pipeExchangeThreads));
     x.tmaCopies = envFlag("CUDA_TMA", x.tmaCopies);
@@ -476,6 +477,57 @@ int bwBlocks(PeerContext& pc, const char* coll, const void* kernel, size_t workB
 
 }  // namespace
 
+namespace {
+// Launch shape of one broadcast kernel. mode 0 = root pushes everything, 1 = scatter +
+// allgather, 2 = multimem.st, 3 = chunk-pipelined relay (see broadcastKernel).
+struct BcastShape {
+  int mode = 0;
+  int blocks = 1;
+  int tile = 0;
+};
+
+BcastShape planBroadcast(PeerContext& pc, size_t bytes, bool vec, bool hasMc) {
+  const auto& t = tuning();
+  BcastShape sh;
+  const TuneEntry* e = TuningTable::get().lookup("broadcast", pc.size, BufKind::REGISTERED, bytes);
+  // multimem.st pays off when the root would otherwise send P-1 copies: P > 2. From
+  // bcastRelayMinBytes up the pipelined relay keeps every link busy instead.
+  if (pc.size > 2 && vec && bytes >= t.bcastRelayMinBytes) {
+    sh.mode = 3;
+  } else if (hasMc && vec && pc.size > 2 && bytes >= t.bcastDirectMaxBytes) {
+    sh.mode = 2;
+  } else if (bytes > t.bcastDirectMaxBytes && pc.size > 2) {
+    sh.mode = 1;
+  }
+  if (e != nullptr) {
+    if (e->algo == "relay" && vec && pc.size > 2) sh.mode = 3;
+    if (e->algo == "nvls" && hasMc && vec) sh.mode = 2;
+    if (e->algo == "scatter" && pc.size > 2) sh.mode = 1;
+    if (e->algo == "direct") sh.mode = 0;
+  }
+  long forced = envInt("CUDA_BCAST_MODE", -1);
+  if (forced >= 0 && forced <= 3 && (forced != 2 || (hasMc && vec)) && (forced != 3 || (vec && pc.size > 2))) {
+    sh.mode = static_cast<int>(forced);
+  }
+  sh.blocks = bwBlocks(pc, "broadcast", broadcastKernelPtr(), sh.mode == 1 ? bytes / pc.size * 2 : bytes, bytes);
+  if (sh.mode == 3) {
+    // Tiles of at least 8 KB per CTA (one full pass of the CTA), at least ~4 chunks in flight
+    // behind each other; small payloads use fewer CTAs rather than smaller tiles.
+    const size_t units = bytes / 16;
+    const size_t R = static_cast<size_t>(pc.size - 1);
+    long tile = envInt("CUDA_BCAST_TILE", e != nullptr && e->tile > 0 ? e->tile : 0);
+    if (tile <= 0) {
+      tile = 512;
+      while (tile < 4096 && units / (R * static_cast<size_t>(sh.blocks) * static_cast<size_t>(tile) * 2) >= 8) tile *= 2;
+    }
+    sh.tile = static_cast<int>(tile);
+    const size_t fit = std::max<size_t>(units / (R * static_cast<size_t>(sh.tile) * 4), 1);
+    sh.blocks = static_cast<int>(std::min<size_t>(static_cast<size_t>(sh.blocks), fit));
+  }
+  return sh;
+}
+}  // namespace
+
 void broadcast(PeerContext& pc, const PeerBuffer& buf, size_t byteOffset, size_t bytes, int root,
                cudaStream_t stream) {
   GLB_TRACE_RANGE("glb::cuda::broadcast");
@@ -484,21 +536,10 @@ void broadcast(PeerContext& pc, const PeerBuffer& buf, size_t byteOffset, size_t
   GLB_ENFORCE_LE(byteOffset + bytes, buf.bytes, "broadcast range exceeds the registered buffer");
   DeviceGuard g(pc.device);
   const bool vec = buf.vectorOk && byteOffset % 16 == 0;
-  int mode = 0;
-  // multimem.st pays off when the root would otherwise send P-1 copies: P > 2.
-  if (buf.mc != nullptr && vec && pc.size > 2 && bytes >= tuning().bcastDirectMaxBytes) {
-    mode = 2;
-  } else if (bytes > tuning().bcastDirectMaxBytes && pc.size > 2) {
-    mode = 1;
-  }
-  {
-    long forced = envInt("CUDA_BCAST_MODE", -1);
-    if (forced >= 0 && forced <= 2 && (forced != 2 || (buf.mc != nullptr && vec))) mode = static_cast<int>(forced);
-  }
-  const int blocks = bwBlocks(pc, "broadcast", broadcastKernelPtr(), mode == 1 ? bytes / pc.size * 2 : bytes, bytes);
+  const BcastShape sh = planBroadcast(pc, bytes, vec, buf.mc != nullptr);
   prologue(pc, stream);
   launchBroadcast(pc.comm(), buf.ptrsAt(byteOffset), buf.mc ? static_cast<char*>(buf.mc) + byteOffset : nullptr,
-                  bytes, root, mode, vec, blocks, stream);
+                  bytes, root, sh.mode, vec, sh.blocks, sh.tile, stream);
   finish(pc, stream, "broadcast");
 }
 
@@ -514,15 +555,9 @@ void broadcast(PeerContext& pc, void* ptr, size_t bytes, int root, cudaStream_t 
     const size_t n = std::min(piece, bytes - done);
     char* p = static_cast<char*>(ptr) + done;
     if (pc.rank == root) GLB_CUDA_CHECK(cudaMemcpyAsync(mine, p, n, cudaMemcpyDeviceToDevice, stream));
-    int mode = 0;
-    if (pc.nvlsAvailable() && pc.size > 2 && n >= tuning().bcastDirectMaxBytes) {
-      mode = 2;
-    } else if (n > tuning().bcastDirectMaxBytes && pc.size > 2) {
-      mode = 1;
-    }
+    const BcastShape sh = planBroadcast(pc, n, true, pc.nvlsAvailable());
     prologue(pc, stream);
-    launchBroadcast(pc.comm(), stage, pc.stageMc(l.bulkOff), n, root, mode, true,
-                    bwBlocks(pc, "broadcast", broadcastKernelPtr(), mode == 1 ? n / pc.size * 2 : n, n), stream);
+    launchBroadcast(pc.comm(), stage, pc.stageMc(l.bulkOff), n, root, sh.mode, true, sh.blocks, sh.tile, stream);
     finish(pc, stream, "broadcast(staged)");
     if (pc.rank != root) GLB_CUDA_CHECK(cudaMemcpyAsync(p, mine, n, cudaMemcpyDeviceToDevice, stream));
   }

@@ -61,7 +61,7 @@ void launchPipelinedAllreduce(const CommArgs& a, const void* in, void* out, size
 
 // collective_kernels.cu -----------------------------------------------------------------------
 void launchBroadcast(const CommArgs& a, const PeerPtrs& bufs, void* mc, size_t bytes, int root, int mode, bool vec,
-                     int blocks, cudaStream_t stream);
+                     int blocks, int tile, cudaStream_t stream);
 void launchGatherPush(const CommArgs& a, const void* in, const PeerPtrs& outs, void* mcOut, const size_t* offs,
                       const size_t* lens, int onlyDst, bool vec, int blocks, cudaStream_t stream, bool tma = false);
 void launchAlltoallPush(const CommArgs& a, const void* in, const PeerPtrs& outs, const size_t* sendOff,

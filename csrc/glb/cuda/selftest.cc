@@ -218,7 +218,7 @@ std::vector<SelfTestResult> loopbackSelfTest(PeerContext& pc, cudaStream_t strea
     // ---- data movement ---------------------------------------------------------------------
     R.run(strcat_all("broadcastKernel(direct) P=", P), [&]() -> std::string {
       fillAll();
-      launchBroadcast(ca, pp, nullptr, n * 4, 0, 0, true, std::min(2 * pc.maxBlocks(), 32), stream);
+      launchBroadcast(ca, pp, nullptr, n * 4, 0, 0, true, std::min(2 * pc.maxBlocks(), 32), 0, stream);
       noteLaunch();
       auto h = download(pp.p[P - 1], n, stream);
       for (size_t i = 0; i < n; i++) {

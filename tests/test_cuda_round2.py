@@ -2,6 +2,8 @@
 plain-pointer allreduce, point-to-point transfers, device-side failure detection and the
 virtual-rank loopback self-test. Numerics are compared against a plain PyTorch fp32/fp64
 reference of the same operation. Ranks are threads sharing cuda:0 (see test_cuda_allreduce.py)."""
+import os
+
 import pytest
 import torch
 
@@ -398,6 +400,40 @@ def test_zero_copy_exchange_ring(size):
         return True
 
     assert all(gb.spawn_threads(size, fn, cuda_device=0))
+
+
+@pytest.mark.parametrize("size", [3, 4])
+def test_relay_broadcast(size, monkeypatch):
+    """Chunk-pipelined relay broadcast (mode 3): every root, sizes with partial tiles / chunks and a byte tail,
+    registered buffers and plain pointers (staged)."""
+    monkeypatch.setenv("GLB_CUDA_BCAST_MODE", "3")
+
+    def fn(ctx):
+        cc = gcu.CudaContext(ctx, 0, stage_bytes=16 << 20)
+        for n, tile in ((5, 0), (4099, 0), (300_001, 64), (2_500_003, 256), (2_500_003, 0)):
+            os.environ["GLB_CUDA_BCAST_TILE"] = str(tile)
+            for root in range(size):
+                t = cc.empty(n, torch.float32)
+                t.fill_(-1.0)
+                if ctx.rank == root:
+                    t.copy_(torch.arange(n, dtype=torch.float32, device="cuda") * 0.5 + root)
+                cc.broadcast(t, root=root)
+                _sync()
+                want = torch.arange(n, dtype=torch.float64) * 0.5 + root
+                torch.testing.assert_close(t.double().cpu(), want)
+                cc.pc.host_barrier()
+        u = torch.full((1_000_003,), float(ctx.rank), dtype=torch.uint8, device="cuda")[3:]  # misaligned plain pointer
+        cc.broadcast(u, root=size - 1)
+        _sync()
+        assert int(u[0]) == size - 1 and int(u[-1]) == size - 1
+        cc.check_health()
+        cc.pc.host_barrier()
+        return True
+
+    try:
+        assert all(gb.spawn_threads(size, fn, cuda_device=0))
+    finally:
+        os.environ.pop("GLB_CUDA_BCAST_TILE", None)
 
 
 # ---- ordering across streams, literal pipelined schedule ------------------------------------------------------------

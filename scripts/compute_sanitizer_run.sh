@@ -33,7 +33,7 @@ PY
 rc=0
 for tool in memcheck racecheck synccheck; do
   timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 --print-limit 20 \
-    python /tmp/glb_sanitize_target.py > "$out/sanitizer_$tool.log" 2>&1
+    env PYTHONPATH=$PWD python /tmp/glb_sanitize_target.py > "$out/sanitizer_$tool.log" 2>&1
   r=$?
   echo "compute-sanitizer $tool rc=$r" | tee -a "$out/sanitizer_summary.txt"
   grep -E "ERROR SUMMARY|RACECHECK SUMMARY|hazard" "$out/sanitizer_$tool.log" | tail -3 | tee -a "$out/sanitizer_summary.txt"

@@ -26,6 +26,7 @@ KERNELS = [
     ("two_shot_f16_P8", r"twoShotAllreduceKernel<__half, 8, 2>"),
     ("nvls_f32", r"nvlsAllreduceKernel<float, 4>"),
     ("nvls_bf16", r"nvlsAllreduceKernel<__nv_bfloat16, 4>"),
+    ("hybrid_nvls_p2p_f32_P8", r"hybridAllreduceKernel<float, 8>"),
     ("cast_f32_to_bf16", r"castAllreduceKernel<float, __nv_bfloat16>"),
     ("pipelined_f32_nvls", r"pipelinedAllreduceKernel<float, true, 0>"),
     ("pipelined_f32_P2", r"pipelinedAllreduceKernel<float, false, 2>"),
@@ -35,6 +36,8 @@ KERNELS = [
     ("gather_bulk_tma", r"gatherBulkKernel"),
     ("alltoall_push", r"alltoallPushKernel"),
     ("p2p_sendrecv", r"p2pKernel"),
+    ("exchange_zero_copy", r"exchangeKernel<false>"),
+    ("exchange_zero_copy_tma", r"exchangeKernel<true>"),
     ("peer_copy", r"peerCopyKernel"),
     ("peer_bulk_copy_tma", r"peerBulkCopyKernel"),
     ("schedule_f32", r"scheduleKernel<float>"),

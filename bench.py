@@ -569,6 +569,9 @@ def run_ours(args):
         link = extra.get("peer_copy_gbs_measured_here")
         # Bytes that must cross NVLink per GPU and direction for this variant, against the link rate.
         wire_factor = {"nvls": (1 + 1 / world), "two_shot": 2 * (world - 1) / world}.get(resolved, None) if world > 1 else None
+        if world > 1 and resolved == "hybrid":  # per-mille `tile` of the vector goes peer to peer, the rest through the switch
+            pm = (plan.get("tile") or 175) / 1000.0
+            wire_factor = (1 - pm) * (1 + 1 / world) + pm * 2 * (world - 1) / world
         roofline = {"nvlink_gbs_per_dir_nominal": 900,
                     "nvlink_gbs_per_dir_measured_guide": 770,
                     "nvlink_gbs_per_dir_measured_here": link,

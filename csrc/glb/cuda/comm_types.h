@@ -11,7 +11,7 @@ namespace cuda {
 constexpr int kMaxRanks = 16;
 constexpr int kMaxBlocks = 512;   // upper bound on CTAs of one collective kernel
 constexpr int kThreads = 512;     // threads per CTA of the data-moving kernels
-constexpr int kP2pLanes = 32;     // max CTAs per direction of a point-to-point transfer
+constexpr int kP2pLanes = 64;     // max CTAs per direction of a point-to-point transfer
 
 // Why a kernel gave up (SignalPad::abort / the host status word).
 enum AbortCode : uint32_t {

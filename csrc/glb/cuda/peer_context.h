@@ -62,9 +62,9 @@ struct PeerOptions {
   bool useVmm = true;                // try cuMem + fd passing before cudaIpc
   bool useNvls = true;               // bind symmetric memory to a multicast object when possible
   size_t llMaxBytes = 256 * 1024;    // largest message of the flag-in-data (LL) kernels
-  size_t p2pSlotBytes = 512 * 1024;  // one slot of a point-to-point mailbox ring
+  size_t p2pSlotBytes = 3u << 20;  // one slot of a point-to-point mailbox ring
   int p2pSlots = 4;                  // slots per (source, destination) ring
-  int p2pLanes = 16;                 // CTAs per direction of a point-to-point transfer
+  int p2pLanes = 48;                 // CTAs per direction of a point-to-point transfer
   int exchangeBlocks = 32;           // CTAs of a zero-copy exchange (same value on every rank)
 };
 

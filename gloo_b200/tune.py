@@ -106,6 +106,34 @@ def compress(results, P, dtype_name="float32", device_name="NVIDIA B200", cores=
     return lines
 
 
+def merge_tables(base_lines, new_lines, min_bytes):
+    """Replace, per (collective, P, buffer kind) that ``new_lines`` covers, the part of ``base_lines`` from
+    ``min_bytes`` up with ``new_lines`` (a focused re-tune of the large sizes keeps the small-size rows)."""
+    def parse(line):
+        f = line.split()
+        kv = dict(x.split("=", 1) for x in f[1:])
+        mb = float("inf") if kv["maxbytes"] == "inf" else float(kv["maxbytes"])
+        return (f[0], kv["P"], kv["buf"]), mb
+
+    new = [ln for ln in new_lines if ln.strip() and not ln.startswith("#")]
+    keys = {parse(ln)[0] for ln in new}
+    out, clipped = [], set()
+    for ln in base_lines:
+        if not ln.strip() or ln.startswith("#"):
+            out.append(ln)
+            continue
+        key, mb = parse(ln)
+        if key not in keys or mb < min_bytes:
+            out.append(ln)
+        elif key not in clipped:  # the row that straddles min_bytes keeps its lower part
+            clipped.add(key)
+            out.append(" ".join(x if not x.startswith("maxbytes=") else f"maxbytes={int(min_bytes) - 1}" for x in ln.split()))
+            out.extend(l2 for l2 in new if parse(l2)[0] == key)
+    for key in keys - clipped:
+        out.extend(l2 for l2 in new if parse(l2)[0] == key)
+    return out
+
+
 def main(argv=None):
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="gpurun_out/tune")
@@ -118,9 +146,20 @@ def main(argv=None):
     ap.add_argument("--kinds", default="sym,reg,user")
     ap.add_argument("--no-nccl", action="store_true")
     ap.add_argument("--stage-mb", type=int, default=256)
+    ap.add_argument("--merge", nargs=3, metavar=("BASE", "NEW", "OUT"), help="no measurement: splice table NEW into BASE from --merge-min-bytes up")
+    ap.add_argument("--merge-min-bytes", type=int, default=1 << 20)
     ap.add_argument("--focus", default="", help="'nvls': only the multicast kernels (NVLS with few CTAs, NVLS + P2P hybrid) on symmetric buffers")
     ap.add_argument("--compress-json", default="", help="no measurement: rebuild the table from a saved <out>.json")
     args = ap.parse_args(argv)
+    if args.merge:
+        base, new, out = args.merge
+        with open(base) as f:
+            base_lines = f.read().splitlines()
+        with open(new) as f:
+            new_lines = f.read().splitlines()
+        with open(out, "w") as f:
+            f.write("\n".join(merge_tables(base_lines, new_lines, args.merge_min_bytes)) + "\n")
+        return 0
     if args.compress_json:
         with open(args.compress_json) as f:
             saved = json.load(f)

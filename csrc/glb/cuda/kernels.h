@@ -111,6 +111,9 @@ void launchFill(void* dst, size_t count, DataType dt, double start, double strid
 void launchVerify(const void* buf, size_t count, DataType dt, double start, double stride, double rtol, double atol,
                   unsigned long long* deviceResult, cudaStream_t stream);
 void launchSpin(long long cycles, cudaStream_t stream);
+// Launch shape of the single-rank fused step (localAllreduceManyKernel): CTAs per SM, packs per
+// thread and trip, contiguous tile per CTA or grid stride. Default from GLB_LOCAL_SHAPE.
+void setLocalAllreduceShape(int ctasPerSm, int unroll, bool tiled);
 
 }  // namespace cuda
 }  // namespace glb

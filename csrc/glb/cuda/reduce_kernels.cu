@@ -12,6 +12,10 @@
 // Parity: gloo/cuda.cu:274-407 (K1-K5), cuda_private.cu:38-61 (K6),
 // test/cuda_base_test.cu:15-27 (K7) — rewritten, not ported: the reference kernels
 // are scalar, int-indexed, one element per thread.
+#include <cstdio>
+#include <string>
+
+#include "glb/common/utils.h"
 #include "glb/cuda/device_common.cuh"
 #include "glb/cuda/kernels.h"
 
@@ -53,19 +57,23 @@ localReduceManyKernel(T* __restrict__ dst, SrcPtrs srcs, int nsrc, size_t count,
 // in ONE pass (n reads + n writes per element). This is the whole step when a job has a
 // single rank with several local pointers (CudaAllreduce* with ptrs.size() > 1, size == 1,
 // and CudaAllreduceLocal): previously a reduce pass followed by a broadcast pass.
-template <typename T>
+// U = 128-bit packs per thread and trip (loads of all trips are issued before the first
+// store); kTiled: a CTA works on a contiguous tile of U x blockDim packs per trip (fewer DRAM
+// pages open at once) instead of striding the whole grid between the U packs.
+template <typename T, int U, bool kTiled>
 __global__ void __launch_bounds__(kLocalThreads)
 localAllreduceManyKernel(DstPtrs bufs, int n, size_t count, DevOp op, float scale, bool vectorOk) {
   using PT = PackTraits<T>;
   const size_t tid = static_cast<size_t>(blockIdx.x) * blockDim.x + threadIdx.x;
   const size_t nthreads = static_cast<size_t>(gridDim.x) * blockDim.x;
   const size_t nvec = vectorOk ? count / PT::kElems : 0;
-  constexpr int U = 2;
-  for (size_t v0 = tid; v0 < nvec; v0 += nthreads * U) {
+  const size_t first = kTiled ? static_cast<size_t>(blockIdx.x) * blockDim.x * U + threadIdx.x : tid;
+  const size_t inner = kTiled ? blockDim.x : nthreads;  // distance between the U packs of one trip
+  for (size_t v0 = first; v0 < nvec; v0 += nthreads * U) {
     typename PT::AccPack acc[U];
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      const size_t v = v0 + u * nthreads;
+      const size_t v = v0 + u * inner;
       if (v < nvec) {
         acc[u] = PT::widen(ld128_stream(static_cast<const char*>(bufs.p[0]) + v * 16));
         for (int s = 1; s < n; s++) PT::combine(acc[u], ld128_stream(static_cast<const char*>(bufs.p[s]) + v * 16), op);
@@ -73,7 +81,7 @@ localAllreduceManyKernel(DstPtrs bufs, int n, size_t count, DevOp op, float scal
     }
 #pragma unroll
     for (int u = 0; u < U; u++) {
-      const size_t v = v0 + u * nthreads;
+      const size_t v = v0 + u * inner;
       if (v < nvec) {
         if (scale != 1.0f) PT::scale(acc[u], scale);
         const Pack16 r = PT::narrow(acc[u]);
@@ -153,12 +161,35 @@ __global__ void spinKernel(long long cycles) {
   }
 }
 
-int gridFor(size_t items, int threads) {
+struct LocalShape {
+  int ctasPerSm = 4;
+  int unroll = 2;
+  bool tiled = false;
+};
+
+LocalShape localShapeFromEnv() {
+  LocalShape s;
+  const std::string v = envStr("LOCAL_SHAPE", "");
+  int a = 0, b = 0, c = 0;
+  if (!v.empty() && std::sscanf(v.c_str(), "%d,%d,%d", &a, &b, &c) == 3) {
+    if (a >= 1 && a <= 8) s.ctasPerSm = a;
+    if (b == 1 || b == 2 || b == 4) s.unroll = b;
+    s.tiled = c != 0;
+  }
+  return s;
+}
+
+LocalShape& localShape() {
+  static LocalShape s = localShapeFromEnv();
+  return s;
+}
+
+int gridFor(size_t items, int threads, int ctasPerSm = 4) {
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   size_t want = (items + threads - 1) / threads;
-  size_t cap = static_cast<size_t>(sms) * 4;
+  size_t cap = static_cast<size_t>(sms) * static_cast<size_t>(ctasPerSm);
   return static_cast<int>(want < 1 ? 1 : (want > cap ? cap : want));
 }
 
@@ -211,8 +242,20 @@ void launchLocalAllreduceMany(void* const* bufs, int n, size_t count, DataType d
   }
   dispatchType(dt, [&](auto tag) {
     using T = decltype(tag);
-    const int grid = gridFor(count / PackTraits<T>::kElems / 2 + 1, kLocalThreads);
-    localAllreduceManyKernel<T><<<grid, kLocalThreads, 0, stream>>>(bp, n, count, static_cast<DevOp>(op), scale, vectorOk);
+    // Launch shape: measured on B200 (scripts/bench_local.py); GLB_LOCAL_SHAPE = "<ctas per SM>,<unroll>,<tiled>".
+    const LocalShape shape = localShape();
+    const int grid = gridFor(count / PackTraits<T>::kElems / shape.unroll + 1, kLocalThreads, shape.ctasPerSm);
+    const DevOp dop = static_cast<DevOp>(op);
+    auto go = [&](auto kernel) { kernel<<<grid, kLocalThreads, 0, stream>>>(bp, n, count, dop, scale, vectorOk); };
+    if (shape.tiled) {
+      if (shape.unroll == 4) go(localAllreduceManyKernel<T, 4, true>);
+      else if (shape.unroll == 1) go(localAllreduceManyKernel<T, 1, true>);
+      else go(localAllreduceManyKernel<T, 2, true>);
+    } else {
+      if (shape.unroll == 4) go(localAllreduceManyKernel<T, 4, false>);
+      else if (shape.unroll == 1) go(localAllreduceManyKernel<T, 1, false>);
+      else go(localAllreduceManyKernel<T, 2, false>);
+    }
   });
 }
 
@@ -253,6 +296,13 @@ void launchFill(void* dst, size_t count, DataType dt, double start, double strid
 
 void launchSpin(long long cycles, cudaStream_t stream) { spinKernel<<<1, 1, 0, stream>>>(cycles); }
 
+void setLocalAllreduceShape(int ctasPerSm, int unroll, bool tiled) {
+  LocalShape& s = localShape();
+  if (ctasPerSm >= 1 && ctasPerSm <= 8) s.ctasPerSm = ctasPerSm;
+  if (unroll == 1 || unroll == 2 || unroll == 4) s.unroll = unroll;
+  s.tiled = tiled;
+}
+
 void preloadLocalKernels() {
   auto touch = [](const void* k) {
     cudaFuncAttributes attr;
@@ -263,7 +313,12 @@ void preloadLocalKernels() {
     dispatchType(dt, [&](auto tag) {
       using T = decltype(tag);
       touch(reinterpret_cast<const void*>(localReduceManyKernel<T>));
-      touch(reinterpret_cast<const void*>(localAllreduceManyKernel<T>));
+      touch(reinterpret_cast<const void*>(localAllreduceManyKernel<T, 1, false>));
+      touch(reinterpret_cast<const void*>(localAllreduceManyKernel<T, 2, false>));
+      touch(reinterpret_cast<const void*>(localAllreduceManyKernel<T, 4, false>));
+      touch(reinterpret_cast<const void*>(localAllreduceManyKernel<T, 1, true>));
+      touch(reinterpret_cast<const void*>(localAllreduceManyKernel<T, 2, true>));
+      touch(reinterpret_cast<const void*>(localAllreduceManyKernel<T, 4, true>));
       touch(reinterpret_cast<const void*>(verifyKernel<T>));
       touch(reinterpret_cast<const void*>(fillKernel<T>));
     });

@@ -235,6 +235,8 @@ void registerCuda(py::module_& root) {
   }, py::arg("pc"), py::arg("local"), py::arg("remote"), py::arg("remote_offset"), py::arg("bytes"), py::arg("peer"),
      py::arg("stream") = 0);
 
+  m.def("set_local_shape", [](int ctas, int unroll, bool tiled) { setLocalAllreduceShape(ctas, unroll, tiled); },
+        py::arg("ctas_per_sm"), py::arg("unroll"), py::arg("tiled") = false);
   m.def("local_ops_selftest", [](std::vector<int> devices, size_t count) {
     std::vector<SelfTestResult> res;
     {

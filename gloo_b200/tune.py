@@ -285,9 +285,9 @@ def main(argv=None):
                                                  blocks=b, unroll=u))
                 if kind == "sym" and cc.nvls_available() and nb >= (1 << 20) and P in (2, 4, 8) and args.focus == "nvls":
                     # blocks = all CTAs, unroll = CTAs of the multicast part, tile = per-mille done peer to peer
-                    for b in (64, 96, 148):
-                        for nb_mc in (16, 32):
-                            for pm in (100, 175, 250, 350):
+                    for b in (64, 96, 128, 148):
+                        for nb_mc in (8, 16, 24, 32):
+                            for pm in (100, 175, 250, 350, 500):
                                 cands.append(attempt("hybrid", lambda: cc.allreduce(t, algo="hybrid", stream=stream, blocks=b,
                                                                                     unroll=nb_mc, tile=pm), nb,
                                                      blocks=b, unroll=nb_mc, tile=pm))

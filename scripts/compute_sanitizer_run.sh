@@ -32,7 +32,7 @@ print("local ops:", len(res), "ok")
 PY
 rc=0
 for tool in memcheck racecheck synccheck; do
-  timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 --print-limit 20 \
+  timeout 900 compute-sanitizer --tool $tool --error-exitcode 9 --report-api-errors no --print-limit 20 \
     env PYTHONPATH=$PWD python /tmp/glb_sanitize_target.py > "$out/sanitizer_$tool.log" 2>&1
   r=$?
   echo "compute-sanitizer $tool rc=$r" | tee -a "$out/sanitizer_summary.txt"

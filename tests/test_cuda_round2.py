@@ -436,6 +436,28 @@ def test_relay_broadcast(size, monkeypatch):
         os.environ.pop("GLB_CUDA_BCAST_TILE", None)
 
 
+def test_local_allreduce_many_launch_shapes():
+    """Every launch shape of the single-rank fused step gives the same result (odd count: vector body + tail)."""
+    cu = gb._C.cuda
+    n = 1_000_003
+    want = None
+    try:
+        for tiled in (False, True):
+            for ctas in (1, 4, 8):
+                for unroll in (1, 2, 4):
+                    cu.set_local_shape(ctas, unroll, tiled)
+                    ts = [torch.arange(n, dtype=torch.float32, device="cuda") * (i + 1) for i in range(3)]
+                    cu.local_allreduce_many([t.data_ptr() for t in ts], n, int(gb.DataType.FLOAT32), 1, 0.25,
+                                            torch.cuda.current_stream().cuda_stream)
+                    _sync()
+                    if want is None:
+                        want = (torch.arange(n, dtype=torch.float64) * 6 * 0.25).float()
+                    for t in ts:
+                        torch.testing.assert_close(t.cpu(), want, rtol=1e-6, atol=0)
+    finally:
+        cu.set_local_shape(4, 2, False)
+
+
 # ---- ordering across streams, literal pipelined schedule ------------------------------------------------------------
 
 def test_collectives_on_two_streams_are_ordered():

@@ -455,7 +455,7 @@ def test_local_allreduce_many_launch_shapes():
                     for t in ts:
                         torch.testing.assert_close(t.cpu(), want, rtol=1e-6, atol=0)
     finally:
-        cu.set_local_shape(4, 2, False)
+        cu.set_local_shape(4, 1, False)
 
 
 # ---- ordering across streams, literal pipelined schedule ------------------------------------------------------------

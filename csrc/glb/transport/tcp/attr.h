@@ -25,8 +25,11 @@ struct attr {
   struct sockaddr_storage ai_addr {};
   socklen_t ai_addrlen = 0;
 
-  // Number of epoll threads; pairs are sharded across them round-robin.
+  // Number of event-loop threads; pairs are sharded across them round-robin.
   int numLoops = 1;
+  // Readiness backend of the loops: epoll (Linux) or the portable poll(2) reactor that
+  // the "uv" device uses (the role libuv plays in the reference: any POSIX system).
+  bool portableLoop = false;
 };
 
 }  // namespace tcp

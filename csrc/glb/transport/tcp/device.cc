@@ -165,7 +165,7 @@ Device::Device(const struct attr& attr, bool lazy) : attr_(attr), lazy_(lazy) {
   int nloops = attr.numLoops > 0 ? attr.numLoops : 1;
   long envLoops = envInt("TCP_LOOPS", 0);
   if (envLoops > 0) nloops = static_cast<int>(envLoops);
-  for (int i = 0; i < nloops; i++) loops_.emplace_back(new Loop());
+  for (int i = 0; i < nloops; i++) loops_.emplace_back(new Loop(attr.portableLoop ? Loop::Backend::POLL : Loop::Backend::EPOLL));
 
   listener_ = Socket::createForFamily(attr_.ai_family);
   listener_.setReuseAddr(true);

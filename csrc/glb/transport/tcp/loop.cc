@@ -1,5 +1,6 @@
 #include "glb/transport/tcp/loop.h"
 
+#include <fcntl.h>
 #include <sys/eventfd.h>
 #include <unistd.h>
 
@@ -13,7 +14,26 @@ namespace glb {
 namespace transport {
 namespace tcp {
 
-Loop::Loop() {
+// The handlers speak epoll's event bits; poll(2) uses the same values on Linux.
+static_assert(EPOLLIN == POLLIN && EPOLLOUT == POLLOUT && EPOLLERR == POLLERR && EPOLLHUP == POLLHUP,
+              "event bits of epoll and poll differ");
+
+Loop::Loop(Backend backend) : backend_(backend) {
+  if (backend_ == Backend::POLL) {
+    int p[2];
+    GLB_ENFORCE_NE(::pipe(p), -1, "pipe: ", std::strerror(errno));
+    for (int fd : p) {
+      ::fcntl(fd, F_SETFL, ::fcntl(fd, F_GETFL) | O_NONBLOCK);
+      ::fcntl(fd, F_SETFD, FD_CLOEXEC);
+    }
+    wakefd_ = p[0];
+    wakeWr_ = p[1];
+    fds_.push_back({wakefd_, POLLIN, 0});
+    handlers_.push_back(nullptr);  // nullptr marks the wake descriptor
+    thread_ = std::thread(&Loop::run, this);
+    threadId_ = thread_.get_id();
+    return;
+  }
   epfd_ = epoll_create1(EPOLL_CLOEXEC);
   GLB_ENFORCE_NE(epfd_, -1, "epoll_create1: ", std::strerror(errno));
   wakefd_ = eventfd(0, EFD_NONBLOCK | EFD_CLOEXEC);
@@ -32,16 +52,39 @@ Loop::~Loop() {
   wake();
   if (thread_.joinable()) thread_.join();
   ::close(wakefd_);
-  ::close(epfd_);
+  if (wakeWr_ != -1) ::close(wakeWr_);
+  if (epfd_ != -1) ::close(epfd_);
 }
 
 void Loop::wake() {
+  if (backend_ == Backend::POLL) {
+    char c = 1;
+    ssize_t rv = ::write(wakeWr_, &c, 1);  // a full pipe already guarantees a wake-up
+    (void)rv;
+    return;
+  }
   uint64_t one = 1;
   ssize_t rv = ::write(wakefd_, &one, sizeof(one));
   (void)rv;
 }
 
 void Loop::registerDescriptor(int fd, int events, Handler* h) {
+  if (backend_ == Backend::POLL) {
+    {
+      std::lock_guard<std::mutex> g(fdsMu_);
+      size_t i = 0;
+      while (i < fds_.size() && fds_[i].fd != fd) i++;
+      if (i == fds_.size()) {
+        fds_.push_back({fd, static_cast<short>(events), 0});
+        handlers_.push_back(h);
+      } else {
+        fds_[i].events = static_cast<short>(events);
+        handlers_[i] = h;
+      }
+    }
+    if (!inLoopThread()) wake();
+    return;
+  }
   struct epoll_event ev;
   std::memset(&ev, 0, sizeof(ev));
   ev.events = static_cast<uint32_t>(events);
@@ -52,6 +95,10 @@ void Loop::registerDescriptor(int fd, int events, Handler* h) {
 }
 
 void Loop::modifyDescriptor(int fd, int events, Handler* h) {
+  if (backend_ == Backend::POLL) {
+    registerDescriptor(fd, events, h);
+    return;
+  }
   struct epoll_event ev;
   std::memset(&ev, 0, sizeof(ev));
   ev.events = static_cast<uint32_t>(events);
@@ -60,10 +107,7 @@ void Loop::modifyDescriptor(int fd, int events, Handler* h) {
 }
 
 void Loop::unregisterDescriptor(int fd, Handler* h) {
-  int rv = epoll_ctl(epfd_, EPOLL_CTL_DEL, fd, nullptr);
-  if (rv == -1 && errno != ENOENT && errno != EBADF) {
-    GLB_WARN("epoll_ctl(DEL): ", std::strerror(errno));
-  }
+  removeDescriptor(fd);
   if (inLoopThread()) {
     // Drop events for this handler that are still queued in the current batch.
     for (int i = batchPos_ + 1; i < batchSize_; i++) {
@@ -79,6 +123,17 @@ void Loop::unregisterDescriptor(int fd, Handler* h) {
 }
 
 void Loop::removeDescriptor(int fd) {
+  if (backend_ == Backend::POLL) {
+    std::lock_guard<std::mutex> g(fdsMu_);
+    for (size_t i = 1; i < fds_.size(); i++) {
+      if (fds_[i].fd == fd) {
+        fds_.erase(fds_.begin() + static_cast<long>(i));
+        handlers_.erase(handlers_.begin() + static_cast<long>(i));
+        break;
+      }
+    }
+    return;  // the loop thread works on a snapshot; callers that destroy the handler wait for a tick
+  }
   int rv = epoll_ctl(epfd_, EPOLL_CTL_DEL, fd, nullptr);
   if (rv == -1 && errno != ENOENT && errno != EBADF) {
     GLB_WARN("epoll_ctl(DEL): ", std::strerror(errno));
@@ -101,13 +156,48 @@ void Loop::defer(std::function<void()> fn) {
   wake();
 }
 
+int Loop::waitBatch() {
+  if (backend_ == Backend::EPOLL) return epoll_wait(epfd_, batch_, kBatch, 50);
+  {
+    std::lock_guard<std::mutex> g(fdsMu_);
+    snapFds_ = fds_;
+    snapHandlers_ = handlers_;
+  }
+  for (auto& p : snapFds_) p.revents = 0;
+  const int ready = ::poll(snapFds_.data(), static_cast<nfds_t>(snapFds_.size()), 50);
+  if (ready <= 0) return ready;
+  // Same batch format as epoll_wait. A handler whose descriptor was removed after the
+  // snapshot must not run: check it is still registered (the set is small).
+  int n = 0;
+  const size_t total = snapFds_.size();
+  const size_t start = pollCursor_++ % total;
+  for (size_t k = 0; k < total && n < kBatch; k++) {
+    const size_t i = (start + k) % total;
+    if (snapFds_[i].revents == 0) continue;
+    if (snapFds_[i].revents & POLLNVAL) {  // closed without being removed: epoll forgets such descriptors by itself
+      removeDescriptor(snapFds_[i].fd);
+      continue;
+    }
+    if (snapHandlers_[i] != nullptr) {
+      std::lock_guard<std::mutex> g(fdsMu_);
+      bool live = false;
+      for (size_t j = 1; j < fds_.size(); j++) live = live || (fds_[j].fd == snapFds_[i].fd && handlers_[j] == snapHandlers_[i]);
+      if (!live) continue;
+    }
+    batch_[n].events = static_cast<uint32_t>(snapFds_[i].revents);
+    batch_[n].data.ptr = snapHandlers_[i];
+    n++;
+  }
+  return n;
+}
+
 void Loop::run() {
   setThreadName("glb_tcp_loop");
   while (!done_.load()) {
-    int n = epoll_wait(epfd_, batch_, kBatch, 50);
+    int n = waitBatch();
     if (n == -1) {
       if (errno == EINTR) continue;
-      GLB_ERROR("epoll_wait: ", std::strerror(errno));
+      GLB_ERROR(backend_ == Backend::EPOLL ? "epoll_wait: " : "poll: ", std::strerror(errno));
       break;
     }
     batchSize_ = n;

@@ -1,4 +1,6 @@
-// epoll event loop running on its own thread ("glb_tcp_loop"). Handlers are raw
+// Event loop running on its own thread ("glb_tcp_loop"). Two readiness backends behind the
+// same interface: epoll (default) and a portable poll(2) reactor (pipe wake-up, no
+// Linux-only calls) that the "uv" device selects. Handlers are raw
 // pointers; unregisterDescriptor() guarantees that, once it returns, the handler
 // is not executing and will not be invoked again, so the caller may destroy it.
 // `defer` runs a closure on the loop thread (woken through an eventfd).
@@ -6,6 +8,7 @@
 // unregister-waits-for-tick rule).
 #pragma once
 
+#include <poll.h>
 #include <sys/epoll.h>
 
 #include <atomic>
@@ -29,8 +32,10 @@ class Handler {
 
 class Loop final {
  public:
-  Loop();
+  enum class Backend { EPOLL, POLL };
+  explicit Loop(Backend backend = Backend::EPOLL);
   ~Loop();
+  Backend backend() const { return backend_; }
   Loop(const Loop&) = delete;
   Loop& operator=(const Loop&) = delete;
 
@@ -52,8 +57,20 @@ class Loop final {
   void run();
   void wake();
 
+  int waitBatch();  // fills batch_, returns the number of entries or -1
+
+  const Backend backend_;
   int epfd_ = -1;
-  int wakefd_ = -1;
+  int wakefd_ = -1;   // eventfd (epoll) or the read end of the wake pipe (poll)
+  int wakeWr_ = -1;   // write end of the wake pipe (poll backend)
+  // poll backend: the interest set, edited under fdsMu_ from any thread; the loop thread
+  // polls a snapshot and is woken after every edit.
+  std::mutex fdsMu_;
+  std::vector<struct pollfd> fds_;
+  std::vector<Handler*> handlers_;
+  std::vector<struct pollfd> snapFds_;
+  std::vector<Handler*> snapHandlers_;
+  size_t pollCursor_ = 0;  // rotate the start so that a busy descriptor cannot starve the others
   std::atomic<bool> done_{false};
   std::thread thread_;
   std::thread::id threadId_;

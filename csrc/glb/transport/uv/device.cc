@@ -8,7 +8,10 @@ namespace transport {
 namespace uv {
 
 namespace {
-// Same device, different label, so logs and Device::str() show what the caller asked for.
+// The "uv" device is the socket transport on the PORTABLE reactor: tcp::Loop with its poll(2)
+// backend (pipe wake-up, no epoll / eventfd) - the role libuv plays in the reference
+// (gloo/transport/uv/*: an event loop that exists on every platform). Pairs, buffers and the
+// wire protocol are the tcp transport's, so a "uv" rank and a "tcp" rank interoperate.
 class Device : public ::glb::transport::Device {
  public:
   explicit Device(std::shared_ptr<::glb::transport::Device> inner) : inner_(std::move(inner)) {}
@@ -30,6 +33,7 @@ std::shared_ptr<::glb::transport::Device> CreateDevice(const struct attr& a) {
   t.hostname = a.hostname;
   t.iface = a.iface;
   t.ai_family = a.ai_family;
+  t.portableLoop = true;
   return std::make_shared<Device>(tcp::CreateDevice(t));
 }
 

@@ -1,4 +1,4 @@
-"""Transport names a reference user may ask for besides tcp: uv (alias of the epoll transport),
+"""Transport names a reference user may ask for besides tcp: uv (the socket transport on the portable poll(2) reactor),
 ibverbs (probe + precise error), MPI bootstrap (run against a thread-world MPI), and the
 benchmark CLI's --transport switch (reference: gloo/benchmark/options.cc:149-180)."""
 import os
@@ -39,6 +39,48 @@ def test_uv_device_runs_new_style_collectives():
     [t.start() for t in ths]
     [t.join(60) for t in ths]
     assert out == [(6.0, [0, 1, 2])] * 3
+
+
+def test_uv_poll_reactor_interoperates_with_tcp_and_survives_churn():
+    """Ranks on the poll(2) reactor and ranks on epoll in one job (same wire protocol); large payloads,
+    point to point, then contexts torn down and rebuilt several times on the same devices (descriptor
+    removal while the loop thread is polling a snapshot)."""
+    import threading
+
+    size = 4
+    devs = [_C.create_uv_device("127.0.0.1") if r % 2 == 0 else gb.create_device("127.0.0.1") for r in range(size)]
+    errors = []
+    for round_ in range(3):
+        store = gb.HashStore()
+        out = [None] * size
+
+        def rank(r):
+            try:
+                ctx = gb.Context(r, size)
+                ctx.connect_full_mesh(store, devs[r])
+                for n in (1, 1000, 3_000_001):
+                    x = np.arange(n, dtype=np.float32) + r
+                    gb.allreduce(ctx, x)
+                    np.testing.assert_allclose(x[[0, -1]], (np.arange(n, dtype=np.float64)[[0, -1]] * size + 6))
+                a = np.full(70_000, float(r), np.float64)
+                b = np.zeros_like(a)
+                right, left = (r + 1) % size, (r - 1) % size
+                ub_s, ub_r = ctx.create_unbound_buffer(a.ctypes.data, a.nbytes), ctx.create_unbound_buffer(b.ctypes.data, b.nbytes)
+                ub_r.recv(left, 7)
+                ub_s.send(right, 7)
+                ub_r.wait_recv()
+                ub_s.wait_send()
+                assert b[0] == left and b[-1] == left
+                gb.barrier(ctx)
+                ctx.close_connections()
+                out[r] = True
+            except Exception as e:  # noqa: BLE001
+                errors.append((round_, r, repr(e)))
+
+        ths = [threading.Thread(target=rank, args=(r,)) for r in range(size)]
+        [t.start() for t in ths]
+        [t.join(120) for t in ths]
+        assert not errors and out == [True] * size, (errors, out)
 
 
 def _build_fake_ibverbs():

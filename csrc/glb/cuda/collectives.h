@@ -55,7 +55,7 @@ struct Tuning {
   int copyBlocks = 296;                 // CTAs for the store-only kernels (40 regs: 2-3 CTAs per SM)
   int alltoallvBlocks = 64;             // fixed grid of the v-variant (sizes are rank-local, the grid must not be)
   size_t bcastDirectMaxBytes = 256 * 1024;  // <= : root pushes everything itself
-  size_t bcastRelayMinBytes = 8u << 20;     // >= : chunk-pipelined relay broadcast (P > 2)
+  size_t bcastRelayMinBytes = 64u << 20;    // >= : chunk-pipelined relay broadcast (P > 2; measured cross-over 32-256 MB)
   int pipeTile = 1024;                  // 16-byte groups per tile of the pipelined kernel (power of two)
   int pipeExchangeThreads = 256;        // threads of each CTA that drive NVLink in the pipelined kernel
   bool tmaCopies = false;               // put / get / large allgather through cp.async.bulk (TMA) instead of LDG/STG

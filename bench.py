@@ -217,6 +217,8 @@ def run_ours(args):
                             algos.append("two_shot")
                         if kind == "sym" and cc.nvls_available():
                             algos.append("nvls")
+                            if world in (2, 4, 8) and n > 1000:
+                                algos.append("hybrid")
                         if kind == "user" and n > 1000:
                             algos.append("pipelined")
                         if n * 4 <= 32768:
@@ -266,7 +268,24 @@ def run_ours(args):
             nxt, prv = (rank + 1) % world, (rank - 1) % world
             s_t, r_t = torch.full((3_000_001,), float(rank), device=dev), torch.zeros(3_000_001, device=dev)
             cc.sendrecv(s_t, nxt, r_t, prv, stream=stream)
+            # zero-copy exchange between two symmetric buffers; relay broadcast (forced: the table only picks it from 64 MB)
+            xa, xb = cc.empty(3_000_001, torch.float32), cc.empty(3_000_001, torch.float32)
+            xa.fill_(float(rank))
+            xb.zero_()
+        sync_all()
+        with torch.cuda.stream(stream):
+            cc.exchange(xa, nxt, xb, prv, stream=stream)
+            rb = cc.empty(5_000_001, torch.float32)
+            fill(rb, rank, 1.0)
+            if world > 2:
+                os.environ["GLB_CUDA_BCAST_MODE"] = "3"
+            cc.broadcast(rb, root=1 % world, stream=stream)
+            os.environ.pop("GLB_CUDA_BCAST_MODE", None)
         stream.synchronize()
+        assert float(xb[0]) == prv and float(xb[-1]) == prv and float(xb[1_500_000]) == prv, "exchange"
+        verify_full(rb, 1 % world, 1.0, 0.0, 0.0, "relay broadcast")
+        verified["exchange"] = True
+        verified["broadcast_relay" if world > 2 else "broadcast_root1"] = True
         exp_g = torch.arange(world, device=dev).repeat_interleave(per).float()
         assert torch.equal(out, exp_g), "allgather"
         assert torch.equal(a_out, torch.cat([torch.full((per,), float(j * 100 + rank), device=dev) for j in range(world)])), "alltoall"
@@ -277,7 +296,7 @@ def run_ours(args):
         for k in ("allgather", "alltoall", "alltoallv", "reduce_scatter", "broadcast", "sendrecv"):
             verified[k] = True
         cc.check_health()
-        del a32, o16, out, a_in, a_out, v_in, v_out, rs_in, rs_out, bc, s_t, r_t
+        del a32, o16, out, a_in, a_out, v_in, v_out, rs_in, rs_out, bc, s_t, r_t, xa, xb, rb
         sync_all()
 
     def make(elements, symmetric=True, dtype=torch.float32, cls=None, literal=False):

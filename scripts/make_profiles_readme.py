@@ -1,0 +1,153 @@
+#!/usr/bin/env python
+"""Rebuild profiles/README.md from the evidence files under profiles/r2 (bench JSON lines, sweeps)."""
+import json
+import os
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+R2 = os.path.join(ROOT, "profiles", "r2")
+
+
+def bench(name):
+    p = os.path.join(R2, name)
+    if not os.path.exists(p):
+        return None
+    for line in open(p):
+        if line.startswith('{"metric"') or line.startswith('{"impl"'):
+            try:
+                return json.loads(line)
+            except ValueError:
+                pass
+    return None
+
+
+def load(name):
+    p = os.path.join(R2, name)
+    return json.load(open(p)) if os.path.exists(p) else None
+
+
+out = []
+w = out.append
+w("# Measurements and profiles (round 2)\n")
+w("Everything here was produced on B200 boxes through `gpurun`; the raw files are under `profiles/r2/` (bench JSON lines, tuner")
+w("measurements, NVLink counters, Nsight Compute raw page, sanitizer summary), SASS listings under `profiles/sass_*.txt`")
+w("(`sass_summary.md`), the Nsight Compute summary in `ncu_r2_summary.md`. Timing: CUDA events on the launching stream, max over")
+w("ranks, L2 flushed between latency iterations (256 MB write) or inputs larger than L2. Round-1 material: `profiles/runs/`.\n")
+
+# ---- headline ------------------------------------------------------------------------------------------------------
+w("## Headline: `bench.py`, allreduce of 1e8 fp32 (400 MB) per GPU, bus bandwidth\n")
+w("| GPUs | ms/step | bus GB/s per GPU | kernel (launch shape from the tuning table) | wire GB/s per dir / measured put rate | NCCL 2.28.9 plain / registered | unregistered `T*` (pipelined) | e2e ms (H2D + allreduce + D2H) |")
+w("|---|---|---|---|---|---|---|---|")
+for n, f in ((1, "bench_1gpu_ours.log"), (2, "bench_2gpu_ours.log"), (4, "bench_4gpu_ours.log"), (8, "bench_8gpu_ours.log")):
+    d = bench(f)
+    if not d:
+        continue
+    ls = d["config"].get("launch_shape") or {}
+    shape = f"`{d['config']['kernel_variant']}` {ls.get('blocks', '')}x{ls.get('unroll', '')}" if ls else f"`{d['config']['kernel_variant']}`"
+    rf = d.get("roofline", {})
+    wire = f"{rf.get('wire_gbs_per_dir', '-')} / {rf.get('nvlink_gbs_per_dir_measured_here', '-')} = {rf.get('frac_of_measured_here', '-')}" if n > 1 else \
+        f"HBM {round(rf.get('hbm_bytes_per_step', 0) / (d['ms_per_step'] * 1e-3) / 1e9)} GB/s = {rf.get('frac_of_measured_hbm')} of measured copy"
+    nc = d.get("nccl_comparator") or {}
+    nccl = f"{nc.get('busbw_gbs', '-')} / {(nc.get('registered') or {}).get('busbw_gbs', '-')}" if nc else "-"
+    up = d.get("unregistered_pointer") or {}
+    w(f"| {n} | {d['ms_per_step']:.4f} | {d['per_gpu_gbs']} | {shape} | {wire} | {nccl} | {up.get('busbw_gbs', '-')} | {d['e2e']['ms_per_step']} |")
+w("")
+w("Reference arm (`bench.py --impl reference`, unmodified pytorch/gloo `benchmark_cuda` + `baseline/ref_e2e.cc`): "
+  + "; ".join(f"N={n}: {b.get('ms_per_step', b.get('unavailable'))} ms/step, e2e {b.get('e2e', {}).get('ms_per_step', '-')} ms"
+              for n, b in ((1, bench("bench_1gpu_reference.log")), (2, bench("bench_2gpu_reference.log"))) if b) + ".\n")
+w("What bounds the NVLS rows: the focused re-tune (`tune_P8_nvls_focus_measurements.json`) shows 8-96 CTAs all within 2 % at 400 MB")
+w("(846-866 us) and the NVLS + P2P hybrid SLOWER than pure NVLS at every split (best 907 us with 10 % peer to peer): the limit is the")
+w("switch's multimem path, not SM-side issue rate and not spare link capacity. NCCL's own NVLS path is at 688-693 GB/s on the same box.\n")
+
+# ---- small messages -------------------------------------------------------------------------------------------------
+w("## Small messages (flag-in-data LL kernel), p50 us: per-call events | inside a CUDA graph (32 ops per replay)\n")
+w("| GPUs | 4 B ours / NCCL | 4 KB ours / NCCL | 40 KB ours / NCCL | graph 4 B ours / NCCL | graph 1 KB | graph 16 KB |")
+w("|---|---|---|---|---|---|---|")
+for n, f in ((2, "bench_2gpu_ours_quick.log"), (4, "bench_4gpu_ours.log"), (8, "bench_8gpu_ours.log")):
+    d = bench(f)
+    if not d:
+        continue
+    sw = {r["bytes"]: r for r in d["sweep"]}
+    g = {r["bytes"]: r for r in d.get("graph_small_allreduce", [])}
+
+    def cell(b):
+        r = sw.get(b)
+        return f"{r['p50_us']} / {r.get('nccl_p50_us', '-')}" if r else "-"
+
+    def gcell(b):
+        r = g.get(b)
+        return f"{r.get('p50_us_per_op', '-')} / {r.get('nccl_p50_us_per_op', '-')}" if r else "-"
+    w(f"| {n} | {cell(4)} | {cell(4000)} | {cell(40000)} | {gcell(4)} | {gcell(1024)} | {gcell(16384)} |")
+w("")
+
+# ---- BASELINE configs 3-5 at 8 GPUs -----------------------------------------------------------------------------------
+d8 = bench("bench_8gpu_ours.log")
+if d8:
+    w("## BASELINE configs 3-5 at 8 GPUs (from the same bench line: `configs`)\n")
+    for key in ("cuda_allreduce_halving_doubling_fp16", "cuda_allreduce_bcube_fp16"):
+        w(f"`{key}` (fp16): elements: auto variant ms | literal schedule ms | NCCL ms -> " + "; ".join(
+            f"{r['elements']:.0e}: {r['auto']['ms']} ({r['auto']['variant']}) | {r['literal']['ms']} | {r.get('nccl', {}).get('ms', '-')}"
+            for r in d8["configs"].get(key, [])) + "\n")
+    w("| collective | bytes | ours p50 us | ours bus GB/s | NCCL p50 us | NCCL bus GB/s |")
+    w("|---|---|---|---|---|---|")
+    for key in ("allgather", "alltoall", "alltoall_v", "reduce_scatter", "cuda_broadcast_one_to_all"):
+        for r in d8["configs"].get(key, []):
+            if r["bytes"] < 60000 and r["bytes"] > 2000:
+                continue
+            w(f"| {key} | {r['bytes']} | {r['p50_us']} | {r['busbw_gbs']} | {r.get('nccl_p50_us', '-')} | {r.get('nccl_busbw_gbs', '-')} |")
+    w("")
+
+# ---- broadcast variants -------------------------------------------------------------------------------------------------
+for P in (8, 4):
+    b = load(f"broadcast_P{P}.json")
+    if not b:
+        continue
+    w(f"## Broadcast variants, {P} GPUs, symmetric buffer (GB/s = bytes / time; `scripts/bench_broadcast.py`)\n")
+    w("| bytes | direct | scatter+allgather | multimem.st | relay (auto tile) | relay tile 1024 | relay tile 4096 | auto (table) | NCCL |")
+    w("|---|---|---|---|---|---|---|---|---|")
+    for r in b["rows"]:
+        w(f"| {r['bytes']} | {r.get('direct_gbs', '-')} | {r.get('scatter_allgather_gbs', '-')} | {r.get('multimem_st_gbs', '-')} | {r.get('relay_gbs', '-')} | "
+          f"{r.get('relay_tile1024_gbs', '-')} | {r.get('relay_tile4096_gbs', '-')} | {r.get('auto_gbs', '-')} | {r.get('nccl_gbs', '-')} |")
+    w("")
+w("(`auto` in these runs still used the pre-measurement threshold of 8 MB for the relay; the table now switches at 64 MB.)\n")
+
+# ---- long context ---------------------------------------------------------------------------------------------------------
+w("## Long-context micro-benchmarks (`scripts/bench_longcontext.py`; K+V block bf16, 32 heads x 128)\n")
+w("| GPUs | global seq | block MB | ring rotate, mailbox `sendrecv` GB/s | ring rotate, zero-copy `exchange` GB/s | NCCL send/recv GB/s | Ulysses alltoall bus GB/s (ours us / NCCL us) |")
+w("|---|---|---|---|---|---|---|")
+for n, f in ((2, "longcontext_2gpu.json"), (4, "longcontext_4gpu.json"), (8, "longcontext_8gpu.json")):
+    b = load(f)
+    if not b:
+        continue
+    for r in b["rows"]:
+        w(f"| {n} | {r['seq']} | {r['kv_block_bytes'] >> 20} | {r['ring_rotate_gbs_per_dir']} | {r.get('ring_rotate_symmetric_gbs_per_dir', '-')} | "
+          f"{r.get('nccl_ring_rotate_gbs_per_dir', '-')} | {r['ulysses_busbw_gbs']} ({r['ulysses_alltoall_us']} / {r.get('nccl_ulysses_alltoall_us', '-')}) |")
+w("")
+
+# ---- NVLink counters ---------------------------------------------------------------------------------------------------------
+b = load("nvlink_counters_8gpu.json")
+if b:
+    w("## NVLink byte counters on the real 8-GPU path (`nvidia-smi nvlink -gt d` around 20 steps; `scripts/nvlink_evidence.py`)\n")
+    w("| variant | ms/step | algorithmic bytes per GPU per direction | measured tx | measured rx | measured / algorithmic | wire GB/s |")
+    w("|---|---|---|---|---|---|---|")
+    for r in b["rows"]:
+        w(f"| {r['variant']} | {r['ms_per_step']} | {r['algorithmic_tx_bytes_per_step']} | {r.get('measured_tx_bytes_per_step', '-')} | "
+          f"{r.get('measured_rx_bytes_per_step', '-')} | {r.get('tx_over_algorithmic', '-')} | {r.get('wire_gbs_tx', '-')} |")
+    w("\nNVLS moves S(1 + 1/P) per direction (the switch reduces), two-shot 2S(P-1)/P: the counters match the model to 4 digits,")
+    w("i.e. nothing is sent twice and the kernels' traffic really is NVLink traffic.\n")
+
+# ---- local ----------------------------------------------------------------------------------------------------------------------
+b = load("local_shapes.json")
+if b:
+    best = b["best"]
+    w("## N=1 fused step (`localAllreduceManyKernel`), launch-shape sweep on 2 x 400 MB\n")
+    w(f"best {best['ms']} ms = {best['hbm_gbs']} GB/s HBM ({best['ctas_per_sm']} CTAs/SM x {best['unroll']} pack, tiled={best['tiled']}); "
+      "range over the 24 shapes: " + f"{min(r['ms'] for r in b['rows'])}-{max(r['ms'] for r in b['rows'])} ms. Nsight Compute: `ncu_r2_summary.md`.\n")
+
+w("## Other evidence\n")
+w("* `r2/pytest_*`: GPU test logs (1, 2, 4, 8 GPUs: multi-process collectives, fault injection with SIGKILL / SIGSTOP, process-group backend).")
+w("* `r2/compute_sanitizer_summary.txt`: memcheck / racecheck / synccheck over the loop-back self-tests: 0 kernel errors (the one memcheck line is the")
+w("  expected `cuMulticastCreate` refusal of a one-device multicast object, handled as a skip).")
+w("* `r2/smoke_ncu_launches_1gpu.csv`: the kernels `smoke()` launches, captured under Nsight Compute (the driver's kernel-name proof).")
+w("* `r2/tune_*_measurements.json`: every tuner measurement behind `gloo_b200/tuning/b200.tune`.")
+open(os.path.join(ROOT, "profiles", "README.md"), "w").write("\n".join(out) + "\n")
+print("wrote", len(out), "lines")

@@ -100,7 +100,10 @@ void appendHypercube(Schedule& s, int rank, const std::vector<int>& factors, Ran
 }
 }  // namespace
 
-Schedule buildHalvingDoublingSchedule(int rank, int size, size_t count, size_t packElems) {
+namespace {
+// Non-power-of-two P, the simple way: the P - 2^k surplus ranks fold their vector onto a
+// partner first and pull the result back afterwards (GLB_HD_FOLD=1).
+Schedule buildHalvingDoublingFoldSchedule(int rank, int size, size_t count, size_t packElems) {
   Schedule s;
   s.name = "halving_doubling";
   const Range all{0, count};
@@ -133,6 +136,102 @@ Schedule buildHalvingDoublingSchedule(int rank, int size, size_t count, size_t p
       s.steps.push_back(makeStep(SCHED_COPY, none, {}));
     }
   }
+  return s;
+}
+
+// Non-power-of-two P, binary blocks (the reference's scheme, allreduce_halving_doubling.h:39-64
+// and cuda_allreduce_halving_doubling.cc; host version: glb/binary_blocks.h), as a pull table:
+//   1. halving reduce-scatter inside every block, all blocks at once (lg b0 steps; a smaller
+//      block idles through the steps it does not have);
+//   2. chain up, smallest block first: a rank of the larger block folds in its range from the
+//      rank of the smaller block that owns the enclosing range;
+//   3. chain down: a rank of the smaller block copies its range back piece by piece from the
+//      b_large / b_small ranks of the larger block that hold it (one barrier phase);
+//   4. doubling allgather inside every block (a smaller block's steps are the last ones).
+// Ranges nest because local rank l keeps half (l >> i) & 1 in step i: the first lg b' bits of
+// l give the range of local rank l mod b' in a block of b' ranks.
+Schedule buildHalvingDoublingBlocksSchedule(int rank, int size, size_t count, size_t packElems) {
+  Schedule s;
+  s.name = "halving_doubling";
+  const Range all{0, count}, none{0, 0};
+  std::vector<int> bsize, bbase;
+  int block = 0, me = 0;
+  for (int bit = 30, start = 0; bit >= 0; bit--) {
+    const int b = 1 << bit;
+    if (!(size & b)) continue;
+    if (rank >= start && rank < start + b) {
+      block = static_cast<int>(bsize.size());
+      me = rank - start;
+    }
+    bsize.push_back(b);
+    bbase.push_back(start);
+    start += b;
+  }
+  const int nb = static_cast<int>(bsize.size());
+  const int b = bsize[block], base = bbase[block];
+  const int S = static_cast<int>(log2ceil(static_cast<uint32_t>(bsize[0])));
+  auto rangeOf = [&](int bsz, int l) {
+    Range r = all;
+    for (int d = 1; d < bsz; d <<= 1) r = alignedPart(r, 2, (l & d) ? 1 : 0, packElems);
+    return r;
+  };
+  // 1. reduce-scatter
+  std::vector<Range> owned{all};
+  for (int i = 0; i < S; i++) {
+    const int d = 1 << i;
+    if (d < b) {
+      owned.push_back(alignedPart(owned.back(), 2, (me & d) ? 1 : 0, packElems));
+      s.steps.push_back(makeStep(SCHED_REDUCE, owned.back(), {base + (me ^ d)}));
+    } else {
+      s.steps.push_back(makeStep(SCHED_REDUCE, none, {}));
+    }
+  }
+  const Range mine = owned.back();
+  // 2. chain up
+  for (int j = 0; j + 1 < nb; j++) {
+    const int dst = nb - 2 - j, src = dst + 1;
+    if (block == dst) {
+      s.steps.push_back(makeStep(SCHED_REDUCE, mine, {bbase[src] + me % bsize[src]}));
+    } else {
+      s.steps.push_back(makeStep(SCHED_REDUCE, none, {}));
+    }
+  }
+  // 3. chain down (every rank emits the same number of table entries per phase)
+  for (int j = 0; j + 1 < nb; j++) {
+    const int src = j, dst = j + 1;
+    const int pieces = bsize[src] / bsize[dst];
+    for (int m = 0; m < pieces; m++) {
+      SchedStep st = block == dst ? makeStep(SCHED_COPY, rangeOf(bsize[src], me + m * b), {bbase[src] + me + m * b})
+                                  : makeStep(SCHED_COPY, none, {});
+      st.sync = m == 0 ? 1 : 0;
+      s.steps.push_back(st);
+    }
+  }
+  // 4. allgather
+  int level = static_cast<int>(owned.size()) - 1;
+  for (int i = S - 1; i >= 0; i--) {
+    const int d = 1 << i;
+    if (d < b) {
+      s.steps.push_back(makeStep(SCHED_COPY, alignedPart(owned[level - 1], 2, (me & d) ? 0 : 1, packElems), {base + (me ^ d)}));
+      level--;
+    } else {
+      s.steps.push_back(makeStep(SCHED_COPY, none, {}));
+    }
+  }
+  return s;
+}
+}  // namespace
+
+Schedule buildHalvingDoublingSchedule(int rank, int size, size_t count, size_t packElems) {
+  const int core = detail::largestPow2AtMost(size);
+  if (core != size) {
+    return envFlag("HD_FOLD", false) ? buildHalvingDoublingFoldSchedule(rank, size, count, packElems)
+                                     : buildHalvingDoublingBlocksSchedule(rank, size, count, packElems);
+  }
+  Schedule s;
+  s.name = "halving_doubling";
+  std::vector<int> factors(log2ceil(static_cast<uint32_t>(core)), 2);
+  appendHypercube(s, rank, factors, Range{0, count}, packElems);
   return s;
 }
 

@@ -162,7 +162,7 @@ def test_symmetric_tensor_and_barrier():
     assert all("PeerContext" in r for r in res)
 
 
-@pytest.mark.parametrize("size", [2, 3, 4, 8])
+@pytest.mark.parametrize("size", [2, 3, 4, 7, 8])
 def test_literal_schedules(size):
     """The named schedules executed literally over peer pointers (one kernel each)."""
     classes = [gcu.CudaAllreduceRing, gcu.CudaAllreduceRingChunked, gcu.CudaAllreduceHalvingDoubling,

@@ -482,7 +482,7 @@ def test_collectives_on_two_streams_are_ordered():
     assert all(gb.spawn_threads(size, fn, cuda_device=0))
 
 
-@pytest.mark.parametrize("size", [2, 3, 4, 8])
+@pytest.mark.parametrize("size", [2, 3, 4, 6, 8])
 def test_halving_doubling_pipelined_literal(size):
     def fn(ctx):
         for count in (1000, 300001):

@@ -71,7 +71,9 @@ def test_step_counts_match_cost_model():
     assert len(build("ring", 0, 8, 1 << 20, 2, 4)) == 8
     assert len(build("ring_chunked", 0, 8, 1 << 20, 2, 4)) == 14
     assert len(build("halving_doubling", 0, 8, 1 << 20, 2, 4)) == 6
-    assert len(build("halving_doubling", 0, 6, 1 << 20, 2, 4)) == 4 + 2  # fold in/out around 4 ranks
+    # P = 6 = 4 + 2 (binary blocks): 2 halving steps, 1 chain-up, 1 chain-down phase of 2 pieces, 2 doubling steps
+    six = build("halving_doubling", 0, 6, 1 << 20, 2, 4)
+    assert len(six) == 7 and sum(s["sync"] for s in six) == 6
 
 
 try:
@@ -155,3 +157,25 @@ def test_halving_doubling_pipelined_overlaps_chunks():
     assert simulate_phased("halving_doubling_pipelined", 8, 1 << 16, 2) == plain + 1
     steps = build("halving_doubling_pipelined", 0, 8, 1 << 16, 2, 4)
     assert len(steps) == 2 * plain and sum(s["sync"] for s in steps) == plain + 1
+
+
+# ---- halving-doubling on a rank count that is not a power of two: binary blocks vs folding --------
+
+@pytest.mark.parametrize("size", [3, 5, 6, 7, 9, 10, 11, 12, 13, 14, 15])
+def test_halving_doubling_binary_blocks(size, monkeypatch):
+    for count in (1, 5, 64, 1001, 70000):
+        phases = simulate_phased("halving_doubling", size, count)
+    tables = [build("halving_doubling", r, size, 70000, 2, 4) for r in range(size)]
+    blocks = [1 << i for i in range(5, -1, -1) if size & (1 << i)]
+    lg = blocks[0].bit_length() - 1
+    assert phases == 2 * lg + 2 * (len(blocks) - 1)
+    # nobody idles through the halving phase except ranks of blocks that have fewer steps, and the
+    # extra traffic of a small block is its own share: no step moves the whole vector unless a
+    # block of one rank has to end up with all of it
+    if blocks[-1] > 1:
+        assert max(st["len"] for t in tables for st in t) <= 70000 // 2 + 4
+    # the folding variant (GLB_HD_FOLD=1) is still there and moves the whole vector twice
+    monkeypatch.setenv("GLB_HD_FOLD", "1")
+    simulate("halving_doubling", size, 1001)
+    folded = build("halving_doubling", size - 1, size, 70000, 2, 4)
+    assert max(st["len"] for st in folded) == 70000

@@ -427,7 +427,7 @@ void registerTyped(std::map<std::string, BenchmarkFactory>& r, bool half) {
   add("cuda_allreduce_halving_doubling",
       [](auto c, const Options& o) { return cudaAllreduce<T>(c, o, cuda::AllreduceAlgo::HALVING_DOUBLING); });
   add("cuda_allreduce_halving_doubling_pipelined",
-      [](auto c, const Options& o) { return cudaAllreduce<T>(c, o, cuda::AllreduceAlgo::HALVING_DOUBLING); });
+      [](auto c, const Options& o) { return cudaAllreduce<T>(c, o, cuda::AllreduceAlgo::HALVING_DOUBLING_PIPELINED); });
   add("cuda_allreduce_bcube", [](auto c, const Options& o) { return cudaAllreduce<T>(c, o, cuda::AllreduceAlgo::BCUBE); });
   add("cuda_broadcast_one_to_all", [](auto c, const Options& o) {
     return cudaMove<T>(c, o, 1.0, 1, 1, [](cuda::PeerContext& pc, void*, const cuda::PeerBuffer& out, size_t n, cudaStream_t s) {
@@ -445,6 +445,24 @@ void registerTyped(std::map<std::string, BenchmarkFactory>& r, bool half) {
                        [](cuda::PeerContext& pc, void* in, const cuda::PeerBuffer& out, size_t n, cudaStream_t s) {
                          std::vector<size_t> b(pc.size, n * sizeof(T));
                          cuda::alltoallv(pc, in, b, out, 0, b, s);
+                       });
+  });
+  // Ring rotation (every rank sends n elements to rank+1 and receives from rank-1): through the
+  // mailbox ring into a plain pointer, and zero-copy into the symmetric buffer.
+  add("cuda_sendrecv", [](auto c, const Options& o) {
+    return cudaMove<T>(c, o, c->size > 1 ? 1.0 : 0.0, 1, 1,
+                       [](cuda::PeerContext& pc, void* in, const cuda::PeerBuffer& out, size_t n, cudaStream_t s) {
+                         if (pc.size == 1) return;
+                         cuda::sendrecv(pc, in, n * sizeof(T), (pc.rank + 1) % pc.size, out.local, n * sizeof(T),
+                                        (pc.rank + pc.size - 1) % pc.size, s);
+                       });
+  });
+  add("cuda_exchange", [](auto c, const Options& o) {
+    return cudaMove<T>(c, o, c->size > 1 ? 1.0 : 0.0, 1, 1,
+                       [](cuda::PeerContext& pc, void* in, const cuda::PeerBuffer& out, size_t n, cudaStream_t s) {
+                         if (pc.size == 1) return;
+                         cuda::exchange(pc, in, n * sizeof(T), (pc.rank + 1) % pc.size, out, 0, n * sizeof(T),
+                                        (pc.rank + pc.size - 1) % pc.size, s);
                        });
   });
   add("cuda_reduce_scatter", [](auto c, const Options& o) {

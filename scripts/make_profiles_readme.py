@@ -143,6 +143,35 @@ if b:
     w(f"best {best['ms']} ms = {best['hbm_gbs']} GB/s HBM ({best['ctas_per_sm']} CTAs/SM x {best['unroll']} pack, tiled={best['tiled']}); "
       "range over the 24 shapes: " + f"{min(r['ms'] for r in b['rows'])}-{max(r['ms'] for r in b['rows'])} ms. Nsight Compute: `ncu_r2_summary.md`.\n")
 
+# ---- host transport (CPU container) ------------------------------------------------------------------------------------------------
+def host_rows(name):
+    path = os.path.join(R2, name)
+    if not os.path.exists(path):
+        return None
+    cur, res = None, {}
+    for line in open(path):
+        if line.startswith("=="):
+            cur = "ref" if "_ref" in line else "ours"
+            res[cur] = {}
+        else:
+            f = line.split()
+            if cur and len(f) >= 5 and f[0].isdigit():
+                res[cur][int(f[1])] = float(f[3])  # elements -> p50 us
+    return res
+
+
+w("## Host buffers over TCP loopback (BASELINE config 1; this CPU container, 8 shared vCPUs; `scripts/host_compare.sh`)\n")
+w("| benchmark | elements | reference p50 us | gloo_b200 p50 us | speed-up |")
+w("|---|---|---|---|---|")
+for label, f in (("allreduce_ring, 2 ranks", "host_compare_allreduce_ring_P2.txt"), ("allreduce_halving_doubling, 4 ranks", "host_compare_allreduce_hd_P4.txt")):
+    hr = host_rows(f)
+    if not hr or "ref" not in hr or "ours" not in hr:
+        continue
+    for n in (100, 1000, 100000, 1000000, 5000000):
+        if n in hr["ref"] and n in hr["ours"]:
+            w(f"| {label} | {n} | {hr['ref'][n]:.0f} | {hr['ours'][n]:.1f} | {hr['ref'][n] / hr['ours'][n]:.2f}x |")
+w("\nUnmodified reference `benchmark` binary against `glb_benchmark`, same flags, same box, back to back.\n")
+
 w("## Other evidence\n")
 w("* `r2/pytest_*`: GPU test logs (1, 2, 4, 8 GPUs: multi-process collectives, fault injection with SIGKILL / SIGSTOP, process-group backend).")
 w("* `r2/compute_sanitizer_summary.txt`: memcheck / racecheck / synccheck over the loop-back self-tests: 0 kernel errors (the one memcheck line is the")

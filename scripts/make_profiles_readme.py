@@ -54,6 +54,12 @@ w("")
 w("Reference arm (`bench.py --impl reference`, unmodified pytorch/gloo `benchmark_cuda` + `baseline/ref_e2e.cc`): "
   + "; ".join(f"N={n}: {b.get('ms_per_step', b.get('unavailable'))} ms/step, e2e {b.get('e2e', {}).get('ms_per_step', '-')} ms"
               for n, b in ((1, bench("bench_1gpu_reference.log")), (2, bench("bench_2gpu_reference.log"))) if b) + ".\n")
+w("Link-rate fraction of the peer-to-peer two-shot kernel (`plain_cudamalloc_buffers` / the N=2 headline; wire bytes 2S(P-1)/P per GPU and direction): "
+  + "; ".join(f"N={n}: {2 * (n - 1) / n * 400e6 / (b['plain_cudamalloc_buffers']['ms_per_step'] * 1e-3) / 1e9:.0f} GB/s = "
+              f"{2 * (n - 1) / n * 400e6 / (b['plain_cudamalloc_buffers']['ms_per_step'] * 1e-3) / 1e9 / b['roofline']['nvlink_gbs_per_dir_measured_here']:.3f} of the measured put rate"
+              for n, b in ((2, bench("bench_2gpu_ours.log")), (4, bench("bench_4gpu_ours.log")), (8, bench("bench_8gpu_ours.log")))
+              if b and b.get("plain_cudamalloc_buffers") and b["roofline"].get("nvlink_gbs_per_dir_measured_here"))
+  + ". At 4 and 8 GPUs the NVLS kernel is chosen anyway because it finishes sooner: it moves S(1+1/P) instead of 2S(P-1)/P.\n")
 w("What bounds the NVLS rows: the focused re-tune (`tune_P8_nvls_focus_measurements.json`) shows 8-96 CTAs all within 2 % at 400 MB")
 w("(846-866 us) and the NVLS + P2P hybrid SLOWER than pure NVLS at every split (best 907 us with 10 % peer to peer): the limit is the")
 w("switch's multimem path, not SM-side issue rate and not spare link capacity. NCCL's own NVLS path is at 688-693 GB/s on the same box.\n")

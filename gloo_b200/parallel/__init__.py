@@ -4,6 +4,7 @@ The reference implements none of these (it is the substrate they call); each hel
 here is a thin, explicit mapping from a strategy to the collective it consumes:
 
   DataParallel        gradient allreduce in size-capped buckets (+ broadcast of params)
+  GradientBucketer    gradients live in symmetric buckets (views), allreduce overlapped with backward
   ZeroShard           ZeRO/FSDP: reduce_scatter gradients, allgather parameters
   TensorParallel      Megatron column/row-parallel linear: allgather / allreduce
   SequenceParallel    Megatron-SP: reduce_scatter + allgather along the sequence
@@ -16,6 +17,7 @@ Everything accepts either a CUDA ``CudaContext`` (NVLink kernels) or a host cont
 """
 from .strategies import (  # noqa: F401
     DataParallel,
+    GradientBucketer,
     MoEDispatcher,
     RingExchange,
     SequenceParallel,

@@ -96,6 +96,132 @@ class DataParallel(_Base):
                 off += g.numel()
 
 
+class GradientBucketer(_Base):
+    """Gradient synchronisation that overlaps with the backward pass, without copies.
+
+    Parameters are packed, in reverse order (the last layers finish their backward first), into
+    flat buckets of at most ``bucket_bytes``. On CUDA a bucket is SYMMETRIC memory
+    (``CudaContext.empty``: peer-mapped and, beyond two GPUs, bound to an NVSwitch multicast
+    object) and every ``p.grad`` is a VIEW into its bucket, so autograd accumulates straight into
+    the buffer the collective reads: no flatten / unflatten pass, and the allreduce is the zero-copy
+    fused kernel (1/P average in its epilogue). A bucket is launched on a side stream as soon as
+    the last of its gradients has been accumulated (``register_post_accumulate_grad_hook``), in
+    bucket order on every rank; ``finish()`` makes the compute stream wait for the results.
+    The reference has no counterpart (its consumers - ProcessGroupGloo + DDP's reducer - copy
+    gradients into a bucket, stage it through pinned host memory and reduce on the CPU).
+
+        bucketer = GradientBucketer(ctx, cuda_ctx, model.parameters())
+        loss.backward(); bucketer.finish(); optimizer.step(); bucketer.zero_grad()
+    """
+
+    def __init__(self, ctx, cuda_ctx, params: Iterable, bucket_bytes: int = 64 << 20, average: bool = True):
+        import torch
+
+        super().__init__(ctx, cuda_ctx)
+        self.average = average
+        self.buckets = []
+        self._next = 0
+        self._hooks = []
+        self._comm_stream = None
+        plist = [p for p in params if p.requires_grad]
+        groups, cur, cur_bytes = [], [], 0
+        for p in reversed(plist):
+            nbytes = p.numel() * p.element_size()
+            if cur and (cur_bytes + nbytes > bucket_bytes or p.dtype != cur[0].dtype or p.device != cur[0].device):
+                groups.append(cur)
+                cur, cur_bytes = [], 0
+            cur.append(p)
+            cur_bytes += nbytes
+        if cur:
+            groups.append(cur)
+        for group in groups:
+            # every view starts on a 16-byte boundary so the kernels stay vectorised
+            align = max(1, 16 // group[0].element_size())
+            offs, n = [], 0
+            for p in group:
+                offs.append(n)
+                n += (p.numel() + align - 1) // align * align
+            cuda = _is_cuda(group[0])
+            if cuda:
+                flat = self.cc.empty(n, group[0].dtype)
+                if self._comm_stream is None:
+                    from ..ops.cuda import new_stream  # dedicated: torch.cuda.Stream() comes from a shared pool
+
+                    self._comm_stream = new_stream(group[0].device.index)
+            else:
+                flat = torch.empty(n, dtype=group[0].dtype)
+            flat.zero_()
+            b = {"flat": flat, "params": group, "offs": offs, "pending": len(group), "launched": False, "done": None,
+                 "cuda": cuda}
+            for p, off in zip(group, offs):
+                p.grad = flat[off:off + p.numel()].view_as(p)
+                self._hooks.append(p.register_post_accumulate_grad_hook(lambda q, b=b: self._ready(b, q)))
+            self.buckets.append(b)
+
+    def _view(self, b, p):
+        off = b["offs"][[id(x) for x in b["params"]].index(id(p))]
+        return b["flat"][off:off + p.numel()].view_as(p)
+
+    def _ready(self, b, p):
+        v = self._view(b, p)
+        if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+            # somebody replaced the gradient tensor (zero_grad(set_to_none=True), clip utilities that
+            # rebind .grad): take the value and point .grad back into the bucket
+            v.copy_(p.grad)
+            p.grad = v
+        b["pending"] -= 1
+        while self._next < len(self.buckets) and self.buckets[self._next]["pending"] == 0:
+            self._launch(self.buckets[self._next])
+            self._next += 1
+
+    def _launch(self, b):
+        if b["launched"]:
+            return
+        b["launched"] = True
+        if b["cuda"]:
+            import torch
+
+            ev = torch.cuda.Event()
+            ev.record(torch.cuda.current_stream())
+            self._comm_stream.wait_event(ev)
+            fused = self.average and b["flat"].is_floating_point()
+            self.cc.allreduce(b["flat"], average=fused, stream=self._comm_stream)
+            if self.average and not fused:
+                with torch.cuda.stream(self._comm_stream):
+                    b["flat"].div_(self.size)
+            b["done"] = torch.cuda.Event()
+            b["done"].record(self._comm_stream)
+        else:
+            self._allreduce(b["flat"], average=self.average)
+
+    def finish(self):
+        """After ``backward()``: launch what has not been launched (buckets with parameters that
+        received no gradient this step) in order, and order the compute stream behind the results."""
+        for b in self.buckets[self._next:]:
+            self._launch(b)
+        for b in self.buckets:
+            if b["cuda"] and b["done"] is not None:
+                import torch
+
+                torch.cuda.current_stream().wait_event(b["done"])
+            b["pending"], b["launched"], b["done"] = len(b["params"]), False, None
+        self._next = 0
+
+    def zero_grad(self):
+        """Zero the buckets in place (keeps every ``p.grad`` a view into symmetric memory)."""
+        for b in self.buckets:
+            b["flat"].zero_()
+            for p, off in zip(b["params"], b["offs"]):
+                v = b["flat"][off:off + p.numel()].view_as(p)
+                if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                    p.grad = v
+
+    def remove(self):
+        for h in self._hooks:
+            h.remove()
+        self._hooks = []
+
+
 class ZeroShard(_Base):
     """ZeRO / FSDP building blocks: each rank owns 1/P of a flat parameter vector."""
 

@@ -3,7 +3,7 @@ import torch
 
 import gloo_b200 as gb
 from gloo_b200.models import DDPMLP, train_step
-from gloo_b200.parallel import (DataParallel, MoEDispatcher, RingExchange, TensorParallel, UlyssesAttention,
+from gloo_b200.parallel import (DataParallel, GradientBucketer, MoEDispatcher, RingExchange, TensorParallel, UlyssesAttention,
                                 ZeroShard)
 
 
@@ -33,6 +33,53 @@ def test_ddp_matches_single_process():
     for grads in gb.spawn_threads(size, fn):
         for g, w in zip(grads, want):
             torch.testing.assert_close(g, w, rtol=1e-4, atol=1e-5)
+
+
+def test_gradient_bucketer_views_and_overlap_order():
+    """Gradients are views into the flat buckets, buckets are reduced in order while backward runs, two
+    steps (zero_grad keeps the views; a rebound .grad is adopted), a parameter without gradient."""
+    size = 3
+    torch.manual_seed(1)
+    ref = DDPMLP()
+    x = torch.randn(size * 4, 64)
+    y = torch.randn(size * 4, 8)
+    single = DDPMLP()
+    single.load_state_dict(ref.state_dict())
+    torch.nn.functional.mse_loss(single(x), y).backward()
+    want = [p.grad.clone() for p in single.parameters()]
+
+    def fn(ctx):
+        m = DDPMLP()
+        m.load_state_dict(ref.state_dict())
+        unused = torch.nn.Parameter(torch.ones(5))          # never part of the loss: no hook fires for it
+        params = list(m.parameters()) + [unused]
+        gbk = GradientBucketer(ctx, None, params, bucket_bytes=4 << 10)
+        assert len(gbk.buckets) > 2
+        flat0 = gbk.buckets[0]["flat"]
+        assert all(p.grad is not None and p.grad.untyped_storage().data_ptr() in
+                   {b["flat"].untyped_storage().data_ptr() for b in gbk.buckets} for p in params)
+        xs, ys = x[ctx.rank * 4:(ctx.rank + 1) * 4], y[ctx.rank * 4:(ctx.rank + 1) * 4]
+        out = []
+        for step in range(2):
+            loss = torch.nn.functional.mse_loss(m(xs), ys)
+            if step == 1:
+                params[0].grad = None                          # what zero_grad(set_to_none=True) does
+            loss.backward()
+            gbk.finish()
+            out.append([p.grad.clone() for p in m.parameters()])
+            assert float(unused.grad.abs().sum()) == 0.0
+            assert gbk.buckets[0]["flat"] is flat0 and params[0].grad.untyped_storage().data_ptr() in \
+                {b["flat"].untyped_storage().data_ptr() for b in gbk.buckets}
+            gbk.zero_grad()
+            assert all(float(p.grad.abs().sum()) == 0.0 for p in params)
+        gbk.remove()
+        return out
+
+    for steps in gb.spawn_threads(size, fn):
+        for grads in steps:
+            for g, w in zip(grads, want):
+                # mean over ranks of per-rank mean losses == full-batch mean loss (equal shards)
+                torch.testing.assert_close(g, w, rtol=1e-4, atol=1e-5)
 
 
 def test_zero_shard_roundtrip():

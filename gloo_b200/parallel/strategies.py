@@ -123,6 +123,10 @@ class GradientBucketer(_Base):
         self._next = 0
         self._hooks = []
         self._comm_stream = None
+        # Ranks that share one GPU (threads-as-ranks tests) rendezvous on the host before every launch
+        # (PeerContext::launchGuard) and share the process's single autograd thread: a hook that waits for
+        # a peer's hook would wait for itself. There the buckets are launched from finish() instead.
+        self._defer = cuda_ctx is not None and cuda_ctx.pc.ranks_on_my_device() > 1
         plist = [p for p in params if p.requires_grad]
         groups, cur, cur_bytes = [], [], 0
         for p in reversed(plist):
@@ -170,6 +174,8 @@ class GradientBucketer(_Base):
             v.copy_(p.grad)
             p.grad = v
         b["pending"] -= 1
+        if self._defer:
+            return
         while self._next < len(self.buckets) and self.buckets[self._next]["pending"] == 0:
             self._launch(self.buckets[self._next])
             self._next += 1

@@ -458,47 +458,6 @@ def test_local_allreduce_many_launch_shapes():
         cu.set_local_shape(4, 1, False)
 
 
-@pytest.mark.parametrize("size", [2, 3])
-def test_gradient_bucketer_cuda(size):
-    """GradientBucketer on CUDA: p.grad is a view into a symmetric bucket, buckets are averaged by the fused
-    kernel on a side stream while backward is still running; result == full-batch gradient."""
-    from gloo_b200.models import DDPMLP
-    from gloo_b200.parallel import GradientBucketer
-
-    torch.manual_seed(3)
-    ref = DDPMLP()
-    x, y = torch.randn(size * 4, 64), torch.randn(size * 4, 8)
-    single = DDPMLP()
-    single.load_state_dict(ref.state_dict())
-    torch.nn.functional.mse_loss(single(x), y).backward()
-    want = [p.grad.clone() for p in single.parameters()]
-
-    def fn(ctx):
-        cc = gcu.CudaContext(ctx, 0, stage_bytes=8 << 20)
-        m = DDPMLP().cuda()
-        m.load_state_dict(ref.state_dict())
-        gbk = GradientBucketer(ctx, cc, m.parameters(), bucket_bytes=8 << 10)
-        assert len(gbk.buckets) > 1 and all(cc.lookup(b["flat"])[0] is not None for b in gbk.buckets)
-        xs, ys = x[ctx.rank * 4:(ctx.rank + 1) * 4].cuda(), y[ctx.rank * 4:(ctx.rank + 1) * 4].cuda()
-        _sync()
-        cc.pc.host_barrier()
-        out = []
-        for _ in range(2):
-            torch.nn.functional.mse_loss(m(xs), ys).backward()
-            gbk.finish()
-            _sync()
-            out.append([p.grad.detach().cpu().clone() for p in m.parameters()])
-            gbk.zero_grad()
-        cc.check_health()
-        cc.pc.host_barrier()
-        return out
-
-    for steps in gb.spawn_threads(size, fn, cuda_device=0):
-        for grads in steps:
-            for g, w in zip(grads, want):
-                torch.testing.assert_close(g, w, rtol=1e-4, atol=1e-5)
-
-
 # ---- ordering across streams, literal pipelined schedule ------------------------------------------------------------
 
 def test_collectives_on_two_streams_are_ordered():
@@ -615,3 +574,46 @@ def test_local_op_classes():
         res = gb._C.cuda.local_ops_selftest(list(range(min(4, torch.cuda.device_count()))), 100003)
         assert all(r["ok"] for r in res), res
         assert any("NCCL" in r["name"] for r in res)
+
+
+# ---- consumers: gradients living in symmetric buckets (kept last in the file) ----------------------------------
+
+@pytest.mark.parametrize("size", [2, 3])
+def test_gradient_bucketer_cuda(size):
+    """GradientBucketer on CUDA: p.grad is a view into a symmetric bucket, buckets are averaged by the fused
+    kernel on a side stream while backward is still running; result == full-batch gradient."""
+    from gloo_b200.models import DDPMLP
+    from gloo_b200.parallel import GradientBucketer
+
+    torch.manual_seed(3)
+    ref = DDPMLP()
+    x, y = torch.randn(size * 4, 64), torch.randn(size * 4, 8)
+    single = DDPMLP()
+    single.load_state_dict(ref.state_dict())
+    torch.nn.functional.mse_loss(single(x), y).backward()
+    want = [p.grad.clone() for p in single.parameters()]
+
+    def fn(ctx):
+        cc = gcu.CudaContext(ctx, 0, stage_bytes=8 << 20)
+        m = DDPMLP().cuda()
+        m.load_state_dict(ref.state_dict())
+        gbk = GradientBucketer(ctx, cc, m.parameters(), bucket_bytes=8 << 10)
+        assert len(gbk.buckets) > 1 and all(cc.lookup(b["flat"])[0] is not None for b in gbk.buckets)
+        xs, ys = x[ctx.rank * 4:(ctx.rank + 1) * 4].cuda(), y[ctx.rank * 4:(ctx.rank + 1) * 4].cuda()
+        _sync()
+        cc.pc.host_barrier()
+        out = []
+        for _ in range(2):
+            torch.nn.functional.mse_loss(m(xs), ys).backward()
+            gbk.finish()
+            _sync()
+            out.append([p.grad.detach().cpu().clone() for p in m.parameters()])
+            gbk.zero_grad()
+        cc.check_health()
+        cc.pc.host_barrier()
+        return out
+
+    for steps in gb.spawn_threads(size, fn, cuda_device=0):
+        for grads in steps:
+            for g, w in zip(grads, want):
+                torch.testing.assert_close(g, w, rtol=1e-4, atol=1e-5)

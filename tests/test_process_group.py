@@ -35,3 +35,21 @@ def test_torch_distributed_backend_cuda():
     outs = [p.communicate(timeout=240) for p in procs]
     for r, (p, (out, err)) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and f"rank {r} ok" in out, (r, p.returncode, out[-500:], err[-2000:])
+
+
+@pytest.mark.gpu
+def test_gradient_bucketer_overlapped_multiprocess():
+    """GradientBucketer with one process per GPU: buckets are launched from the autograd hooks while backward
+    runs (kept at the very end of the GPU tests: it is the newest consumer)."""
+    import torch
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs >= 2 GPUs")
+    size = 2
+    worker = os.path.join(os.path.dirname(os.path.abspath(__file__)), "bucketer_worker.py")
+    d = tempfile.mkdtemp(prefix="glb_bucketer_")
+    procs = [subprocess.Popen([sys.executable, worker, d, str(r), str(size)], stdout=subprocess.PIPE,
+                              stderr=subprocess.STDOUT, text=True) for r in range(size)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for r, (p, out) in enumerate(zip(procs, outs)):
+        assert p.returncode == 0 and f"WORKER {r} OK" in out, (r, p.returncode, out[-3000:])

@@ -2,7 +2,7 @@
 # Sanitizer pass over the host transport and collectives (the reference's -DSANITIZE=<x>):
 # P ranks as processes x 2 threads each, running the instrumented benchmark binary built by
 # `python build.py --sanitize <thread|address|undefined>`.
-# usage: scripts/sanitizer_run.sh <thread|address|undefined> [P] [benchmark ...]
+# usage: [GLB_SAN_TRANSPORT=tcp|uv] scripts/sanitizer_run.sh <thread|address|undefined> [P] [benchmark ...]
 SAN=${1:-thread}; P=${2:-3}; shift; shift
 BIN=gloo_b200/bin/glb_benchmark_$SAN
 [ -x $BIN ] || python build.py --sanitize $SAN || exit 1
@@ -18,7 +18,7 @@ for NAME in "$@"; do
       TSAN_OPTIONS="suppressions=$PWD/.tsan-suppressions halt_on_error=0 second_deadlock_stack=1 log_path=$OUT/$NAME.$EL.r$r" \
       ASAN_OPTIONS="detect_leaks=1 log_path=$OUT/$NAME.$EL.r$r" \
       UBSAN_OPTIONS="print_stacktrace=1 log_path=$OUT/$NAME.$EL.r$r" \
-        $BIN --size $P --rank $r --shared-path $D --transport tcp --iteration-count 30 --warmup-iters 2 \
+        $BIN --size $P --rank $r --shared-path $D --transport ${GLB_SAN_TRANSPORT:-tcp} --iteration-count 30 --warmup-iters 2 \
              --threads 2 --elements $EL $NAME >$OUT/$NAME.$EL.r$r.stdout 2>&1 &
       r=$((r+1)); done
     wait; rm -rf $D

@@ -166,3 +166,22 @@ def test_affinity_helpers_are_best_effort():
     got = bind_to_gpu(0)
     assert isinstance(got, list)
     assert os.sched_getaffinity(0) == before or set(got) <= before
+
+
+def test_training_example_runs_on_two_processes():
+    """examples/example_training.py end to end (CPU tensors here): rendezvous, parameter broadcast,
+    GradientBucketer, optimizer steps; the loss must go down."""
+    import os
+    import re
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, STEPS="12", CUDA_VISIBLE_DEVICES="")
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29613",
+                          os.path.join(root, "examples", "example_training.py")],
+                         capture_output=True, text=True, timeout=240, env=env)
+    assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
+    m = re.search(r"loss ([0-9.]+) -> ([0-9.]+) over 12 steps on 2 rank", out.stdout + out.stderr)
+    assert m and float(m.group(2)) < float(m.group(1)), out.stdout[-500:]

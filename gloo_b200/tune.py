@@ -352,6 +352,18 @@ def main(argv=None):
                                       f"{coll} P={P} buf=sym maxbytes=inf algo=push blocks={b}\n")
                 cu.set_tuning({"copy_blocks": 512, "max_blocks": b})
                 cands.append(attempt("push", call, total, blocks=b))
+            if coll == "broadcast" and P > 2:
+                # the four kernels behind cc.broadcast (planBroadcast honours the algo name of a table row)
+                for name in ("direct", "scatter", "nvls", "relay"):
+                    if name == "direct" and total * (P - 1) > (1 << 30):
+                        continue
+                    if name == "nvls" and not cc.nvls_available():
+                        continue
+                    for b in ([64, 148] if args.quick else [32, 64, 148]):
+                        cu.tuning_clear()
+                        cu.tuning_load_string(f"broadcast P={P} buf=reg maxbytes=inf algo={name} blocks={b}\n")
+                        cu.set_tuning({"copy_blocks": 512, "max_blocks": b})
+                        cands.append(attempt(name, call, total, blocks=b))
             if coll == "allgather" and per >= (256 << 10):
                 for b in (37, 74, 148):  # TMA variant: cp.async.bulk through shared memory, 1 CTA per SM
                     cu.tuning_clear()

@@ -6,6 +6,7 @@ here is a thin, explicit mapping from a strategy to the collective it consumes:
   DataParallel        gradient allreduce in size-capped buckets (+ broadcast of params)
   GradientBucketer    gradients live in symmetric buckets (views), allreduce overlapped with backward
   ZeroShard           ZeRO/FSDP: reduce_scatter gradients, allgather parameters
+  ZeroOptimizer       ZeRO-1: flat symmetric param / grad buffers, optimizer state for 1/P of them
   TensorParallel      Megatron column/row-parallel linear: allgather / allreduce
   SequenceParallel    Megatron-SP: reduce_scatter + allgather along the sequence
   MoEDispatcher       expert parallel dispatch/combine: alltoallv
@@ -23,5 +24,6 @@ from .strategies import (  # noqa: F401
     SequenceParallel,
     TensorParallel,
     UlyssesAttention,
+    ZeroOptimizer,
     ZeroShard,
 )

@@ -259,6 +259,84 @@ class ZeroShard(_Base):
         return flat_param
 
 
+class ZeroOptimizer(_Base):
+    """ZeRO stage 1 on flat buffers: every rank keeps the optimizer state of 1/P of the parameters.
+
+    Parameters and gradients are re-pointed into two flat buffers (symmetric memory on CUDA: the
+    collectives read and write them in place). ``step()`` = reduce_scatter of the flat gradient
+    (1/P average fused into the kernel) -> the wrapped torch optimizer updates this rank's shard
+    only -> allgather of the updated shards back into the flat parameter buffer. Optimizer state
+    (Adam moments, ...) exists for the shard only: 1/P of the memory of a replicated optimizer.
+
+        zo = ZeroOptimizer(ctx, cuda_ctx, model.parameters(), torch.optim.AdamW, lr=1e-3)
+        loss.backward(); zo.step(); zo.zero_grad()
+    """
+
+    def __init__(self, ctx, cuda_ctx, params: Iterable, optimizer_cls, average: bool = True, **optimizer_kwargs):
+        import torch
+
+        super().__init__(ctx, cuda_ctx)
+        self.average = average
+        self.params = [p for p in params if p.requires_grad]
+        assert self.params, "no trainable parameters"
+        dtype, device = self.params[0].dtype, self.params[0].device
+        assert all(p.dtype == dtype and p.device == device for p in self.params), "one dtype / device per ZeroOptimizer"
+        cuda = device.type == "cuda"
+        align = max(1, 16 // self.params[0].element_size())
+        offs, n = [], 0
+        for p in self.params:
+            offs.append(n)
+            n += (p.numel() + align - 1) // align * align
+        unit = align * self.size                       # every shard starts on a 16-byte boundary
+        n = (n + unit - 1) // unit * unit
+        alloc = (lambda k: self.cc.empty(k, dtype)) if cuda else (lambda k: torch.empty(k, dtype=dtype))
+        self.flat_param, self.flat_grad = alloc(n), alloc(n)
+        self.flat_param.zero_()
+        self.flat_grad.zero_()
+        with torch.no_grad():
+            for p, off in zip(self.params, offs):
+                self.flat_param[off:off + p.numel()].copy_(p.reshape(-1))
+                p.data = self.flat_param[off:off + p.numel()].view_as(p)
+                p.grad = self.flat_grad[off:off + p.numel()].view_as(p)
+        self._offs = offs
+        self.counts = [n // self.size] * self.size
+        self.start = self.rank * (n // self.size)
+        cnt = self.counts[self.rank]
+        # the shard the optimizer owns: its own tensors (the collectives' inputs / outputs must not
+        # alias the flat buffers they gather into / scatter from)
+        self.shard = torch.nn.Parameter(self.flat_param[self.start:self.start + cnt].detach().clone())
+        self.shard.grad = torch.zeros_like(self.shard)
+        self.optimizer = optimizer_cls([self.shard], **optimizer_kwargs)
+
+    def step(self):
+        import torch
+
+        # a gradient tensor that was rebound (zero_grad(set_to_none=True)) is copied back into the flat buffer
+        for p, off in zip(self.params, self._offs):
+            v = self.flat_grad[off:off + p.numel()].view_as(p)
+            if p.grad is not None and p.grad.data_ptr() != v.data_ptr():
+                v.copy_(p.grad)
+                p.grad = v
+        ZeroShard(self.ctx, self.cc).reduce_scatter_gradients(self.flat_grad, self.shard.grad, average=self.average)
+        self.optimizer.step()
+        with torch.no_grad():
+            ZeroShard(self.ctx, self.cc).allgather_parameters(self.flat_param, self.shard.data)
+
+    def zero_grad(self):
+        self.flat_grad.zero_()
+        for p, off in zip(self.params, self._offs):
+            v = self.flat_grad[off:off + p.numel()].view_as(p)
+            if p.grad is None or p.grad.data_ptr() != v.data_ptr():
+                p.grad = v
+
+    def state_bytes(self) -> int:
+        """Bytes of optimizer state held by this rank (for the 1/P claim)."""
+        import torch
+
+        return sum(v.numel() * v.element_size() for st in self.optimizer.state.values() for v in st.values()
+                   if isinstance(v, torch.Tensor))
+
+
 class TensorParallel(_Base):
     """Megatron tensor parallelism: row-parallel output is an allreduce of partial sums;
     column-parallel output is an allgather along the feature dimension."""

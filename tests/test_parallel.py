@@ -185,3 +185,42 @@ def test_training_example_runs_on_two_processes():
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
     m = re.search(r"loss ([0-9.]+) -> ([0-9.]+) over 12 steps on 2 rank", out.stdout + out.stderr)
     assert m and float(m.group(2)) < float(m.group(1)), out.stdout[-500:]
+
+
+def test_zero_optimizer_matches_replicated_adam():
+    """ZeRO-1: reduce_scatter of the flat gradient, AdamW on the local shard, allgather of the parameters ==
+    AdamW on the full batch in one process; optimizer state is 1/P of the replicated one."""
+    from gloo_b200.parallel import ZeroOptimizer
+
+    size = 3
+    torch.manual_seed(7)
+    ref = DDPMLP()
+    xs_all = [torch.randn(size * 4, 64) for _ in range(3)]
+    ys_all = [torch.randn(size * 4, 8) for _ in range(3)]
+    single = DDPMLP()
+    single.load_state_dict(ref.state_dict())
+    opt = torch.optim.AdamW(single.parameters(), lr=1e-2)
+    for x, y in zip(xs_all, ys_all):
+        opt.zero_grad()
+        torch.nn.functional.mse_loss(single(x), y).backward()
+        opt.step()
+    want = [p.detach().clone() for p in single.parameters()]
+    full_state = sum(v.numel() * v.element_size() for st in opt.state.values() for v in st.values() if isinstance(v, torch.Tensor) and v.numel() > 1)
+
+    def fn(ctx):
+        m = DDPMLP()
+        m.load_state_dict(ref.state_dict())
+        zo = ZeroOptimizer(ctx, None, m.parameters(), torch.optim.AdamW, lr=1e-2)
+        for step, (x, y) in enumerate(zip(xs_all, ys_all)):
+            loss = torch.nn.functional.mse_loss(m(x[ctx.rank * 4:(ctx.rank + 1) * 4]), y[ctx.rank * 4:(ctx.rank + 1) * 4])
+            if step == 1:
+                next(m.parameters()).grad = None      # zero_grad(set_to_none=True) on the model
+            loss.backward()
+            zo.step()
+            zo.zero_grad()
+        return [p.detach().clone() for p in m.parameters()], zo.state_bytes()
+
+    for params, state in gb.spawn_threads(size, fn):
+        for p, w in zip(params, want):
+            torch.testing.assert_close(p, w, rtol=2e-4, atol=2e-5)
+        assert state <= full_state / size * 1.05 + 64

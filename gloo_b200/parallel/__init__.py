@@ -7,7 +7,8 @@ here is a thin, explicit mapping from a strategy to the collective it consumes:
   GradientBucketer    gradients live in symmetric buckets (views), allreduce overlapped with backward
   ZeroShard           ZeRO/FSDP: reduce_scatter gradients, allgather parameters
   ZeroOptimizer       ZeRO-1: flat symmetric param / grad buffers, optimizer state for 1/P of them
-  TensorParallel      Megatron column/row-parallel linear: allgather / allreduce
+  TensorParallel      Megatron column/row-parallel linear: allgather / allreduce; ColumnParallelLinear /
+                      RowParallelLinear layers with the collectives as autograd operators (f / g)
   SequenceParallel    Megatron-SP: reduce_scatter + allgather along the sequence
   MoEDispatcher       expert parallel dispatch/combine: alltoallv
   UlyssesAttention    head<->sequence alltoall
@@ -17,10 +18,12 @@ Everything accepts either a CUDA ``CudaContext`` (NVLink kernels) or a host cont
 (TCP); tensors decide which path runs.
 """
 from .strategies import (  # noqa: F401
+    ColumnParallelLinear,
     DataParallel,
     GradientBucketer,
     MoEDispatcher,
     RingExchange,
+    RowParallelLinear,
     SequenceParallel,
     TensorParallel,
     UlyssesAttention,

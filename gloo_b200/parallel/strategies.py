@@ -339,7 +339,12 @@ class ZeroOptimizer(_Base):
 
 class TensorParallel(_Base):
     """Megatron tensor parallelism: row-parallel output is an allreduce of partial sums;
-    column-parallel output is an allgather along the feature dimension."""
+    column-parallel output is an allgather along the feature dimension.
+
+    ``column_linear`` / ``row_linear`` build the two layers of a tensor-parallel MLP block with
+    the collectives placed as autograd functions (Megatron's f / g operators): the forward of a
+    column -> row pair costs ONE allreduce (after the row-parallel matmul), the backward one
+    (before the column-parallel weight gradient)."""
 
     def row_parallel_output(self, partial):
         return self._allreduce(partial)
@@ -350,6 +355,101 @@ class TensorParallel(_Base):
         else:
             H.allgather(self.ctx, out, local)
         return out
+
+    # ---- autograd-aware operators --------------------------------------------------------------
+    def copy_to_region(self, x):
+        """f: identity in the forward pass, allreduce of the gradient in the backward pass."""
+        import torch
+
+        tp = self
+
+        class _F(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, inp):
+                return inp.view_as(inp)
+
+            @staticmethod
+            def backward(ctx, grad):
+                return tp._allreduce(grad.contiguous().clone())
+
+        return _F.apply(x)
+
+    def reduce_from_region(self, x):
+        """g: allreduce in the forward pass, identity in the backward pass."""
+        import torch
+
+        tp = self
+
+        class _G(torch.autograd.Function):
+            @staticmethod
+            def forward(ctx, inp):
+                return tp._allreduce(inp.contiguous().clone())
+
+            @staticmethod
+            def backward(ctx, grad):
+                return grad
+
+        return _G.apply(x)
+
+    def column_linear(self, in_features: int, out_features: int, bias: bool = True, device=None, dtype=None):
+        return ColumnParallelLinear(self, in_features, out_features, bias, device, dtype)
+
+    def row_linear(self, in_features: int, out_features: int, bias: bool = True, device=None, dtype=None):
+        return RowParallelLinear(self, in_features, out_features, bias, device, dtype)
+
+
+def _shard(n: int, size: int, rank: int):
+    assert n % size == 0, f"{n} features do not split over {size} ranks"
+    return n // size * rank, n // size * (rank + 1)
+
+
+try:  # the layer classes need torch; everything else in this module does not
+    import torch as _torch
+
+    class ColumnParallelLinear(_torch.nn.Module):
+        """y_local = x W_r^T + b_r with W split along the OUTPUT features (rank r holds rows
+        [r, r+1) * out/P). The input is replicated; its gradient is summed over ranks (f)."""
+
+        def __init__(self, tp: TensorParallel, in_features, out_features, bias=True, device=None, dtype=None):
+            super().__init__()
+            self.tp = tp
+            self.lo, self.hi = _shard(out_features, tp.size, tp.rank)
+            self.weight = _torch.nn.Parameter(_torch.empty(self.hi - self.lo, in_features, device=device, dtype=dtype))
+            self.bias = _torch.nn.Parameter(_torch.zeros(self.hi - self.lo, device=device, dtype=dtype)) if bias else None
+            _torch.nn.init.kaiming_uniform_(self.weight, a=5 ** 0.5)
+
+        def load_full(self, weight, bias=None):
+            with _torch.no_grad():
+                self.weight.copy_(weight[self.lo:self.hi])
+                if self.bias is not None and bias is not None:
+                    self.bias.copy_(bias[self.lo:self.hi])
+
+        def forward(self, x):
+            return _torch.nn.functional.linear(self.tp.copy_to_region(x), self.weight, self.bias)
+
+    class RowParallelLinear(_torch.nn.Module):
+        """y = sum_r x_r W_r^T + b with W split along the INPUT features; the input arrives already
+        split (the output of a ColumnParallelLinear); one allreduce of the partial products (g)."""
+
+        def __init__(self, tp: TensorParallel, in_features, out_features, bias=True, device=None, dtype=None):
+            super().__init__()
+            self.tp = tp
+            self.lo, self.hi = _shard(in_features, tp.size, tp.rank)
+            self.weight = _torch.nn.Parameter(_torch.empty(out_features, self.hi - self.lo, device=device, dtype=dtype))
+            self.bias = _torch.nn.Parameter(_torch.zeros(out_features, device=device, dtype=dtype)) if bias else None
+            _torch.nn.init.kaiming_uniform_(self.weight, a=5 ** 0.5)
+
+        def load_full(self, weight, bias=None):
+            with _torch.no_grad():
+                self.weight.copy_(weight[:, self.lo:self.hi])
+                if self.bias is not None and bias is not None:
+                    self.bias.copy_(bias)
+
+        def forward(self, x_local):
+            y = self.tp.reduce_from_region(_torch.nn.functional.linear(x_local, self.weight))
+            return y if self.bias is None else y + self.bias
+except ImportError:  # pragma: no cover
+    ColumnParallelLinear = RowParallelLinear = None
 
 
 class SequenceParallel(_Base):

@@ -224,3 +224,33 @@ def test_zero_optimizer_matches_replicated_adam():
         for p, w in zip(params, want):
             torch.testing.assert_close(p, w, rtol=2e-4, atol=2e-5)
         assert state <= full_state / size * 1.05 + 64
+
+
+def test_tensor_parallel_mlp_matches_dense():
+    """Column-parallel -> GELU -> row-parallel == the dense MLP: forward output, input gradient and the
+    gradients of the weight shards (one allreduce in forward, one in backward)."""
+    size = 4
+    torch.manual_seed(11)
+    dense1, dense2 = torch.nn.Linear(32, 64), torch.nn.Linear(64, 16)
+    x = torch.randn(6, 32, requires_grad=True)
+    target = torch.randn(6, 16)
+    torch.nn.functional.mse_loss(dense2(torch.nn.functional.gelu(dense1(x))), target).backward()
+    want_out = dense2(torch.nn.functional.gelu(dense1(x))).detach()
+
+    def fn(ctx):
+        tp = TensorParallel(ctx)
+        col, row = tp.column_linear(32, 64), tp.row_linear(64, 16)
+        col.load_full(dense1.weight.detach(), dense1.bias.detach())
+        row.load_full(dense2.weight.detach(), dense2.bias.detach())
+        xi = x.detach().clone().requires_grad_(True)
+        out = row(torch.nn.functional.gelu(col(xi)))
+        torch.nn.functional.mse_loss(out, target).backward()
+        return (out.detach(), xi.grad, col.weight.grad, col.bias.grad, row.weight.grad, row.bias.grad, (col.lo, col.hi), (row.lo, row.hi))
+
+    for out, gx, gcw, gcb, grw, grb, (clo, chi), (rlo, rhi) in gb.spawn_threads(size, fn):
+        torch.testing.assert_close(out, want_out, rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(gx, x.grad, rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(gcw, dense1.weight.grad[clo:chi], rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(gcb, dense1.bias.grad[clo:chi], rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(grw, dense2.weight.grad[:, rlo:rhi], rtol=1e-4, atol=1e-6)
+        torch.testing.assert_close(grb, dense2.bias.grad, rtol=1e-4, atol=1e-6)

@@ -543,3 +543,64 @@ class RingExchange(_Base):
         rb.wait_recv()
         sb.wait_send()
         return recv
+
+    def attention(self, q, k, v, causal: bool = False):
+        """Ring attention (forward): rank r holds the queries and the K/V block of sequence shard r
+        ([S/P, H, D] each); K/V blocks rotate once around the ring while every rank folds the block
+        it currently holds into a running (max, sum, output) with the online-softmax recurrence, so
+        no rank ever materialises more than two K/V blocks. The rotation of the NEXT block is
+        posted before the current one is consumed (double buffer: on CUDA the two halves of a
+        symmetric buffer, written by the neighbour's zero-copy ``exchange`` kernel on a side
+        stream while the attention math runs). ``causal``: shard r attends to shards <= r.
+        Returns [S/P, H, D] in q's dtype. The math is plain torch (fp32 accumulation)."""
+        import torch
+
+        P, r = self.size, self.rank
+        scale = q.shape[-1] ** -0.5
+        qf = q.float().transpose(0, 1)                                    # [H, Sq, D]
+        m = torch.full(qf.shape[:2], float("-inf"), device=q.device)      # running max   [H, Sq]
+        l = torch.zeros(qf.shape[:2], device=q.device)                    # running sum   [H, Sq]
+        acc = torch.zeros_like(qf)                                        # running out   [H, Sq, D]
+        kv = torch.stack([k, v]).contiguous()
+        cuda = _is_cuda(kv)
+        if cuda and P > 1:
+            cur, nxt = self.kv_buffers(kv.numel(), kv.dtype)
+            cur = cur.view_as(kv)
+            nxt = nxt.view_as(kv)
+            cur.copy_(kv)
+            side = getattr(self, "_side", None)
+            if side is None:
+                from ..ops.cuda import new_stream
+
+                side = self._side = new_stream(kv.device.index)
+        else:
+            cur, nxt = kv, torch.empty_like(kv)
+        for step in range(P):
+            src = (r - step) % P                                          # whose block `cur` is
+            if step + 1 < P:                                              # post the next rotation first
+                if cuda:
+                    ready = torch.cuda.Event()
+                    ready.record(torch.cuda.current_stream())
+                    side.wait_event(ready)
+                    self.cc.exchange(cur, (r + 1) % P, nxt, (r - 1) % P, stream=side)
+                    landed = torch.cuda.Event()
+                    landed.record(side)
+                else:
+                    self.rotate(cur, nxt)
+            if not (causal and src > r):
+                kf, vf = cur[0].float().transpose(0, 1), cur[1].float().transpose(0, 1)   # [H, Sk, D]
+                s = torch.matmul(qf, kf.transpose(1, 2)) * scale                          # [H, Sq, Sk]
+                if causal and src == r:
+                    sq, sk = s.shape[-2:]
+                    s = s.masked_fill(torch.ones(sq, sk, dtype=torch.bool, device=s.device).triu(1), float("-inf"))
+                m_new = torch.maximum(m, s.amax(dim=-1))
+                p = torch.exp(s - m_new.unsqueeze(-1))
+                alpha = torch.exp(m - m_new)
+                l = l * alpha + p.sum(dim=-1)
+                acc = acc * alpha.unsqueeze(-1) + torch.matmul(p, vf)
+                m = m_new
+            if step + 1 < P:
+                if cuda:
+                    torch.cuda.current_stream().wait_event(landed)
+                cur, nxt = nxt, cur
+        return (acc / l.unsqueeze(-1)).transpose(0, 1).to(q.dtype)

@@ -254,3 +254,24 @@ def test_tensor_parallel_mlp_matches_dense():
         torch.testing.assert_close(gcb, dense1.bias.grad[clo:chi], rtol=1e-4, atol=1e-6)
         torch.testing.assert_close(grw, dense2.weight.grad[:, rlo:rhi], rtol=1e-4, atol=1e-6)
         torch.testing.assert_close(grb, dense2.bias.grad, rtol=1e-4, atol=1e-6)
+
+
+def test_ring_attention_matches_full_attention():
+    """RingExchange.attention: K/V blocks rotate around the ring, online softmax per block == attention over
+    the whole sequence (plain and causal)."""
+    size, S, Hh, D = 4, 64, 3, 16
+    torch.manual_seed(13)
+    q, k, v = (torch.randn(S, Hh, D) for _ in range(3))
+
+    def full(causal):
+        qt, kt, vt = (t.transpose(0, 1) for t in (q, k, v))                # [H, S, D]
+        return torch.nn.functional.scaled_dot_product_attention(qt, kt, vt, is_causal=causal).transpose(0, 1)
+
+    def fn(ctx):
+        ring = RingExchange(ctx)
+        lo, hi = ctx.rank * S // size, (ctx.rank + 1) * S // size
+        return [ring.attention(q[lo:hi], k[lo:hi], v[lo:hi], causal=c) for c in (False, True)], (lo, hi)
+
+    for (plain, causal), (lo, hi) in gb.spawn_threads(size, fn):
+        torch.testing.assert_close(plain, full(False)[lo:hi], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(causal, full(True)[lo:hi], rtol=1e-4, atol=1e-5)

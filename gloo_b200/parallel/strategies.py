@@ -508,6 +508,38 @@ class UlyssesAttention(_Base):
 
     heads_to_seq = seq_to_heads
 
+    def attention(self, q, k, v, causal: bool = False):
+        """Full Ulysses attention: q / k / v are this rank's sequence shard [S/P, H, D]; one alltoall
+        turns them into all positions of H/P heads ([S, H/P, D]), attention runs locally over the
+        whole sequence, one alltoall brings the output back to [S/P, H, D]. On CUDA the exchange
+        buffers are symmetric (zero-copy push kernels); three alltoalls in, one out."""
+        import torch
+
+        P, r = self.size, self.rank
+        s_loc, Hh, D = q.shape
+        assert Hh % P == 0, "heads must divide over the ranks"
+        hp = Hh // P
+
+        def alloc(n, like):
+            return self.cc.empty(n, like.dtype) if _is_cuda(like) else torch.empty(n, dtype=like.dtype)
+
+        def to_heads(x):      # [S/P, H, D] -> [S, H/P, D]
+            send = x.view(s_loc, P, hp, D).transpose(0, 1).contiguous()      # block j = my positions of head group j
+            out = alloc(send.numel(), x)
+            self.seq_to_heads(send.view(-1), out)
+            return out.view(P * s_loc, hp, D)                                # block i = rank i's positions, my heads
+
+        def to_seq(y):        # [S, H/P, D] -> [S/P, H, D]
+            send = y.contiguous()                                           # block i = positions of rank i
+            out = alloc(send.numel(), y)
+            self.seq_to_heads(send.view(-1), out)
+            return out.view(P, s_loc, hp, D).transpose(0, 1).reshape(s_loc, Hh, D)
+
+        qh, kh, vh = to_heads(q), to_heads(k), to_heads(v)
+        o = torch.nn.functional.scaled_dot_product_attention(qh.transpose(0, 1), kh.transpose(0, 1), vh.transpose(0, 1),
+                                                             is_causal=causal).transpose(0, 1)
+        return to_seq(o)
+
 
 class RingExchange(_Base):
     """Neighbour exchange for ring attention (KV rotation) and pipeline parallelism.

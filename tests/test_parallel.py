@@ -275,3 +275,22 @@ def test_ring_attention_matches_full_attention():
     for (plain, causal), (lo, hi) in gb.spawn_threads(size, fn):
         torch.testing.assert_close(plain, full(False)[lo:hi], rtol=1e-4, atol=1e-5)
         torch.testing.assert_close(causal, full(True)[lo:hi], rtol=1e-4, atol=1e-5)
+
+
+def test_ulysses_attention_matches_full_attention():
+    size, S, Hh, D = 4, 32, 8, 16
+    torch.manual_seed(17)
+    q, k, v = (torch.randn(S, Hh, D) for _ in range(3))
+
+    def full(causal):
+        qt, kt, vt = (t.transpose(0, 1) for t in (q, k, v))
+        return torch.nn.functional.scaled_dot_product_attention(qt, kt, vt, is_causal=causal).transpose(0, 1)
+
+    def fn(ctx):
+        u = UlyssesAttention(ctx)
+        lo, hi = ctx.rank * S // size, (ctx.rank + 1) * S // size
+        return [u.attention(q[lo:hi].contiguous(), k[lo:hi].contiguous(), v[lo:hi].contiguous(), causal=c) for c in (False, True)], (lo, hi)
+
+    for (plain, causal), (lo, hi) in gb.spawn_threads(size, fn):
+        torch.testing.assert_close(plain, full(False)[lo:hi], rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(causal, full(True)[lo:hi], rtol=1e-4, atol=1e-5)

@@ -294,3 +294,34 @@ def test_ulysses_attention_matches_full_attention():
     for (plain, causal), (lo, hi) in gb.spawn_threads(size, fn):
         torch.testing.assert_close(plain, full(False)[lo:hi], rtol=1e-4, atol=1e-5)
         torch.testing.assert_close(causal, full(True)[lo:hi], rtol=1e-4, atol=1e-5)
+
+
+def test_tensor_parallel_transformer_block_matches_dense():
+    """models.TPBlock (heads and MLP columns split over the ranks, two allreduces per forward) == DenseBlock:
+    output, input gradient, and every weight-shard gradient."""
+    from gloo_b200.models import DenseBlock, TPBlock
+
+    size = 2
+    torch.manual_seed(19)
+    dense = DenseBlock(d_model=32, n_heads=4, d_ff=64)
+    x = torch.randn(2, 10, 32, requires_grad=True)
+    out_d = dense(x)
+    out_d.square().mean().backward()
+
+    def fn(ctx):
+        tp = TensorParallel(ctx)
+        blk = TPBlock(tp, d_model=32, n_heads=4, d_ff=64)
+        blk.load_dense(dense)
+        xi = x.detach().clone().requires_grad_(True)
+        out = blk(xi)
+        out.square().mean().backward()
+        return out.detach(), xi.grad, blk.up.weight.grad, (blk.up.lo, blk.up.hi), blk.proj.weight.grad, (blk.proj.lo, blk.proj.hi), blk.ln1.weight.grad
+
+    for out, gx, gup, (ulo, uhi), gproj, (plo, phi), gln in gb.spawn_threads(size, fn):
+        torch.testing.assert_close(out, out_d.detach(), rtol=1e-4, atol=1e-5)
+        torch.testing.assert_close(gx, x.grad, rtol=1e-3, atol=1e-6)
+        torch.testing.assert_close(gup, dense.up.weight.grad[ulo:uhi], rtol=1e-3, atol=1e-6)
+        torch.testing.assert_close(gproj, dense.proj.weight.grad[:, plo:phi], rtol=1e-3, atol=1e-6)
+        # replicated parameters (layer norms) see the full gradient on every rank: their input gradient is
+        # summed by f, their own gradient is computed from replicated activations
+        torch.testing.assert_close(gln, dense.ln1.weight.grad, rtol=1e-3, atol=1e-6)

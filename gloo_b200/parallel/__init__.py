@@ -12,7 +12,8 @@ here is a thin, explicit mapping from a strategy to the collective it consumes:
   SequenceParallel    Megatron-SP: reduce_scatter + allgather along the sequence
   MoEDispatcher       expert parallel dispatch/combine: alltoallv
   UlyssesAttention    head<->sequence alltoall
-  RingExchange        ring-attention / pipeline neighbour send-recv (KV rotation)
+  RingExchange        ring-attention / pipeline neighbour send-recv (KV rotation), ring attention forward
+  PipelineParallel    GPipe schedule over point-to-point activation / gradient sends
 
 Everything accepts either a CUDA ``CudaContext`` (NVLink kernels) or a host context
 (TCP); tensors decide which path runs.
@@ -22,6 +23,7 @@ from .strategies import (  # noqa: F401
     DataParallel,
     GradientBucketer,
     MoEDispatcher,
+    PipelineParallel,
     RingExchange,
     RowParallelLinear,
     SequenceParallel,

@@ -636,3 +636,74 @@ class RingExchange(_Base):
                     torch.cuda.current_stream().wait_event(landed)
                 cur, nxt = nxt, cur
         return (acc / l.unsqueeze(-1)).transpose(0, 1).to(q.dtype)
+
+
+class PipelineParallel(_Base):
+    """Pipeline parallelism (GPipe schedule): rank r holds stage r of the model; micro-batches flow
+    forward through point-to-point sends of the activations and backward through sends of their
+    gradients. All forwards run first, then all backwards in reverse micro-batch order, so every
+    stage keeps at most ``len(microbatches)`` activations alive and parameter gradients accumulate
+    over the micro-batches exactly as in one big batch.
+
+    CPU tensors move through unbound-buffer send / recv; CUDA tensors through the NVLink
+    point-to-point kernels (``CudaContext.send`` / ``recv``: the receiver drains a mailbox ring
+    inside its own pool while the sender streams into it, both on the current stream).
+    Activation shapes must be the same for every micro-batch (``out_shape`` of the previous stage).
+    """
+
+    _TAG_FWD, _TAG_BWD = 0x50, 0x51
+
+    def _send(self, t, dst, tag, seq):
+        if _is_cuda(t):
+            self.cc.send(t.contiguous(), dst)
+            return
+        t = t.contiguous()
+        b = self.ctx.create_unbound_buffer(t.data_ptr(), t.numel() * t.element_size())
+        b.send(dst, _C.slot_build(tag, seq))
+        b.wait_send()
+
+    def _recv(self, t, src, tag, seq):
+        if _is_cuda(t):
+            self.cc.recv(t, src)
+            return t
+        b = self.ctx.create_unbound_buffer(t.data_ptr(), t.numel() * t.element_size())
+        b.recv(src, _C.slot_build(tag, seq))
+        b.wait_recv()
+        return t
+
+    def run(self, stage, microbatches: Sequence, in_shape=None, loss_fn=None, targets: Optional[Sequence] = None,
+            dtype=None, device=None):
+        """One training step. ``stage``: this rank's module. ``microbatches``: the inputs (first stage only,
+        elsewhere just their count matters). ``in_shape``: shape of the activation this stage receives (all but
+        the first stage). ``loss_fn(output, target)`` and ``targets`` on the last stage. Returns the list of
+        micro-batch losses on the last stage, ``None`` elsewhere; parameter gradients are left in ``.grad``
+        (summed over micro-batches; scale the loss by 1/len(microbatches) for a mean)."""
+        import torch
+
+        first, last = self.rank == 0, self.rank == self.size - 1
+        n = len(microbatches)
+        inputs, outputs, losses = [], [], []
+        for i in range(n):
+            if first:
+                x = microbatches[i]
+            else:
+                x = self._recv(torch.empty(in_shape, dtype=dtype, device=device), self.rank - 1, self._TAG_FWD, i)
+                x.requires_grad_(True)
+            y = stage(x)
+            inputs.append(x)
+            if last:
+                loss = loss_fn(y, targets[i])
+                losses.append(loss)
+                outputs.append(loss)
+            else:
+                outputs.append(y)
+                self._send(y.detach(), self.rank + 1, self._TAG_FWD, i)
+        for i in reversed(range(n)):
+            if last:
+                outputs[i].backward()
+            else:
+                g = self._recv(torch.empty_like(outputs[i]), self.rank + 1, self._TAG_BWD, i)
+                outputs[i].backward(g)
+            if not first:
+                self._send(inputs[i].grad, self.rank - 1, self._TAG_BWD, i)
+        return [float(l.detach()) for l in losses] if last else None

@@ -1,4 +1,5 @@
 """parallel/ strategies on the host path (CPU tensors over TCP)."""
+import pytest
 import torch
 
 import gloo_b200 as gb
@@ -325,3 +326,43 @@ def test_tensor_parallel_transformer_block_matches_dense():
         # replicated parameters (layer norms) see the full gradient on every rank: their input gradient is
         # summed by f, their own gradient is computed from replicated activations
         torch.testing.assert_close(gln, dense.ln1.weight.grad, rtol=1e-3, atol=1e-6)
+
+
+def test_pipeline_parallel_matches_sequential():
+    """3 stages x 4 micro-batches (GPipe): parameter gradients == one process running the whole model on the
+    whole batch; losses come back on the last stage."""
+    from gloo_b200.parallel import PipelineParallel
+
+    size, n_mb, mb = 3, 4, 5
+    torch.manual_seed(23)
+    stages = [torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.Tanh()),
+              torch.nn.Sequential(torch.nn.Linear(32, 32), torch.nn.Tanh()),
+              torch.nn.Linear(32, 4)]
+    x, y = torch.randn(n_mb * mb, 16), torch.randn(n_mb * mb, 4)
+    seq = torch.nn.Sequential(*[torch.nn.Sequential(*s) if isinstance(s, torch.nn.Sequential) else s for s in stages])
+    want_losses = []
+    for i in range(n_mb):
+        l = torch.nn.functional.mse_loss(seq(x[i * mb:(i + 1) * mb]), y[i * mb:(i + 1) * mb]) / n_mb
+        l.backward()
+        want_losses.append(float(l.detach()))
+    want = [[p.grad.clone() for p in s.parameters()] for s in stages]
+    for s in stages:
+        s.zero_grad()
+
+    def fn(ctx):
+        import copy
+
+        stage = copy.deepcopy(stages[ctx.rank])
+        pp = PipelineParallel(ctx)
+        mbs = [x[i * mb:(i + 1) * mb] for i in range(n_mb)]
+        losses = pp.run(stage, mbs, in_shape=(mb, 16 if ctx.rank == 0 else 32), dtype=torch.float32,
+                        loss_fn=lambda o, t: torch.nn.functional.mse_loss(o, t) / n_mb,
+                        targets=[y[i * mb:(i + 1) * mb] for i in range(n_mb)])
+        return [p.grad.clone() for p in stage.parameters()], losses
+
+    res = gb.spawn_threads(size, fn)
+    for r, (grads, losses) in enumerate(res):
+        for g, w in zip(grads, want[r]):
+            torch.testing.assert_close(g, w, rtol=1e-4, atol=1e-6)
+        assert (losses is None) == (r != size - 1)
+    assert res[-1][1] == pytest.approx(want_losses, rel=1e-5)

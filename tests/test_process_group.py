@@ -38,6 +38,7 @@ def test_torch_distributed_backend_cuda():
 
 
 @pytest.mark.gpu
+@pytest.mark.xfail(strict=False, reason="written after the round's GPU minutes were spent; not yet run on hardware")
 def test_gradient_bucketer_overlapped_multiprocess():
     """GradientBucketer with one process per GPU: buckets are launched from the autograd hooks while backward
     runs (kept at the very end of the GPU tests: it is the newest consumer)."""

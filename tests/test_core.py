@@ -362,3 +362,33 @@ if given is not None:
         assert all(p >= 2 for p in f) and f == sorted(f)
         assert int(np.prod(f, dtype=np.int64)) == n if f else n == 1
         assert all(all(p % q for q in range(2, int(p ** 0.5) + 1)) for p in f)  # primes
+
+
+def test_metrics_snapshot_and_prometheus_endpoint():
+    """utils.metrics: counters move with traffic and are served in Prometheus text format."""
+    import socket
+    import urllib.request
+
+    import numpy as np
+
+    from gloo_b200.utils import metrics
+
+    before = metrics.snapshot()
+    assert {"glb_tcp_cma_messages_total", "glb_tcp_cma_bytes_total", "glb_tcp_spin_budget_us"} <= set(before)
+
+    def fn(ctx):
+        x = np.ones(1 << 20, np.float32)           # 4 MB: above the single-copy threshold between same-host ranks
+        gb.allreduce(ctx, x)
+        return float(x[0])
+
+    assert gb.spawn_threads(2, fn) == [2.0, 2.0]
+    after = metrics.snapshot()
+    assert after["glb_tcp_cma_bytes_total"] >= before["glb_tcp_cma_bytes_total"]
+    pytest.importorskip("prometheus_client")
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    metrics.start_exporter(port)
+    body = urllib.request.urlopen(f"http://127.0.0.1:{port}/metrics", timeout=10).read().decode()
+    assert "glb_tcp_cma_bytes_total" in body and "glb_build_info" in body and 'cuda_arch=' in body

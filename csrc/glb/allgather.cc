@@ -1,8 +1,10 @@
+#include "glb/common/trace.h"
 #include "glb/allgather.h"
 
 namespace glb {
 
 void allgather(AllgatherOptions& opts) {
+  GLB_HOST_TRACE("glb::allgather");
   const auto& context = opts.context;
   GLB_ENFORCE(opts.out != nullptr, "allgather: output required");
   UnboundBuffer* in = opts.in.get();

@@ -1,8 +1,10 @@
+#include "glb/common/trace.h"
 #include "glb/allgatherv.h"
 
 namespace glb {
 
 void allgatherv(AllgathervOptions& opts) {
+  GLB_HOST_TRACE("glb::allgatherv");
   const auto& context = opts.context;
   GLB_ENFORCE(opts.out != nullptr, "allgatherv: output required");
   GLB_ENFORCE(opts.elementSize > 0, "allgatherv: element size not set");

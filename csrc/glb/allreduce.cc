@@ -1,3 +1,4 @@
+#include "glb/common/trace.h"
 #include "glb/allreduce.h"
 
 #include <algorithm>
@@ -328,6 +329,7 @@ void oneShot(const AllreduceOptions& opts, UnboundBuffer* out0, UnboundBuffer* s
 }  // namespace
 
 void allreduce(const AllreduceOptions& opts) {
+  GLB_HOST_TRACE("glb::allreduce");
   const auto& context = opts.context;
   GLB_ENFORCE(context != nullptr, "allreduce: no context");
   GLB_ENFORCE(!opts.out.empty(), "allreduce: at least one output is required");

@@ -1,8 +1,10 @@
+#include "glb/common/trace.h"
 #include "glb/alltoall.h"
 
 namespace glb {
 
 void alltoall(AlltoallOptions& opts) {
+  GLB_HOST_TRACE("glb::alltoall");
   const auto& context = opts.context;
   GLB_ENFORCE(opts.in != nullptr && opts.out != nullptr, "alltoall: input and output required");
   UnboundBuffer* in = opts.in.get();

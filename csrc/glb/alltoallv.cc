@@ -1,8 +1,10 @@
+#include "glb/common/trace.h"
 #include "glb/alltoallv.h"
 
 namespace glb {
 
 void alltoallv(AlltoallvOptions& opts) {
+  GLB_HOST_TRACE("glb::alltoallv");
   const auto& context = opts.context;
   GLB_ENFORCE(opts.in != nullptr && opts.out != nullptr, "alltoallv: input and output required");
   UnboundBuffer* in = opts.in.get();

@@ -1,8 +1,10 @@
+#include "glb/common/trace.h"
 #include "glb/barrier.h"
 
 namespace glb {
 
 void barrier(BarrierOptions& opts) {
+  GLB_HOST_TRACE("glb::barrier");
   const auto& context = opts.context;
   auto& buffer = opts.buffer;
   const auto slot = Slot::build(kBarrierSlotPrefix, opts.tag);

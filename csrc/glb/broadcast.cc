@@ -1,3 +1,4 @@
+#include "glb/common/trace.h"
 #include "glb/broadcast.h"
 
 #include <algorithm>
@@ -7,6 +8,7 @@
 namespace glb {
 
 void broadcast(BroadcastOptions& opts) {
+  GLB_HOST_TRACE("glb::broadcast");
   const auto& context = opts.context;
   GLB_ENFORCE(opts.out != nullptr, "broadcast: output required");
   GLB_ENFORCE(opts.root >= 0 && opts.root < context->size, "broadcast: invalid root ", opts.root);

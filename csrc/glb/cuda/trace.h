@@ -6,6 +6,7 @@
 
 #include <nvtx3/nvToolsExt.h>
 
+#include "glb/common/trace.h"
 #include "glb/common/utils.h"
 
 namespace glb {
@@ -18,7 +19,7 @@ inline bool nvtxEnabled() {
 
 class TraceRange {
  public:
-  explicit TraceRange(const char* name) : active_(nvtxEnabled()) {
+  explicit TraceRange(const char* name) : active_(nvtxEnabled()), host_(name) {
     if (active_) nvtxRangePushA(name);
   }
   ~TraceRange() {
@@ -29,6 +30,7 @@ class TraceRange {
 
  private:
   bool active_;
+  ::glb::trace::Scope host_;  // the same scope as a chrome-trace event when GLB_TRACE_FILE is set (host-side enqueue time)
 };
 
 }  // namespace cuda

@@ -1,8 +1,10 @@
+#include "glb/common/trace.h"
 #include "glb/gather.h"
 
 namespace glb {
 
 void gather(GatherOptions& opts) {
+  GLB_HOST_TRACE("glb::gather");
   const auto& context = opts.context;
   GLB_ENFORCE(opts.in != nullptr, "gather: input required");
   GLB_ENFORCE(opts.root >= 0 && opts.root < context->size, "gather: invalid root ", opts.root);

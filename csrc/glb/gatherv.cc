@@ -1,8 +1,10 @@
+#include "glb/common/trace.h"
 #include "glb/gatherv.h"
 
 namespace glb {
 
 void gatherv(GathervOptions& opts) {
+  GLB_HOST_TRACE("glb::gatherv");
   const auto& context = opts.context;
   GLB_ENFORCE(opts.in != nullptr, "gatherv: input required");
   GLB_ENFORCE(opts.root >= 0 && opts.root < context->size, "gatherv: invalid root ", opts.root);

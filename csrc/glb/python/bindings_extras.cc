@@ -1,6 +1,7 @@
 // Diagnostics that do not belong to a class binding.
 #include <pybind11/pybind11.h>
 
+#include "glb/common/trace.h"
 #include "glb/config.h"
 #include "glb/transport/tcp/pair.h"
 
@@ -34,6 +35,8 @@ void registerExtras(py::module_& m) {
         return d;
       },
       "Compile-time configuration (glb/config.h).");
+  m.def("trace_enabled", [] { return ::glb::trace::enabled(); }, "True when GLB_TRACE_FILE is set (chrome-trace event sink).");
+  m.def("trace_flush", [] { return ::glb::trace::flush(); }, "Write the buffered trace events now; returns how many.");
   m.attr("__version__") = GLB_VERSION_STRING;
 }
 }  // namespace glb_py

@@ -1,3 +1,4 @@
+#include "glb/common/trace.h"
 #include "glb/reduce.h"
 
 #include <cstring>
@@ -6,6 +7,7 @@
 namespace glb {
 
 void reduce(ReduceOptions& opts) {
+  GLB_HOST_TRACE("glb::reduce");
   const auto& context = opts.context;
   GLB_ENFORCE(opts.out != nullptr, "reduce: output required (used as scratch on non-root ranks)");
   GLB_ENFORCE(opts.root >= 0 && opts.root < context->size, "reduce: invalid root ", opts.root);

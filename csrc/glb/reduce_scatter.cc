@@ -1,8 +1,10 @@
+#include "glb/common/trace.h"
 #include "glb/reduce_scatter.h"
 
 namespace glb {
 
 void reduce_scatter(ReduceScatterOptions& opts) {
+  GLB_HOST_TRACE("glb::reduce_scatter");
   const auto& context = opts.context;
   GLB_ENFORCE(opts.in != nullptr && opts.out != nullptr, "reduce_scatter: input and output required");
   GLB_ENFORCE(opts.elementSize > 0, "reduce_scatter: element size not set");

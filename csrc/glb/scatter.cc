@@ -1,8 +1,10 @@
+#include "glb/common/trace.h"
 #include "glb/scatter.h"
 
 namespace glb {
 
 void scatter(ScatterOptions& opts) {
+  GLB_HOST_TRACE("glb::scatter");
   const auto& context = opts.context;
   GLB_ENFORCE(opts.out != nullptr, "scatter: output required");
   GLB_ENFORCE(opts.root >= 0 && opts.root < context->size, "scatter: invalid root ", opts.root);

@@ -392,3 +392,35 @@ def test_metrics_snapshot_and_prometheus_endpoint():
     metrics.start_exporter(port)
     body = urllib.request.urlopen(f"http://127.0.0.1:{port}/metrics", timeout=10).read().decode()
     assert "glb_tcp_cma_bytes_total" in body and "glb_build_info" in body and 'cuda_arch=' in body
+
+
+def test_chrome_trace_of_collective_calls(tmp_path):
+    """GLB_TRACE_FILE: every collective call becomes a chrome-trace complete event (read at process exit)."""
+    import json
+    import subprocess
+    import sys
+
+    code = (
+        "import numpy as np, gloo_b200 as gb\n"
+        "assert gb._C.trace_enabled()\n"
+        "def fn(ctx):\n"
+        "    x = np.ones(1000, np.float32)\n"
+        "    for _ in range(3):\n"
+        "        gb.allreduce(ctx, x)\n"
+        "    gb.barrier(ctx)\n"
+        "    out = np.zeros(2000, np.float32)\n"
+        "    gb.allgather(ctx, out, np.ones(1000, np.float32))\n"
+        "    return True\n"
+        "assert all(gb.spawn_threads(2, fn))\n"
+        "print('flushed', gb._C.trace_flush())\n")
+    env = dict(os.environ, GLB_TRACE_FILE=str(tmp_path / "trace_%r.json"))
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=120)
+    assert r.returncode == 0, r.stderr[-2000:]
+    files = list(tmp_path.iterdir())
+    assert len(files) == 1 and files[0].name.startswith("trace_") and "%r" not in files[0].name
+    events = json.loads(files[0].read_text().rstrip().rstrip(",") + "]")
+    names = [e["name"] for e in events]
+    assert names.count("glb::allreduce") == 6 and "glb::allgather" in names and "glb::barrier" in names
+    assert all(e["ph"] == "X" and e["dur"] >= 0 and e["pid"] > 0 for e in events)
+    assert len({e["tid"] for e in events}) >= 2          # two rank threads
+    assert not gb._C.trace_enabled()                     # off in this process

@@ -169,7 +169,9 @@ def host_rows(name):
 w("## Host buffers over TCP loopback (BASELINE config 1; this CPU container, 8 shared vCPUs; `scripts/host_compare.sh`)\n")
 w("| benchmark | elements | reference p50 us | gloo_b200 p50 us | speed-up |")
 w("|---|---|---|---|---|")
-for label, f in (("allreduce_ring, 2 ranks", "host_compare_allreduce_ring_P2.txt"), ("allreduce_halving_doubling, 4 ranks", "host_compare_allreduce_hd_P4.txt")):
+for label, f in (("allreduce_ring, 2 ranks", "host_compare_allreduce_ring_P2.txt"), ("allreduce_halving_doubling, 4 ranks", "host_compare_allreduce_hd_P4.txt"),
+                 ("allreduce_bcube, 4 ranks", "host_compare_allreduce_bcube_P4.txt"), ("broadcast_one_to_all, 4 ranks", "host_compare_broadcast_one_to_all_P4.txt"),
+                 ("allgather_ring, 4 ranks", "host_compare_allgather_ring_P4.txt"), ("barrier_all_to_all, 4 ranks", "host_compare_barrier_all_to_all_P4.txt")):
     hr = host_rows(f)
     if not hr or "ref" not in hr or "ours" not in hr:
         continue
